@@ -1,0 +1,355 @@
+// Bandwidth-bound helpers: split-bf16 conversion, NCHW<->NHWC, stem im2col, max-pool,
+// relation-head row softmax.  All HBM-bound: 128-bit accesses, coalesced along C.
+#include <string.h>
+
+#include "common.cuh"
+
+thread_local int g_hvr_last_cuda_error = 0;
+std::atomic<uint64_t> g_hvr_launches{0};
+
+extern "C" const char* hvr_strerror(int code) {
+  switch (code) {
+    case HVR_OK: return "ok";
+    case HVR_ERR_ARG: return "bad argument";
+    case HVR_ERR_CUDA: return "CUDA call failed (see hvr_last_cuda_error)";
+    case HVR_ERR_WORKSPACE: return "workspace too small";
+    case HVR_ERR_UNSUPPORTED: return "unsupported on this device/driver";
+    default: return "unknown error";
+  }
+}
+extern "C" int hvr_last_cuda_error(void) { return g_hvr_last_cuda_error; }
+extern "C" int hvr_abi_version(void) { return 1; }
+extern "C" uint64_t hvr_launch_count(void) { return g_hvr_launches.load(); }
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+inline int ew_grid(size_t n, int per_thread = 1) {
+  size_t b = (n + (size_t)EW_THREADS * per_thread - 1) / ((size_t)EW_THREADS * per_thread);
+  const size_t cap = 148 * 32;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+__global__ void split_kernel(const float* __restrict__ x, size_t n, __nv_bfloat16* __restrict__ hi,
+                             __nv_bfloat16* __restrict__ lo) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) split2(x[i], hi[i], lo[i]);
+}
+__global__ void merge_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, size_t n,
+                             float* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = merge2(hi[i], lo[i]);
+}
+__global__ void split2d_kernel(const float* __restrict__ x, int rows, int cols, int ld_in,
+                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ld_out) {
+  const size_t total = (size_t)rows * ld_out;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int r = (int)(i / ld_out), c = (int)(i % ld_out);
+    const float v = c < cols ? x[(size_t)r * ld_in + c] : 0.f;
+    split2(v, hi[i], lo[i]);
+  }
+}
+
+// [B,C,HW] -> [B,HW,C] through a 32x33 shared tile (coalesced on both sides).
+template <bool SPLIT>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, int HW, float* __restrict__ of,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const float* xb = x + (size_t)b * C * HW;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, p = p0 + threadIdx.x;
+    t[j][threadIdx.x] = (c < C && p < HW) ? xb[(size_t)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int p = p0 + j, c = c0 + threadIdx.x;
+    if (p < HW && c < C) {
+      const size_t o = ((size_t)b * HW + p) * C + c;
+      const float v = t[threadIdx.x][j];
+      if (SPLIT) split2(v, hi[o], lo[o]);
+      else of[o] = v;
+    }
+  }
+}
+// [B,HW,C] -> [B,C,HW]
+template <bool SPLIT>
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ xf, const __nv_bfloat16* __restrict__ hi,
+                                    const __nv_bfloat16* __restrict__ lo, int C, int HW, float* __restrict__ out) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int p = p0 + j, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (p < HW && c < C) {
+      const size_t o = ((size_t)b * HW + p) * C + c;
+      v = SPLIT ? merge2(hi[o], lo[o]) : xf[o];
+    }
+    t[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  float* ob = out + (size_t)b * C * HW;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, p = p0 + threadIdx.x;
+    if (c < C && p < HW) ob[(size_t)c * HW + p] = t[threadIdx.x][j];
+  }
+}
+
+// Stem im2col: out[(b,oy,ox), k] with k = (r*7+s)*3 + c for the 7x7/2 pad-3 conv, 192 columns
+// (147 real + zero padding).  One thread per (pixel, 8-column group): 16-byte stores.
+__global__ void im2col_stem_kernel(const float* __restrict__ img, int B, int H, int W, int OH, int OW,
+                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const size_t total = (size_t)B * OH * OW * 24;  // 192 / 8 groups
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int g = (int)(i % 24);
+    const size_t pix = i / 24;
+    const int ox = (int)(pix % OW);
+    const int oy = (int)((pix / OW) % OH);
+    const int b = (int)(pix / ((size_t)OW * OH));
+    uint32_t hp[4], lp[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      unsigned short hs[2], ls[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = g * 8 + j + e;
+        float v = 0.f;
+        if (k < 147) {
+          const int c = k % 3, rs = k / 3;
+          const int s = rs % 7, r = rs / 7;
+          const int iy = oy * 2 - 3 + r, ix = ox * 2 - 3 + s;
+          if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + (((size_t)b * 3 + c) * H + iy) * W + ix);
+        }
+        __nv_bfloat16 h, l;
+        split2(v, h, l);
+        hs[e] = __bfloat16_as_ushort(h);
+        ls[e] = __bfloat16_as_ushort(l);
+      }
+      hp[j / 2] = (uint32_t)hs[0] | ((uint32_t)hs[1] << 16);
+      lp[j / 2] = (uint32_t)ls[0] | ((uint32_t)ls[1] << 16);
+    }
+    const size_t o = pix * 192 + (size_t)g * 8;
+    *reinterpret_cast<uint4*>(hi + o) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+    *reinterpret_cast<uint4*>(lo + o) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+  }
+}
+
+// 3x3 stride-2 pad-1 max-pool on split NHWC, 8 channels per thread.
+__global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int B,
+                               int H, int W, int C, __nv_bfloat16* __restrict__ ohi, __nv_bfloat16* __restrict__ olo,
+                               int OH, int OW) {
+  const int cg = C / 8;
+  const size_t total = (size_t)B * OH * OW * cg;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int g = (int)(i % cg);
+    const size_t pix = i / cg;
+    const int ox = (int)(pix % OW);
+    const int oy = (int)((pix / OW) % OH);
+    const int b = (int)(pix / ((size_t)OW * OH));
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+    for (int r = 0; r < 3; ++r) {
+      const int iy = oy * 2 - 1 + r;
+      if (iy < 0 || iy >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int ix = ox * 2 - 1 + s;
+        if (ix < 0 || ix >= W) continue;
+        const size_t o = (((size_t)b * H + iy) * W + ix) * C + (size_t)g * 8;
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + o));
+        const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + o));
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          m[2 * q] = fmaxf(m[2 * q], __fadd_rn(bf16bits_to_f32(hw[q] & 0xFFFFu), bf16bits_to_f32(lw[q] & 0xFFFFu)));
+          m[2 * q + 1] = fmaxf(m[2 * q + 1], __fadd_rn(bf16bits_to_f32(hw[q] >> 16), bf16bits_to_f32(lw[q] >> 16)));
+        }
+      }
+    }
+    uint32_t hp[4], lp[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split2(m[2 * q], h0, l0);
+      split2(m[2 * q + 1], h1, l1);
+      hp[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      lp[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    const size_t o = pix * C + (size_t)g * 8;
+    *reinterpret_cast<uint4*>(ohi + o) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+    *reinterpret_cast<uint4*>(olo + o) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+  }
+}
+
+// Row softmax, one CTA per row, row cached in registers (cols <= 256*32 = 8192) or re-read.
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+constexpr int SM_THREADS = 256;
+constexpr int SM_PER = 32;  // register-cached elements per thread
+__global__ void __launch_bounds__(SM_THREADS) softmax_rows_kernel(const float* __restrict__ S, int cols, long long ld_s,
+                                                                  __nv_bfloat16* __restrict__ phi,
+                                                                  __nv_bfloat16* __restrict__ plo, long long ld_p) {
+  __shared__ float red[SM_THREADS / 32];
+  __shared__ float bcast;
+  const int row = blockIdx.x;
+  const float* s = S + (size_t)row * ld_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  float v[SM_PER];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < SM_PER; ++j) {
+    const int c = tid + j * SM_THREADS;
+    v[j] = c < cols ? __ldg(s + c) : -INFINITY;
+    mx = fmaxf(mx, v[j]);
+  }
+  for (int c = tid + SM_PER * SM_THREADS; c < cols; c += SM_THREADS) mx = fmaxf(mx, __ldg(s + c));
+  mx = warp_max(mx);
+  if (lane == 0) red[wid] = mx;
+  __syncthreads();
+  if (wid == 0) {
+    float t = lane < SM_THREADS / 32 ? red[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) bcast = t;
+  }
+  __syncthreads();
+  mx = bcast;
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < SM_PER; ++j) {
+    const int c = tid + j * SM_THREADS;
+    v[j] = c < cols ? expf(v[j] - mx) : 0.f;
+    sum += v[j];
+  }
+  for (int c = tid + SM_PER * SM_THREADS; c < cols; c += SM_THREADS) sum += expf(__ldg(s + c) - mx);
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) red[wid] = sum;
+  __syncthreads();
+  if (wid == 0) {
+    float t = lane < SM_THREADS / 32 ? red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) bcast = t;
+  }
+  __syncthreads();
+  const float inv = 1.0f / bcast;
+  __nv_bfloat16* ph = phi + (size_t)row * ld_p;
+  __nv_bfloat16* pl = plo + (size_t)row * ld_p;
+#pragma unroll
+  for (int j = 0; j < SM_PER; ++j) {
+    const int c = tid + j * SM_THREADS;
+    if (c < ld_p) {
+      __nv_bfloat16 h, l;
+      split2(c < cols ? v[j] * inv : 0.f, h, l);
+      ph[c] = h;
+      pl[c] = l;
+    }
+  }
+  for (int c = tid + SM_PER * SM_THREADS; c < ld_p; c += SM_THREADS) {
+    __nv_bfloat16 h, l;
+    split2(c < cols ? expf(__ldg(s + c) - mx) * inv : 0.f, h, l);
+    ph[c] = h;
+    pl[c] = l;
+  }
+}
+
+}  // namespace
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int hvr_split_f32(const float* x, size_t n, hvr_bf16* hi, hvr_bf16* lo, void* stream) {
+  if (!x || !hi || !lo) return HVR_ERR_ARG;
+  if (n == 0) return HVR_OK;
+  split_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST(stream)>>>(x, n, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  HVR_LAUNCHED();
+  return HVR_OK;
+}
+extern "C" int hvr_merge_f32(const hvr_bf16* hi, const hvr_bf16* lo, size_t n, float* out, void* stream) {
+  if (!out || !hi || !lo) return HVR_ERR_ARG;
+  if (n == 0) return HVR_OK;
+  merge_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST(stream)>>>((const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo, n,
+                                                              out);
+  HVR_LAUNCHED();
+  return HVR_OK;
+}
+extern "C" int hvr_split_f32_2d(const float* x, int rows, int cols, int ld_in, hvr_bf16* hi, hvr_bf16* lo,
+                                int ld_out, void* stream) {
+  if (!x || !hi || !lo || cols > ld_out || cols > ld_in) return HVR_ERR_ARG;
+  if (rows == 0) return HVR_OK;
+  split2d_kernel<<<ew_grid((size_t)rows * ld_out, 4), EW_THREADS, 0, ST(stream)>>>(
+      x, rows, cols, ld_in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld_out);
+  HVR_LAUNCHED();
+  return HVR_OK;
+}
+extern "C" int hvr_nchw_to_nhwc_split(const float* x, int B, int C, int H, int W, hvr_bf16* hi, hvr_bf16* lo,
+                                      void* stream) {
+  if (!x || !hi || !lo || B < 1 || B > 65535) return HVR_ERR_ARG;
+  dim3 grid(hvr_cdiv(H * W, 32), hvr_cdiv(C, 32), B), block(32, 8);
+  nchw_to_nhwc_kernel<true><<<grid, block, 0, ST(stream)>>>(x, C, H * W, nullptr, (__nv_bfloat16*)hi,
+                                                            (__nv_bfloat16*)lo);
+  HVR_LAUNCHED();
+  return HVR_OK;
+}
+extern "C" int hvr_nchw_to_nhwc_f32(const float* x, int B, int C, int H, int W, float* out, void* stream) {
+  if (!x || !out || B < 1 || B > 65535) return HVR_ERR_ARG;
+  dim3 grid(hvr_cdiv(H * W, 32), hvr_cdiv(C, 32), B), block(32, 8);
+  nchw_to_nhwc_kernel<false><<<grid, block, 0, ST(stream)>>>(x, C, H * W, out, nullptr, nullptr);
+  HVR_LAUNCHED();
+  return HVR_OK;
+}
+extern "C" int hvr_nhwc_split_to_nchw(const hvr_bf16* hi, const hvr_bf16* lo, int B, int C, int H, int W,
+                                      float* out, void* stream) {
+  if (!out || !hi || !lo || B < 1 || B > 65535) return HVR_ERR_ARG;
+  dim3 grid(hvr_cdiv(H * W, 32), hvr_cdiv(C, 32), B), block(32, 8);
+  nhwc_to_nchw_kernel<true><<<grid, block, 0, ST(stream)>>>(nullptr, (const __nv_bfloat16*)hi,
+                                                            (const __nv_bfloat16*)lo, C, H * W, out);
+  HVR_LAUNCHED();
+  return HVR_OK;
+}
+extern "C" int hvr_nhwc_to_nchw_f32(const float* x, int B, int C, int H, int W, float* out, void* stream) {
+  if (!out || !x || B < 1 || B > 65535) return HVR_ERR_ARG;
+  dim3 grid(hvr_cdiv(H * W, 32), hvr_cdiv(C, 32), B), block(32, 8);
+  nhwc_to_nchw_kernel<false><<<grid, block, 0, ST(stream)>>>(x, nullptr, nullptr, C, H * W, out);
+  HVR_LAUNCHED();
+  return HVR_OK;
+}
+extern "C" int hvr_im2col_stem(const float* img, int B, int H, int W, hvr_bf16* hi, hvr_bf16* lo, int out_h,
+                               int out_w, void* stream) {
+  if (!img || !hi || !lo) return HVR_ERR_ARG;
+  if (out_h != (H + 6 - 7) / 2 + 1 || out_w != (W + 6 - 7) / 2 + 1) return HVR_ERR_ARG;
+  im2col_stem_kernel<<<ew_grid((size_t)B * out_h * out_w * 24), EW_THREADS, 0, ST(stream)>>>(
+      img, B, H, W, out_h, out_w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  HVR_LAUNCHED();
+  return HVR_OK;
+}
+extern "C" int hvr_maxpool3x3s2_split(const hvr_bf16* hi, const hvr_bf16* lo, int B, int H, int W, int C,
+                                      hvr_bf16* ohi, hvr_bf16* olo, int out_h, int out_w, void* stream) {
+  if (!hi || !lo || !ohi || !olo || C % 8 != 0) return HVR_ERR_ARG;
+  if (out_h != (H + 2 - 3) / 2 + 1 || out_w != (W + 2 - 3) / 2 + 1) return HVR_ERR_ARG;
+  maxpool_kernel<<<ew_grid((size_t)B * out_h * out_w * (C / 8)), EW_THREADS, 0, ST(stream)>>>(
+      (const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo, B, H, W, C, (__nv_bfloat16*)ohi, (__nv_bfloat16*)olo, out_h,
+      out_w);
+  HVR_LAUNCHED();
+  return HVR_OK;
+}
+extern "C" int hvr_softmax_rows_split(const float* S, int rows, int cols, int64_t ld_s, hvr_bf16* p_hi,
+                                      hvr_bf16* p_lo, int64_t ld_p, void* stream) {
+  if (!S || !p_hi || !p_lo || cols < 1 || cols > ld_s || cols > ld_p) return HVR_ERR_ARG;
+  if (rows == 0) return HVR_OK;
+  softmax_rows_kernel<<<rows, SM_THREADS, 0, ST(stream)>>>(S, cols, ld_s, (__nv_bfloat16*)p_hi,
+                                                           (__nv_bfloat16*)p_lo, ld_p);
+  HVR_LAUNCHED();
+  return HVR_OK;
+}

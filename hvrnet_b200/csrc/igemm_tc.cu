@@ -1,0 +1,502 @@
+// Implicit GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulator in TMEM,
+// operands staged by TMA into 128B-swizzled shared memory), with a split-bf16 (hi/lo)
+// three-product evaluation that keeps ~fp32 accuracy:  A*B ~= Ah*Bh + Ah*Bl + Al*Bh.
+//
+// Replaces the cuDNN/cuBLAS calls behind nn.Conv2d / nn.Linear / torch.bmm / torch.mm on
+// the reference hot path (resnet.py:222-257, res_layer.py:67-74, rpn_head.py:30-35,
+// hrnmp_bbox_head.py:283-294,342-350,827-906).  See include/hvr_b200.h (HvrIGemm).
+//
+// One CTA = one 128 x BN output tile.  6 warps:
+//   warp 0    TMA producer (one lane): per K step loads A_hi, A_lo (4-D box = tile_w x tile_h
+//             pixels x 64 channels at the tap's offset; out-of-range pixels arrive as zeros =
+//             conv padding) and B_hi, B_lo (BN x 64) into a STAGES-deep ring
+//   warp 1    TMEM allocator + MMA issuer (one lane): 4 x UMMA_K=16 per 64-wide K step, three
+//             products per step, tcgen05.commit frees the stage / signals the epilogue
+//   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns -> alpha, bias, residual, ReLU ->
+//             split-bf16 / fp32 / transposed stores
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_BYTES = BM * BK * 2;
+
+struct alignas(64) KParams {
+  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+  int ntaps;
+  int tap_dx[9], tap_dy[9];
+  int C, cblocks;
+  int tile_w, tile_h, tiles_x, tiles_y;
+  int out_w, out_h, batch;
+  int n;
+  int passes;
+  int relu;
+  float alpha;
+  const float* bias;
+  const __nv_bfloat16* res_hi;
+  const __nv_bfloat16* res_lo;
+  long long ld_res;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  long long ld_out;
+  float* out_f32;
+  long long ld_f32;
+  __nv_bfloat16* outT_hi;
+  __nv_bfloat16* outT_lo;
+  long long ld_outT;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (BN == 64) ? 4 : (BN == 128 ? 3 : 2);
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// Epilogue for 32 consecutive columns of one output row.
+__device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t (&acc)[32], long long row,
+                                               int n_base, bool row_ok) {
+  if (!row_ok) return;
+  const int n_left = p.n - n_base;
+  if (n_left <= 0) return;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * p.alpha;
+  const bool full = n_left >= 32;
+  if (p.bias) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + j));
+        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < n_left) v[j] += __ldg(p.bias + n_base + j);
+    }
+  }
+  if (p.res_hi) {
+    const __nv_bfloat16* rh = p.res_hi + row * p.ld_res + n_base;
+    const __nv_bfloat16* rl = p.res_lo + row * p.ld_res + n_base;
+    if (full && (p.ld_res % 8 == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(rh + j));
+        const uint4 l = __ldg(reinterpret_cast<const uint4*>(rl + j));
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+        const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          v[j + 2 * q] += __fadd_rn(bf16bits_to_f32(hw[q] & 0xFFFFu), bf16bits_to_f32(lw[q] & 0xFFFFu));
+          v[j + 2 * q + 1] += __fadd_rn(bf16bits_to_f32(hw[q] >> 16), bf16bits_to_f32(lw[q] >> 16));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < n_left) v[j] += merge2(rh[j], rl[j]);
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
+  if (p.out_f32) {
+    float* o = p.out_f32 + row * p.ld_f32 + n_base;
+    if (full && (p.ld_f32 % 4 == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < n_left) o[j] = v[j];
+    }
+  }
+  if (p.out_hi || p.outT_hi) {
+    uint32_t hp[16], lp[16];  // packed pairs
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split2(v[j], h0, l0);
+      split2(v[j + 1], h1, l1);
+      hp[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      lp[j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    if (p.out_hi) {
+      __nv_bfloat16* oh = p.out_hi + row * p.ld_out + n_base;
+      __nv_bfloat16* ol = p.out_lo + row * p.ld_out + n_base;
+      if (full && (p.ld_out % 8 == 0)) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          *reinterpret_cast<uint4*>(oh + 2 * j) = make_uint4(hp[j], hp[j + 1], hp[j + 2], hp[j + 3]);
+          *reinterpret_cast<uint4*>(ol + 2 * j) = make_uint4(lp[j], lp[j + 1], lp[j + 2], lp[j + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < n_left) {
+            oh[j] = __ushort_as_bfloat16((unsigned short)((hp[j / 2] >> (16 * (j & 1))) & 0xFFFFu));
+            ol[j] = __ushort_as_bfloat16((unsigned short)((lp[j / 2] >> (16 * (j & 1))) & 0xFFFFu));
+          }
+      }
+    }
+    if (p.outT_hi) {
+      // transposed: element (n, row); consecutive lanes hold consecutive rows -> coalesced
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < n_left) {
+          const long long o = (long long)(n_base + j) * p.ld_outT + row;
+          p.outT_hi[o] = __ushort_as_bfloat16((unsigned short)((hp[j / 2] >> (16 * (j & 1))) & 0xFFFFu));
+          p.outT_lo[o] = __ushort_as_bfloat16((unsigned short)((lp[j / 2] >> (16 * (j & 1))) & 0xFFFFu));
+        }
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant__ KParams p) {
+  using C_ = Cfg<BN>;
+  constexpr int STAGES = C_::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment of the tile ring (SWIZZLE_128B atoms are 1024 B)
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* tiles = smem_raw + pad;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + STAGES * C_::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tile = blockIdx.x;
+  const int tx = m_tile % p.tiles_x;
+  const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+  const int bimg = m_tile / (p.tiles_x * p.tiles_y);
+  const int x0 = tx * p.tile_w;
+  const int y0 = ty * p.tile_h;
+  const int n0 = blockIdx.y * BN;
+  const int total_k = p.ntaps * p.cblocks;
+  const bool three = p.passes >= 3;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA_hi);
+    tma_prefetch_desc(&p.tmB_hi);
+    if (three) {
+      tma_prefetch_desc(&p.tmA_lo);
+      tma_prefetch_desc(&p.tmB_lo);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const uint32_t stage_tx = three ? (uint32_t)C_::STAGE_BYTES : (uint32_t)(A_BYTES + C_::B_BYTES);
+      int it = 0;
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        const int ax = x0 + p.tap_dx[tap];
+        const int ay = y0 + p.tap_dy[tap];
+        for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* st = tiles + s * C_::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], stage_tx);
+          const int kc = cb * BK;
+          tma_load_4d(st, &p.tmA_hi, &full_bar[s], kc, ax, ay, bimg);
+          tma_load_2d(st + 2 * A_BYTES, &p.tmB_hi, &full_bar[s], tap * p.C + kc, n0);
+          if (three) {
+            tma_load_4d(st + A_BYTES, &p.tmA_lo, &full_bar[s], kc, ax, ay, bimg);
+            tma_load_2d(st + 2 * A_BYTES + C_::B_BYTES, &p.tmB_lo, &full_bar[s], tap * p.C + kc, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = umma_idesc_bf16(BN);
+    for (int it = 0; it < total_k; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = smem_u32(tiles + s * C_::STAGE_BYTES);
+        const uint64_t a_hi = umma_desc_k_sw128(st);
+        const uint64_t a_lo = umma_desc_k_sw128(st + A_BYTES);
+        const uint64_t b_hi = umma_desc_k_sw128(st + 2 * A_BYTES);
+        const uint64_t b_lo = umma_desc_k_sw128(st + 2 * A_BYTES + C_::B_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advancing 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in the (addr>>4) field
+          const uint64_t ko = (uint64_t)(k * 2);
+          tc_mma_f16(tmem_base, a_hi + ko, b_hi + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          if (three) {
+            tc_mma_f16(tmem_base, a_hi + ko, b_lo + ko, idesc, 1u);
+            tc_mma_f16(tmem_base, a_lo + ko, b_hi + ko, idesc, 1u);
+          }
+        }
+        tc_commit(&empty_bar[s]);                       // frees the stage when the MMAs retire
+        if (it == total_k - 1) tc_commit(tmem_full_bar);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================= epilogue =================
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int m = q * 32 + lane;
+    const int px = x0 + m % p.tile_w;
+    const int py = y0 + m / p.tile_w;
+    const bool row_ok = (px < p.out_w) && (py < p.out_h);
+    const long long row = ((long long)bimg * p.out_h + py) * p.out_w + px;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t acc[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+      tmem_ld_wait();
+      epilogue_chunk(p, acc, row, n0 + c0, row_ok);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+// ------------------------------------------------------------------------------------
+// fp32 SIMT evaluation of the same descriptor (cross-check).
+// ------------------------------------------------------------------------------------
+__global__ void igemm_check_kernel(HvrIGemm g, long long rows) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * g.n) return;
+  const int n = (int)(idx % g.n);
+  const long long row = idx / g.n;
+  const int x = (int)(row % g.out_w);
+  const int y = (int)((row / g.out_w) % g.out_h);
+  const int b = (int)(row / ((long long)g.out_w * g.out_h));
+  const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(g.a_hi);
+  const __nv_bfloat16* al = reinterpret_cast<const __nv_bfloat16*>(g.a_lo);
+  const __nv_bfloat16* bh = reinterpret_cast<const __nv_bfloat16*>(g.b_hi);
+  const __nv_bfloat16* bl = reinterpret_cast<const __nv_bfloat16*>(g.b_lo);
+  float acc = 0.f;
+  for (int t = 0; t < g.ntaps; ++t) {
+    const int ax = x + g.tap_dx[t], ay = y + g.tap_dy[t];
+    if (ax < 0 || ax >= g.a_w || ay < 0 || ay >= g.a_h) continue;
+    const long long ao = b * g.a_stride_b + ay * g.a_stride_h + ax * g.a_stride_w;
+    const long long bo = (long long)n * g.ldb + (long long)t * g.a_c;
+    for (int c = 0; c < g.a_c; ++c) {
+      float a = __bfloat162float(ah[ao + c]);
+      float w = __bfloat162float(bh[bo + c]);
+      if (g.passes >= 3) {
+        a = __fadd_rn(a, __bfloat162float(al[ao + c]));
+        w = __fadd_rn(w, __bfloat162float(bl[bo + c]));
+      }
+      acc = fmaf(a, w, acc);
+    }
+  }
+  float v = acc * g.alpha;
+  if (g.bias) v += g.bias[n];
+  if (g.res_hi)
+    v += merge2(reinterpret_cast<const __nv_bfloat16*>(g.res_hi)[row * g.ld_res + n],
+                reinterpret_cast<const __nv_bfloat16*>(g.res_lo)[row * g.ld_res + n]);
+  if (g.relu) v = fmaxf(v, 0.f);
+  if (g.out_f32) g.out_f32[row * g.ld_f32 + n] = v;
+  __nv_bfloat16 h, l;
+  split2(v, h, l);
+  if (g.out_hi) {
+    reinterpret_cast<__nv_bfloat16*>(g.out_hi)[row * g.ld_out + n] = h;
+    reinterpret_cast<__nv_bfloat16*>(g.out_lo)[row * g.ld_out + n] = l;
+  }
+  if (g.outT_hi) {
+    reinterpret_cast<__nv_bfloat16*>(g.outT_hi)[(long long)n * g.ld_outT + row] = h;
+    reinterpret_cast<__nv_bfloat16*>(g.outT_lo)[(long long)n * g.ld_outT + row] = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Host: tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point, so the
+// library links against cudart only), cached by geometry + pointer.
+// ------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
+  });
+  return fn;
+}
+
+using MapKey = std::tuple<const void*, int, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t,
+                          uint32_t, uint32_t, uint32_t>;
+std::map<MapKey, CUtensorMap> g_map_cache;
+std::mutex g_map_mutex;
+
+int make_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+             const uint32_t* box) {
+  MapKey key{ptr, rank, dims[0], dims[1], rank > 2 ? dims[2] : 0, rank > 3 ? dims[3] : 0,
+             strides_bytes[0], rank > 2 ? strides_bytes[1] : 0, rank > 3 ? strides_bytes[2] : 0,
+             box[0], box[1], rank > 2 ? box[2] : 0};
+  {
+    std::lock_guard<std::mutex> lk(g_map_mutex);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) {
+      *out = it->second;
+      return HVR_OK;
+    }
+  }
+  auto enc = get_encode();
+  if (!enc) return HVR_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0) return HVR_ERR_ARG;
+  for (int i = 0; i < rank - 1; ++i)
+    if (strides_bytes[i] % 16 != 0) return HVR_ERR_ARG;
+  cuuint64_t gdim[4];
+  cuuint64_t gstr[3];
+  cuuint32_t bx[4], es[4];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstr, bx,
+                   es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_hvr_last_cuda_error = 100000 + (int)r;
+    return HVR_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> lk(g_map_mutex);
+  if (g_map_cache.size() > 8192) g_map_cache.clear();
+  g_map_cache[key] = *out;
+  return HVR_OK;
+}
+
+int validate(const HvrIGemm* g) {
+  if (!g || !g->a_hi || !g->b_hi) return HVR_ERR_ARG;
+  if (g->passes >= 3 && (!g->a_lo || !g->b_lo)) return HVR_ERR_ARG;
+  if (g->ntaps < 1 || g->ntaps > 9) return HVR_ERR_ARG;
+  if (g->tile_w * g->tile_h != BM || g->tile_w > 256 || g->tile_h > 256) return HVR_ERR_ARG;
+  if (g->a_c < 1 || g->n < 1 || g->out_w < 1 || g->out_h < 1 || g->batch < 1) return HVR_ERR_ARG;
+  if (g->a_c % 8 != 0 && g->ntaps > 1) return HVR_ERR_ARG;
+  if ((g->out_hi == nullptr) != (g->out_lo == nullptr)) return HVR_ERR_ARG;
+  if ((g->outT_hi == nullptr) != (g->outT_lo == nullptr)) return HVR_ERR_ARG;
+  if ((g->res_hi == nullptr) != (g->res_lo == nullptr)) return HVR_ERR_ARG;
+  if (!g->out_hi && !g->out_f32 && !g->outT_hi) return HVR_ERR_ARG;
+  return HVR_OK;
+}
+
+template <int BN>
+int launch(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    HVR_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+    attr_set = true;
+  }
+  const uint64_t ktot = (uint64_t)g->ntaps * g->a_c;
+  const uint64_t bdims[2] = {ktot, (uint64_t)g->n};
+  const uint64_t bstr[1] = {(uint64_t)g->ldb * 2};
+  const uint32_t bbox[2] = {BK, BN};
+  int rc = make_map(&kp.tmB_hi, g->b_hi, 2, bdims, bstr, bbox);
+  if (rc) return rc;
+  if (g->passes >= 3) {
+    rc = make_map(&kp.tmB_lo, g->b_lo, 2, bdims, bstr, bbox);
+    if (rc) return rc;
+  }
+  dim3 grid(kp.tiles_x * kp.tiles_y * kp.batch, hvr_cdiv(g->n, BN));
+  igemm_tc_kernel<BN><<<grid, 192, Cfg<BN>::SMEM, st>>>(kp);
+  HVR_LAUNCHED();
+  return HVR_OK;
+}
+
+}  // namespace
+
+extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
+  int rc = validate(g);
+  if (rc) return rc;
+  KParams kp;
+  memset(&kp, 0, sizeof(kp));
+  const uint64_t adims[4] = {(uint64_t)g->a_c, (uint64_t)g->a_w, (uint64_t)g->a_h, (uint64_t)g->a_b};
+  const uint64_t astr[3] = {(uint64_t)g->a_stride_w * 2, (uint64_t)g->a_stride_h * 2, (uint64_t)g->a_stride_b * 2};
+  const uint32_t abox[4] = {BK, (uint32_t)g->tile_w, (uint32_t)g->tile_h, 1};
+  rc = make_map(&kp.tmA_hi, g->a_hi, 4, adims, astr, abox);
+  if (rc) return rc;
+  if (g->passes >= 3) {
+    rc = make_map(&kp.tmA_lo, g->a_lo, 4, adims, astr, abox);
+    if (rc) return rc;
+  }
+  kp.ntaps = g->ntaps;
+  for (int i = 0; i < 9; ++i) {
+    kp.tap_dx[i] = g->tap_dx[i];
+    kp.tap_dy[i] = g->tap_dy[i];
+  }
+  kp.C = g->a_c;
+  kp.cblocks = hvr_cdiv(g->a_c, BK);
+  kp.tile_w = g->tile_w;
+  kp.tile_h = g->tile_h;
+  kp.tiles_x = hvr_cdiv(g->out_w, g->tile_w);
+  kp.tiles_y = hvr_cdiv(g->out_h, g->tile_h);
+  kp.out_w = g->out_w;
+  kp.out_h = g->out_h;
+  kp.batch = g->batch;
+  kp.n = g->n;
+  kp.passes = g->passes >= 3 ? 3 : 1;
+  kp.relu = g->relu;
+  kp.alpha = g->alpha;
+  kp.bias = g->bias;
+  kp.res_hi = reinterpret_cast<const __nv_bfloat16*>(g->res_hi);
+  kp.res_lo = reinterpret_cast<const __nv_bfloat16*>(g->res_lo);
+  kp.ld_res = g->ld_res;
+  kp.out_hi = reinterpret_cast<__nv_bfloat16*>(g->out_hi);
+  kp.out_lo = reinterpret_cast<__nv_bfloat16*>(g->out_lo);
+  kp.ld_out = g->ld_out;
+  kp.out_f32 = g->out_f32;
+  kp.ld_f32 = g->ld_f32;
+  kp.outT_hi = reinterpret_cast<__nv_bfloat16*>(g->outT_hi);
+  kp.outT_lo = reinterpret_cast<__nv_bfloat16*>(g->outT_lo);
+  kp.ld_outT = g->ld_outT;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (g->n <= 64) return launch<64>(g, kp, st);
+  return launch<128>(g, kp, st);
+}
+
+extern "C" int hvr_igemm_check(const HvrIGemm* g, void* stream) {
+  int rc = validate(g);
+  if (rc) return rc;
+  const long long rows = (long long)g->batch * g->out_h * g->out_w;
+  const long long total = rows * g->n;
+  igemm_check_kernel<<<hvr_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*g, rows);
+  HVR_LAUNCHED();
+  return HVR_OK;
+}

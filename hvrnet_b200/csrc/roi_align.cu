@@ -1,0 +1,248 @@
+// RoIAlign forward for sm_100a: a coalesced, 128-bit-vectorised HBM gather over an NHWC
+// feature map with the bilinear taps of one RoI staged in shared memory.
+//
+// Replaces ROIAlignForward / bilinear_interpolate (mmdet/ops/roi_align/src/
+// roi_align_kernel.cu:16-118) and its launcher (:120-141), which use one thread per output
+// element and 16 scalar gathers per output.  Arithmetic contract (bit-exact with
+// oracle/c/hvr_oracle.c, which restates the reference in strict IEEE fp32): every product
+// and sum is rounded separately (this file is compiled with -fmad=false), sample order
+// iy-outer / ix-inner, w1*lt + w2*rt + w3*lb + w4*rb left to right, divide by the sample
+// count last.
+//
+// Layout of the work: one CTA per RoI.
+//   phase 1  ph*pw*sn*sn threads compute (tap offsets, weights) of every sample once
+//            -> shared memory (the reference recomputes them for each of the C channels)
+//   phase 2  NHWC out: thread = (bin, 4-channel group): 16 x LDG.128 of contiguous channel
+//            rows, 1 x STG.128 (+ optional split-bf16 copy feeding fc_new_1)
+//            NCHW out (reference layout): thread = (bin, channel), lanes along C so loads
+//            stay coalesced; the [C, ph*pw] tile is transposed through shared memory and
+//            leaves as one contiguous, fully coalesced block.
+#include "common.cuh"
+
+namespace {
+
+struct Tap {
+  int o0, o1, o2, o3;      // element offsets (pixel index * C) of lt, rt, lb, rb
+  float w1, w2, w3, w4;
+};
+
+// roi_align_kernel.cu:16-61 -> offsets and weights instead of values.
+__device__ __forceinline__ Tap make_tap(float y, float x, int H, int W, int C) {
+  Tap t;
+  if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) {
+    t.o0 = t.o1 = t.o2 = t.o3 = -1;
+    t.w1 = t.w2 = t.w3 = t.w4 = 0.f;
+    return t;
+  }
+  if (y <= 0) y = 0;
+  if (x <= 0) x = 0;
+  int yl = (int)y, xl = (int)x, yh, xh;
+  if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else { yh = yl + 1; }
+  if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else { xh = xl + 1; }
+  const float ly = y - (float)yl, lx = x - (float)xl;
+  const float hy = 1.0f - ly, hx = 1.0f - lx;
+  t.o0 = (yl * W + xl) * C;
+  t.o1 = (yl * W + xh) * C;
+  t.o2 = (yh * W + xl) * C;
+  t.o3 = (yh * W + xh) * C;
+  t.w1 = hy * hx; t.w2 = hy * lx; t.w3 = ly * hx; t.w4 = ly * lx;
+  return t;
+}
+
+struct RoiGeom {
+  float sw, sh, bw, bh;
+  int b;
+};
+__device__ __forceinline__ RoiGeom roi_geom(const float* __restrict__ r, float scale, int ph, int pw, int n_imgs) {
+  RoiGeom g;
+  int b = (int)r[0];
+  g.b = b < 0 ? 0 : (b >= n_imgs ? n_imgs - 1 : b);
+  g.sw = r[1] * scale;
+  g.sh = r[2] * scale;
+  const float ew = (r[3] + 1.0f) * scale, eh = (r[4] + 1.0f) * scale;
+  const float rw = fmaxf(ew - g.sw, 0.0f), rh = fmaxf(eh - g.sh, 0.0f);
+  g.bh = rh / (float)ph;
+  g.bw = rw / (float)pw;
+  return g;
+}
+
+template <bool NCHW_OUT>
+__global__ void __launch_bounds__(256) roi_align_kernel(const float* __restrict__ feat, const float* __restrict__ rois,
+                                                        int n_imgs, int C, int H, int W, int ph, int pw, float scale,
+                                                        int sn, float* __restrict__ out,
+                                                        __nv_bfloat16* __restrict__ out_hi,
+                                                        __nv_bfloat16* __restrict__ out_lo, long long ld_split) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int nbins = ph * pw;
+  const int ns = sn * sn;
+  Tap* taps = reinterpret_cast<Tap*>(smem);                          // [nbins*ns]
+  float* tile = reinterpret_cast<float*>(smem + (size_t)nbins * ns * sizeof(Tap));  // NCHW_OUT: [cchunk][nbins]
+  const int roi = blockIdx.x;
+  const RoiGeom g = roi_geom(rois + (size_t)roi * 5, scale, ph, pw, n_imgs);
+
+  for (int i = threadIdx.x; i < nbins * ns; i += blockDim.x) {
+    const int s = i % ns, bin = i / ns;
+    const int ix = s % sn, iy = s / sn;
+    const int q = bin % pw, p = bin / pw;
+    const float y = g.sh + (float)p * g.bh + ((float)iy + 0.5f) * g.bh / (float)sn;
+    const float x = g.sw + (float)q * g.bw + ((float)ix + 0.5f) * g.bw / (float)sn;
+    taps[i] = make_tap(y, x, H, W, C);
+  }
+  __syncthreads();
+  const float* fm = feat + (size_t)g.b * H * W * C;
+  const float cnt = (float)ns;
+
+  if (!NCHW_OUT) {
+    const int cg = C >> 2;  // float4 groups
+    const int total = nbins * cg;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int c4 = i % cg, bin = i / cg;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const Tap* tp = taps + bin * ns;
+      for (int s = 0; s < ns; ++s) {
+        const Tap t = tp[s];
+        if (t.o0 < 0) continue;  // bilinear_interpolate returned 0: acc + 0 == acc
+        const float4 a = __ldg(reinterpret_cast<const float4*>(fm + t.o0) + c4);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(fm + t.o1) + c4);
+        const float4 c = __ldg(reinterpret_cast<const float4*>(fm + t.o2) + c4);
+        const float4 d = __ldg(reinterpret_cast<const float4*>(fm + t.o3) + c4);
+        acc.x = acc.x + (((t.w1 * a.x + t.w2 * b.x) + t.w3 * c.x) + t.w4 * d.x);
+        acc.y = acc.y + (((t.w1 * a.y + t.w2 * b.y) + t.w3 * c.y) + t.w4 * d.y);
+        acc.z = acc.z + (((t.w1 * a.z + t.w2 * b.z) + t.w3 * c.z) + t.w4 * d.z);
+        acc.w = acc.w + (((t.w1 * a.w + t.w2 * b.w) + t.w3 * c.w) + t.w4 * d.w);
+      }
+      acc.x = acc.x / cnt; acc.y = acc.y / cnt; acc.z = acc.z / cnt; acc.w = acc.w / cnt;
+      if (out) *(reinterpret_cast<float4*>(out + ((size_t)roi * nbins + bin) * C) + c4) = acc;
+      if (out_hi) {
+        __nv_bfloat16 h[4], l[4];
+        split2(acc.x, h[0], l[0]); split2(acc.y, h[1], l[1]);
+        split2(acc.z, h[2], l[2]); split2(acc.w, h[3], l[3]);
+        const size_t o = (size_t)roi * ld_split + (size_t)bin * C + (size_t)c4 * 4;
+        uint2 hv, lv;
+        hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+        hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+        lv.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+        lv.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+        *reinterpret_cast<uint2*>(out_hi + o) = hv;
+        *reinterpret_cast<uint2*>(out_lo + o) = lv;
+      }
+    }
+  } else {
+    // channel chunks of blockDim.x: lanes along C (coalesced 128 B rows), tile transposed in smem
+    const int cchunk = blockDim.x;
+    for (int cbase = 0; cbase < C; cbase += cchunk) {
+      const int c = cbase + threadIdx.x;
+      const int cw = min(cchunk, C - cbase);
+      if (c < C) {
+        for (int bin = 0; bin < nbins; ++bin) {
+          float acc = 0.f;
+          const Tap* tp = taps + bin * ns;
+          for (int s = 0; s < ns; ++s) {
+            const Tap t = tp[s];
+            if (t.o0 < 0) continue;
+            const float a = __ldg(fm + t.o0 + c), b = __ldg(fm + t.o1 + c);
+            const float cc = __ldg(fm + t.o2 + c), d = __ldg(fm + t.o3 + c);
+            acc = acc + (((t.w1 * a + t.w2 * b) + t.w3 * cc) + t.w4 * d);
+          }
+          tile[threadIdx.x * nbins + bin] = acc / cnt;   // stride nbins (odd for 7x7): conflict-free
+        }
+      }
+      __syncthreads();
+      float* o = out + ((size_t)roi * C + cbase) * nbins;   // [cw][nbins] contiguous in NCHW
+      for (int i = threadIdx.x; i < cw * nbins; i += blockDim.x) o[i] = tile[i];
+      __syncthreads();
+    }
+  }
+}
+
+// Generic path (adaptive sample_num == 0, or very large sampling grids): reference-style, one
+// thread per output element, NHWC or NCHW output.
+__global__ void roi_align_generic_kernel(const float* __restrict__ feat, const float* __restrict__ rois, int n_rois,
+                                         int n_imgs, int C, int H, int W, int ph, int pw, float scale, int sn,
+                                         float* __restrict__ out, int nchw_out) {
+  const size_t total = (size_t)n_rois * C * ph * pw;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c, q, p, n;
+    if (nchw_out) {
+      q = (int)(i % pw); p = (int)((i / pw) % ph); c = (int)((i / ((size_t)pw * ph)) % C);
+      n = (int)(i / ((size_t)pw * ph * C));
+    } else {
+      c = (int)(i % C); q = (int)((i / C) % pw); p = (int)((i / ((size_t)C * pw)) % ph);
+      n = (int)(i / ((size_t)C * pw * ph));
+    }
+    const float* r = rois + (size_t)n * 5;
+    const RoiGeom g = roi_geom(r, scale, ph, pw, n_imgs);
+    const float ew = (r[3] + 1.0f) * scale, eh = (r[4] + 1.0f) * scale;
+    const float rw = fmaxf(ew - g.sw, 0.0f), rh = fmaxf(eh - g.sh, 0.0f);
+    const int nh = sn > 0 ? sn : (int)ceilf(rh / (float)ph);
+    const int nw = sn > 0 ? sn : (int)ceilf(rw / (float)pw);
+    const float* fm = feat + (size_t)g.b * H * W * C;
+    float acc = 0.f;
+    for (int iy = 0; iy < nh; ++iy) {
+      const float y = g.sh + (float)p * g.bh + ((float)iy + 0.5f) * g.bh / (float)nh;
+      for (int ix = 0; ix < nw; ++ix) {
+        const float x = g.sw + (float)q * g.bw + ((float)ix + 0.5f) * g.bw / (float)nw;
+        const Tap t = make_tap(y, x, H, W, C);
+        if (t.o0 < 0) continue;
+        acc = acc + (((t.w1 * fm[t.o0 + c] + t.w2 * fm[t.o1 + c]) + t.w3 * fm[t.o2 + c]) + t.w4 * fm[t.o3 + c]);
+      }
+    }
+    out[i] = acc / (float)(nh * nw);
+  }
+}
+
+}  // namespace
+
+extern "C" int hvr_roi_align_fwd(const float* feat, int feat_nhwc, const float* rois, int n_rois, int n_imgs, int C,
+                                 int H, int W, int ph, int pw, float spatial_scale, int sample_num, float* out,
+                                 int out_layout, hvr_bf16* out_hi, hvr_bf16* out_lo, int64_t ld_split, float* ws,
+                                 void* stream) {
+  if (!feat || !rois || n_rois < 0 || n_imgs < 1 || C < 1 || H < 1 || W < 1 || ph < 1 || pw < 1) return HVR_ERR_ARG;
+  if (!out && !out_hi) return HVR_ERR_ARG;
+  if ((out_hi == nullptr) != (out_lo == nullptr)) return HVR_ERR_ARG;
+  if (out_layout != 0 && out_layout != 1) return HVR_ERR_ARG;
+  if (out_hi && (out_layout != 1 || ld_split < (int64_t)ph * pw * C || ld_split % 4 != 0)) return HVR_ERR_ARG;
+  if ((size_t)H * W * C >= (1u << 31)) return HVR_ERR_ARG;
+  if (n_rois == 0) return HVR_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!feat_nhwc) {
+    if (!ws) return HVR_ERR_WORKSPACE;
+    int rc = hvr_nchw_to_nhwc_f32(feat, n_imgs, C, H, W, ws, stream);
+    if (rc) return rc;
+    feat = ws;
+  }
+  const int nsamp = ph * pw * sample_num * sample_num;
+  const bool fast = sample_num > 0 && nsamp <= 2048 && (out_layout == 0 || C % 4 == 0);
+  if (!fast) {
+    if (out_hi || !out) return HVR_ERR_UNSUPPORTED;
+    const size_t total = (size_t)n_rois * C * ph * pw;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    roi_align_generic_kernel<<<(int)blocks, 256, 0, st>>>(feat, rois, n_rois, n_imgs, C, H, W, ph, pw, spatial_scale,
+                                                          sample_num, out, out_layout == 0);
+    HVR_LAUNCHED();
+    return HVR_OK;
+  }
+  if (out_layout == 1) {
+    const size_t smem = (size_t)nsamp * sizeof(Tap);
+    static bool attr1 = false;
+    if (!attr1) {
+      HVR_CUDA(cudaFuncSetAttribute(roi_align_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+      attr1 = true;
+    }
+    roi_align_kernel<false><<<n_rois, 256, smem, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, sample_num,
+                                                       out, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_split);
+  } else {
+    const size_t smem = (size_t)nsamp * sizeof(Tap) + (size_t)256 * ph * pw * sizeof(float);
+    if (smem > 200 * 1024) return HVR_ERR_UNSUPPORTED;
+    static bool attr0 = false;
+    if (!attr0) {
+      HVR_CUDA(cudaFuncSetAttribute(roi_align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr0 = true;
+    }
+    roi_align_kernel<true><<<n_rois, 256, smem, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, sample_num,
+                                                      out, nullptr, nullptr, 0);
+  }
+  HVR_LAUNCHED();
+  return HVR_OK;
+}

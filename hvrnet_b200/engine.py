@@ -1,0 +1,327 @@
+"""Functional forward of the hot path on the C-ABI kernels.
+
+Weights come in as a flat state_dict with the REFERENCE's parameter names (SURVEY.md
+section 5), are folded / re-laid-out / split once by the ``pack_*`` functions, and every
+forward below is a sequence of libhvr_b200.so calls on the current stream.  Layout inside:
+NHWC split-bf16 activations, K-major split weights [Cout, kh*kw*Cin].
+
+Reference functions mirrored (file:line under /root/reference/mmdet):
+  trunk_forward      models/backbones/resnet.py:222-257,522-533
+  c5_forward         models/shared_heads/res_layer.py:67-74
+  rpn_forward        models/anchor_heads/rpn_head.py:30-35
+  relation           models/bbox_heads/hrnmp_bbox_head.py:216-355
+  hrnmp_forward_test models/bbox_heads/hrnmp_bbox_head.py:800-909
+  selsa_forward      models/bbox_heads/selsa_bbox_head.py:203-261
+  shared_fc_forward  models/bbox_heads/convfc_bbox_head.py:126-167
+"""
+import math
+
+import torch
+
+from . import ops
+from .ops import Split, round_up
+
+BN_EPS = 1e-5
+R101_BLOCKS = (3, 4, 23, 3)
+
+
+# ----------------------------------------------------------------------------------------
+# weight packing (host, once)
+# ----------------------------------------------------------------------------------------
+
+def _bn_fold(sd, name):
+    g, b = sd[name + '.weight'].double(), sd[name + '.bias'].double()
+    m, v = sd[name + '.running_mean'].double(), sd[name + '.running_var'].double()
+    scale = g / torch.sqrt(v + BN_EPS)
+    return scale, b - m * scale
+
+
+def pack_matrix(w2d, device, pad_rows=64, pad_cols=64):
+    """fp32/fp64 [N, K] -> Split [round_up(N), round_up(K)] on device (zero padded)."""
+    n, k = w2d.shape
+    W = torch.zeros((round_up(n, pad_rows), round_up(k, pad_cols)), dtype=torch.float32)
+    W[:n, :k] = w2d.float()
+    W = W.to(device)
+    return ops.split(W)
+
+
+def pack_conv(w, scale, device):
+    """[Cout, Cin, kh, kw] (+ per-Cout BN scale) -> K-major [Cout, (r*kw+s)*Cin + c]."""
+    w = w.double()
+    if scale is not None:
+        w = w * scale.view(-1, 1, 1, 1)
+    cout = w.shape[0]
+    return pack_matrix(w.permute(0, 2, 3, 1).reshape(cout, -1), device)
+
+
+class ConvP:
+    """One packed conv(+BN)(+bias) layer."""
+    __slots__ = ('w', 'bias', 'n', 'k', 'cin', 'dilation')
+
+    def __init__(self, w, bias, n, k, cin, dilation=1):
+        self.w, self.bias, self.n, self.k, self.cin, self.dilation = w, bias, n, k, cin, dilation
+
+
+def _pack_conv_bn(sd, conv, bn, device, dilation=1, bias_name=None):
+    w = sd[conv + '.weight']
+    scale = shift = None
+    if bn is not None:
+        scale, shift = _bn_fold(sd, bn)
+    bias = shift
+    if bias_name is not None:
+        bias = sd[bias_name].double() if bias is None else bias + sd[bias_name].double() * scale
+    n = w.shape[0]
+    b = None
+    if bias is not None:
+        b = torch.zeros(round_up(n, 64), dtype=torch.float32)
+        b[:n] = bias.float()
+        b = b.to(device)
+    return ConvP(pack_conv(w, scale, device), b, n, w.shape[2], w.shape[1], dilation)
+
+
+def _pack_res_layer(sd, p, blocks, dilation, device):
+    out = []
+    for i in range(blocks):
+        q = '%s%d.' % (p, i)
+        blk = dict(conv1=_pack_conv_bn(sd, q + 'conv1', q + 'bn1', device),
+                   conv2=_pack_conv_bn(sd, q + 'conv2', q + 'bn2', device, dilation),
+                   conv3=_pack_conv_bn(sd, q + 'conv3', q + 'bn3', device))
+        if (q + 'downsample.0.weight') in sd:
+            blk['down'] = _pack_conv_bn(sd, q + 'downsample.0', q + 'downsample.1', device)
+        out.append(blk)
+    return out
+
+
+def pack_trunk(sd, device, prefix='backbone.', strides=(1, 2, 2), dilations=(1, 1, 1)):
+    w = sd[prefix + 'conv1.weight'].double()
+    scale, shift = _bn_fold(sd, prefix + 'bn1')
+    w = (w * scale.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(64, 147)      # k = (r*7+s)*3 + c
+    stem = ConvP(pack_matrix(w, device, 64, 192), shift.float().to(device), 64, 7, 3)
+    layers = [_pack_res_layer(sd, '%slayer%d.' % (prefix, i + 1), R101_BLOCKS[i], dilations[i], device)
+              for i in range(len(strides))]
+    return dict(stem=stem, layers=layers, strides=tuple(strides))
+
+
+def pack_c5(sd, device, prefix='shared_head.', stride=1, dilation=2):
+    p = dict(layer4=_pack_res_layer(sd, prefix + 'layer4.', R101_BLOCKS[3], dilation, device), stride=stride)
+    if (prefix + 'new_layer_1.conv.weight') in sd:
+        p['new1'] = _pack_conv_bn(sd, prefix + 'new_layer_1.conv', None, device,
+                                  bias_name=prefix + 'new_layer_1.conv.bias')
+    return p
+
+
+def pack_rpn(sd, device, prefix='rpn_head.'):
+    conv = _pack_conv_bn(sd, prefix + 'rpn_conv', None, device, bias_name=prefix + 'rpn_conv.bias')
+    wc, wr = sd[prefix + 'rpn_cls.weight'], sd[prefix + 'rpn_reg.weight']
+    A = wc.shape[0]
+    w = torch.cat([wc, wr], 0).reshape(A * 5, -1)                                # one GEMM: [cls | reg]
+    b = torch.zeros(round_up(A * 5, 64), dtype=torch.float32)
+    b[:A * 5] = torch.cat([sd[prefix + 'rpn_cls.bias'], sd[prefix + 'rpn_reg.bias']])
+    head = ConvP(pack_matrix(w, device), b.to(device), A * 5, 1, w.shape[1])
+    return dict(conv=conv, head=head, A=A)
+
+
+class LinP:
+    __slots__ = ('w', 'bias', 'n', 'k')
+
+    def __init__(self, w, bias, n, k):
+        self.w, self.bias, self.n, self.k = w, bias, n, k
+
+
+def pack_linear(weight, bias, device, col_perm=None):
+    w = weight.reshape(weight.shape[0], -1)
+    if col_perm is not None:
+        w = w[:, col_perm]
+    n, k = w.shape
+    b = torch.zeros(round_up(n, 64), dtype=torch.float32)
+    if bias is not None:
+        b[:n] = bias
+    return LinP(pack_matrix(w, device), b.to(device), n, k)
+
+
+def nhwc_perm(channels, size):
+    """Column permutation taking flatten(C,h,w) weights to flatten(h,w,C) inputs."""
+    idx = torch.arange(channels * size * size).view(channels, size, size)
+    return idx.permute(1, 2, 0).reshape(-1)
+
+
+def pack_head(sd, device, kind='hrnmp', prefix='bbox_head.', roi_channels=256, roi_size=7):
+    """kind: 'hrnmp' (4 stages) | 'selsa' (2 stages) | 'shared_fc'."""
+    perm = nhwc_perm(roi_channels, roi_size)
+    P = dict(kind=kind)
+
+    def lin(name, col_perm=None):
+        return pack_linear(sd[prefix + name + '.weight'], sd[prefix + name + '.bias'], device, col_perm)
+
+    if kind == 'shared_fc':
+        P['fc1'] = lin('shared_fcs.0', perm)
+        P['fc2'] = lin('shared_fcs.1')
+    else:
+        stages = 4 if kind == 'hrnmp' else 2
+        for k in range(1, stages + 1):
+            P['fc%d' % k] = lin('fc_new_%d' % k, perm if k == 1 else None)
+            s = 'selsa_%d.' % k
+            P['q%d' % k] = lin(s + 'q_data_fc_%d' % k)
+            P['k%d' % k] = lin(s + 'k_data_fc_%d' % k)
+            P['o%d' % k] = lin(s + 'linear_out_%d' % k)
+    # fc_cls and fc_reg share their input: one GEMM, columns [cls | reg]
+    def clsreg(c, r):
+        w = torch.cat([sd[prefix + c + '.weight'], sd[prefix + r + '.weight']], 0)
+        b = torch.cat([sd[prefix + c + '.bias'], sd[prefix + r + '.bias']], 0)
+        return pack_linear(w, b, device)
+    P['n_cls'] = sd[prefix + 'fc_cls.weight'].shape[0]
+    P['n_reg'] = sd[prefix + 'fc_reg.weight'].shape[0]
+    P['out1'] = clsreg('fc_cls', 'fc_reg')
+    if kind == 'hrnmp':
+        P['out2'] = clsreg('fc_cls_2', 'fc_reg_2')
+    return P
+
+
+# ----------------------------------------------------------------------------------------
+# conv / linear execution
+# ----------------------------------------------------------------------------------------
+
+def _taps(k, dil):
+    r = k // 2
+    return tuple(((s - r) * dil, (t - r) * dil) for t in range(k) for s in range(k))   # (dx, dy), r-major
+
+
+def conv(a, cp, stride=1, relu=False, res=None, want_split=True, want_f32=False, passes=3, check_kernel=False):
+    """a: Split NHWC [B,H,W,C].  Returns (Split NHWC or None, fp32 NHWC or None)."""
+    B, H, W, C = a.shape
+    assert C == cp.cin, (C, cp.cin)
+    dev = a.hi.device
+    sb, sh, sw = a.hi.stride(0), a.hi.stride(1), a.hi.stride(2)
+    if stride == 1:
+        Ho, Wo = H, W
+        view = (C, W, H, B, sw, sh, sb)
+    else:
+        assert cp.k == 1, 'strided convs on this path are 1x1 (caffe-style bottleneck)'
+        Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+        view = (C, Wo, Ho, B, sw * stride, sh * stride, sb)
+    n = cp.w.shape[0]          # physical (64-padded) rows; padded outputs are exactly bias-free zeros
+    out = Split.empty((B, Ho, Wo, n), dev) if want_split else None
+    of = torch.empty((B, Ho, Wo, round_up(n, 4)), dtype=torch.float32, device=dev) if want_f32 else None
+    rows = B * Ho * Wo
+    g = ops.igemm_desc(a, cp.w, n, taps=_taps(cp.k, cp.dilation), a_view=view, out_whb=(Wo, Ho, B),
+                       bias=cp.bias, relu=relu,
+                       res=Split(res.hi.view(rows, -1), res.lo.view(rows, -1)) if res is not None else None,
+                       out=Split(out.hi.view(rows, n), out.lo.view(rows, n)) if out is not None else None,
+                       out_f32=of.view(rows, -1) if of is not None else None, passes=passes)
+    ops.igemm_run(g, check_kernel)
+    return out, of
+
+
+def bottleneck(x, blk, stride, **kw):
+    """resnet.py:222-257, caffe style: stride on conv1 (and on the downsample)."""
+    o, _ = conv(x, blk['conv1'], stride=stride, relu=True, **kw)
+    o, _ = conv(o, blk['conv2'], relu=True, **kw)
+    idt = x
+    if 'down' in blk:
+        idt, _ = conv(x, blk['down'], stride=stride, **kw)
+    o, _ = conv(o, blk['conv3'], relu=True, res=idt, **kw)
+    return o
+
+
+def res_layer(x, blocks, stride, **kw):
+    for i, blk in enumerate(blocks):
+        x = bottleneck(x, blk, stride if i == 0 else 1, **kw)
+    return x
+
+
+def trunk_forward(P, img, **kw):
+    """img fp32 NCHW [B,3,H,W] -> C4 Split NHWC [B,H/16,W/16,1024]."""
+    col = ops.im2col_stem(img)                                   # [B,oh,ow,192]
+    x, _ = _stem(P, col, **kw)
+    x = ops.maxpool3x3s2(x)
+    for blocks, s in zip(P['layers'], P['strides']):
+        x = res_layer(x, blocks, s, **kw)
+    return x
+
+
+def _stem(P, col, **kw):
+    st = P['stem']
+    cp = ConvP(st.w, st.bias, 64, 1, 192)
+    return conv(col, cp, relu=True, **kw)
+
+
+def c5_forward(P, c4, **kw):
+    """C4 Split NHWC -> fp32 NHWC [T,h,w,256] (RoIAlign input)."""
+    x = res_layer(c4, P['layer4'], P['stride'], **kw)
+    if 'new1' in P:
+        _, f = conv(x, P['new1'], relu=True, want_split=False, want_f32=True, **kw)
+        return f
+    return ops.merge(x)
+
+
+def rpn_forward(P, c4, **kw):
+    """-> fp32 [T,h,w,64]: columns [0,A) cls logits, [A,5A) deltas (a*4+d)."""
+    x, _ = conv(c4, P['conv'], relu=True, **kw)
+    _, o = conv(x, P['head'], want_split=False, want_f32=True, **kw)
+    return o
+
+
+def lin(a, lp, relu=False, res=None, want_split=True, want_f32=False, want_T=False, **kw):
+    return ops.linear(a, lp.w, lp.w.shape[0], bias=lp.bias, relu=relu, res=res, want_split=want_split, want_f32=want_f32,
+                      want_T=want_T, **kw)
+
+
+def relation(P, idx, X, XT, q_range=None, res=None, relu=True, extra=None, **kw):
+    """SELSA relation block idx on X Split [N,D] (XT = X^T Split [D, ld>=N]).
+    Returns relu(res + NL(X)) (Split [Nq, D]).  hrnmp_bbox_head.py:216-355.
+    extra: optional (Xs Split [M,D]) support rows appended to the key/value set (stage 4)."""
+    N, D = X.shape
+    if extra is not None:
+        Xk = Split(torch.cat([X.hi, extra.hi], 0), torch.cat([X.lo, extra.lo], 0))
+        Nk = Xk.shape[0]
+        XkT = Split.zeros((D, round_up(Nk, 64)), X.hi.device)
+        XkT.hi[:, :Nk] = Xk.hi.t()
+        XkT.lo[:, :Nk] = Xk.lo.t()
+    else:
+        Xk, Nk, XkT = X, N, XT
+    Xq = X if q_range is None else X[q_range[0]:q_range[0] + q_range[1]]
+    Q, _, _ = lin(Xq, P['q%d' % idx], **kw)
+    K, _, _ = lin(Xk, P['k%d' % idx], **kw)
+    # S = Q K^T / sqrt(D)  (1/32 for D=1024: exact power of two)
+    _, S, _ = ops.linear(Q, K, Nk, alpha=1.0 / math.sqrt(float(D)), want_split=False, want_f32=True, **kw)
+    Pm = ops.softmax_rows_split(S, Nk)
+    # O = P V, V = un-projected rows (conv_g False): right operand is X^T [D, Nk]
+    O, _, _ = ops.linear(Pm, XkT, D, **kw)
+    out, _, _ = lin(O, P['o%d' % idx], relu=relu, res=res, **kw)
+    return out
+
+
+def hrnmp_forward_test(P, roi_feats, start, length, support=None, **kw):
+    """roi_feats Split [N, 12544] (NHWC-flattened).  Returns fp32 (out1 [len, 64], out2 [len, 64]):
+    columns [0,n_cls) class logits, [n_cls, n_cls+4) box deltas; plus f4[key] Split."""
+    s, e = start, start + length
+    f1, _, f1T = lin(roi_feats, P['fc1'], want_T=True, **kw)
+    a1 = relation(P, 1, f1, f1T, res=f1, **kw)
+    f2, _, f2T = lin(a1, P['fc2'], want_T=True, **kw)
+    # only the key rows of stage 2 are ever used (hrnmp_bbox_head.py:865-868): key-only queries
+    a2k = relation(P, 2, f2, f2T, q_range=(s, length), res=f2[s:e], **kw)
+    _, out1, _ = lin(a2k, P['out1'], want_split=False, want_f32=True, **kw)
+    x3 = Split(torch.cat([f1.hi[:s], a2k.hi, f1.hi[e:]], 0), torch.cat([f1.lo[:s], a2k.lo, f1.lo[e:]], 0))
+    f3, _, f3T = lin(x3, P['fc3'], want_T=True, **kw)
+    a3 = relation(P, 3, f3, f3T, res=f3, **kw)
+    f4, _, f4T = lin(a3, P['fc4'], want_T=True, **kw)
+    a4 = relation(P, 4, f4, f4T, q_range=(s, length), res=f4[s:e], extra=support, **kw)
+    _, out2, _ = lin(a4, P['out2'], want_split=False, want_f32=True, **kw)
+    return out1, out2, f4[s:e]
+
+
+def selsa_forward(P, roi_feats, start, length, **kw):
+    s, e = start, start + length
+    f1, _, f1T = lin(roi_feats, P['fc1'], want_T=True, **kw)
+    a1 = relation(P, 1, f1, f1T, res=f1, **kw)
+    f2, _, f2T = lin(a1, P['fc2'], want_T=True, **kw)
+    a2k = relation(P, 2, f2, f2T, q_range=(s, length), res=f2[s:e], **kw)   # relu after the key slice
+    _, out1, _ = lin(a2k, P['out1'], want_split=False, want_f32=True, **kw)
+    return out1
+
+
+def shared_fc_forward(P, roi_feats, **kw):
+    x, _, _ = lin(roi_feats, P['fc1'], relu=True, **kw)
+    x, _, _ = lin(x, P['fc2'], relu=True, **kw)
+    _, out1, _ = lin(x, P['out1'], want_split=False, want_f32=True, **kw)
+    return out1

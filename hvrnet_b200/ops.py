@@ -1,0 +1,325 @@
+"""Thin torch-tensor front-end of the C ABI (include/hvr_b200.h).
+
+torch is used for device memory and streams only; every computation below is a call into
+libhvr_b200.so on the current CUDA stream.  CUDA tensors only - there is no CPU path.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import HvrIGemm, check
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.HvrError('hvrnet_b200 ops take CUDA tensors only (got %s); there is no CPU path' % t.device)
+
+
+def round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class Split:
+    """Split-bf16 tensor: x ~= hi + lo (two bf16 tensors of identical shape/strides)."""
+    __slots__ = ('hi', 'lo')
+
+    def __init__(self, hi, lo):
+        self.hi, self.lo = hi, lo
+
+    @staticmethod
+    def empty(shape, device):
+        return Split(torch.empty(shape, dtype=torch.bfloat16, device=device),
+                     torch.empty(shape, dtype=torch.bfloat16, device=device))
+
+    @staticmethod
+    def zeros(shape, device):
+        return Split(torch.zeros(shape, dtype=torch.bfloat16, device=device),
+                     torch.zeros(shape, dtype=torch.bfloat16, device=device))
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    def __getitem__(self, idx):
+        return Split(self.hi[idx], self.lo[idx])
+
+    def float(self):
+        return merge(self)
+
+
+def split(x):
+    """fp32 tensor (contiguous) -> Split of the same shape."""
+    _need_cuda(x)
+    x = x.contiguous().float()
+    s = Split.empty(x.shape, x.device)
+    check(_lib.lib().hvr_split_f32(_p(x), x.numel(), _p(s.hi), _p(s.lo), _stream()), 'hvr_split_f32')
+    return s
+
+
+def split_2d(x, ld_out):
+    """fp32 [rows, cols] -> Split [rows, ld_out] (zero padded columns)."""
+    _need_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    rows, cols = x.shape
+    s = Split.empty((rows, ld_out), x.device)
+    check(_lib.lib().hvr_split_f32_2d(_p(x), rows, cols, x.stride(0), _p(s.hi), _p(s.lo), ld_out, _stream()),
+          'hvr_split_f32_2d')
+    return s
+
+
+def merge(s):
+    _need_cuda(s.hi)
+    assert s.hi.is_contiguous() and s.lo.is_contiguous()
+    out = torch.empty(s.hi.shape, dtype=torch.float32, device=s.hi.device)
+    check(_lib.lib().hvr_merge_f32(_p(s.hi), _p(s.lo), s.hi.numel(), _p(out), _stream()), 'hvr_merge_f32')
+    return out
+
+
+def nchw_to_nhwc_split(x):
+    _need_cuda(x)
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    s = Split.empty((B, H, W, C), x.device)
+    check(_lib.lib().hvr_nchw_to_nhwc_split(_p(x), B, C, H, W, _p(s.hi), _p(s.lo), _stream()), 'hvr_nchw_to_nhwc_split')
+    return s
+
+
+def nhwc_split_to_nchw(s):
+    B, H, W, C = s.shape
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=s.hi.device)
+    check(_lib.lib().hvr_nhwc_split_to_nchw(_p(s.hi), _p(s.lo), B, C, H, W, _p(out), _stream()),
+          'hvr_nhwc_split_to_nchw')
+    return out
+
+
+def nhwc_to_nchw(x):
+    B, H, W, C = x.shape
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+    check(_lib.lib().hvr_nhwc_to_nchw_f32(_p(x), B, C, H, W, _p(out), _stream()), 'hvr_nhwc_to_nchw_f32')
+    return out
+
+
+def nchw_to_nhwc(x):
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    out = torch.empty((B, H, W, C), dtype=torch.float32, device=x.device)
+    check(_lib.lib().hvr_nchw_to_nhwc_f32(_p(x), B, C, H, W, _p(out), _stream()), 'hvr_nchw_to_nhwc_f32')
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# implicit GEMM
+# ----------------------------------------------------------------------------------------
+
+def pick_tile(out_w, out_h):
+    """M tile (tile_w x tile_h = 128 pixels) wasting the fewest rows."""
+    best = None
+    for tw in (128, 64, 32, 16, 8):
+        th = 128 // tw
+        waste = (math.ceil(out_w / tw) * tw) * (math.ceil(out_h / th) * th)
+        if best is None or waste < best[0]:
+            best = (waste, tw, th)
+    return best[1], best[2]
+
+
+def igemm_desc(a, b, n, *, taps=((0, 0),), a_view=None, out_whb=None, tile=None, alpha=1.0, bias=None, res=None,
+               relu=False, out=None, out_f32=None, outT=None, passes=3):
+    """Fill an HvrIGemm.
+
+    a      Split; either 2-D [M, K] (plain GEMM) or NHWC 4-D [B, H, W, C]
+    a_view optional (C, W, H, B, stride_w, stride_h, stride_b) override (strided views)
+    b      Split [n_rows >= n, ktot] K-major weights / right operand
+    out    Split 2-D [rows, ld]; out_f32 fp32 [rows, ld]; outT Split [n, ld]
+    """
+    g = HvrIGemm()
+    g.a_hi, g.a_lo = a.hi.data_ptr(), a.lo.data_ptr()
+    if a_view is not None:
+        C, W, H, B, sw, sh, sb = a_view
+    elif a.hi.dim() == 2:
+        M, K = a.shape
+        C, W, H, B = K, M, 1, 1
+        sw = a.hi.stride(0)
+        sh = sw * M
+        sb = sh
+    else:
+        B, H, W, C = a.shape
+        sb, sh, sw = a.hi.stride(0), a.hi.stride(1), a.hi.stride(2)
+        assert a.hi.stride(3) == 1
+    g.a_c, g.a_w, g.a_h, g.a_b = C, W, H, B
+    g.a_stride_w, g.a_stride_h, g.a_stride_b = sw, sh, sb
+    g.ntaps = len(taps)
+    for i, (dx, dy) in enumerate(taps):
+        g.tap_dx[i], g.tap_dy[i] = dx, dy
+    if out_whb is None:
+        out_whb = (W, H, B)
+    g.out_w, g.out_h, g.batch = out_whb
+    g.tile_w, g.tile_h = tile if tile is not None else pick_tile(g.out_w, g.out_h)
+    g.b_hi, g.b_lo, g.n, g.ldb = b.hi.data_ptr(), b.lo.data_ptr(), n, b.hi.stride(0)
+    g.alpha = alpha
+    g.bias = bias.data_ptr() if bias is not None else None
+    if res is not None:
+        g.res_hi, g.res_lo, g.ld_res = res.hi.data_ptr(), res.lo.data_ptr(), res.hi.stride(0)
+    g.relu = int(relu)
+    if out is not None:
+        g.out_hi, g.out_lo, g.ld_out = out.hi.data_ptr(), out.lo.data_ptr(), out.hi.stride(0)
+    if out_f32 is not None:
+        g.out_f32, g.ld_f32 = out_f32.data_ptr(), out_f32.stride(0)
+    if outT is not None:
+        g.outT_hi, g.outT_lo, g.ld_outT = outT.hi.data_ptr(), outT.lo.data_ptr(), outT.hi.stride(0)
+    g.passes = passes
+    return g
+
+
+def igemm_run(g, check_kernel=False):
+    fn = _lib.lib().hvr_igemm_check if check_kernel else _lib.lib().hvr_igemm
+    check(fn(ctypes.byref(g), _stream()), 'hvr_igemm')
+
+
+def linear(a, w, n, bias=None, relu=False, res=None, alpha=1.0, want_split=True, want_f32=False, want_T=False,
+           passes=3, check_kernel=False):
+    """y = alpha * a @ w[:n].T + bias (+res) (relu).  a Split [M,K]; w Split [>=n, K].
+    Returns (Split or None, fp32 or None, Split^T or None)."""
+    M = a.shape[0]
+    dev = a.hi.device
+    ld = round_up(n, 8)
+    out = Split.empty((M, ld), dev) if want_split else None
+    of = torch.empty((M, round_up(n, 4)), dtype=torch.float32, device=dev) if want_f32 else None
+    oT = Split.zeros((n, round_up(M, 64)), dev) if want_T else None
+    g = igemm_desc(a, w, n, alpha=alpha, bias=bias, res=res, relu=relu, out=out, out_f32=of, outT=oT, passes=passes)
+    igemm_run(g, check_kernel)
+    return out, of, oT
+
+
+# ----------------------------------------------------------------------------------------
+# RoIAlign / NMS / proposals / detections / softmax
+# ----------------------------------------------------------------------------------------
+
+def roi_align(feat, rois, out_size=7, spatial_scale=1 / 16., sample_num=2, feat_nhwc=False, out_nhwc=False,
+              want_split=False, ld_split=None):
+    """feat fp32 NCHW (reference layout) or NHWC; rois [n,5].  Returns fp32 output in the
+    reference layout [n,C,ph,pw] (or [n,ph,pw,C] when out_nhwc), plus an optional Split
+    [n, ld_split] copy in NHWC order."""
+    _need_cuda(feat, rois)
+    feat = feat.contiguous()
+    rois = rois.contiguous().float()
+    if feat_nhwc:
+        B, H, W, C = feat.shape
+    else:
+        B, C, H, W = feat.shape
+    n = rois.shape[0]
+    ph = pw = int(out_size)
+    dev = feat.device
+    out = torch.empty((n, ph, pw, C) if out_nhwc else (n, C, ph, pw), dtype=torch.float32, device=dev)
+    sp = None
+    if want_split:
+        assert out_nhwc
+        ld_split = ld_split or ph * pw * C
+        sp = Split.empty((n, ld_split), dev)
+    ws = None if feat_nhwc else torch.empty(feat.numel(), dtype=torch.float32, device=dev)
+    check(_lib.lib().hvr_roi_align_fwd(_p(feat), int(feat_nhwc), _p(rois), n, B, C, H, W, ph, pw, float(spatial_scale),
+                                       int(sample_num), _p(out), 1 if out_nhwc else 0,
+                                       _p(sp.hi) if sp else None, _p(sp.lo) if sp else None,
+                                       ld_split or 0, _p(ws), _stream()), 'hvr_roi_align_fwd')
+    return (out, sp) if want_split else out
+
+
+def nms(dets, iou_thr, strict_gt=True):
+    """dets [n,5] fp32 CUDA -> kept original indices (int64, ascending).  One D2H read of the
+    count at the end (the reference API returns a tensor of data-dependent length)."""
+    _need_cuda(dets)
+    dets = dets.contiguous().float()
+    n = dets.shape[0]
+    dev = dets.device
+    if n == 0:
+        return torch.zeros(0, dtype=torch.long, device=dev)
+    L = _lib.lib()
+    wsb = L.hvr_nms_workspace_bytes(n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    keep = torch.empty(n, dtype=torch.long, device=dev)
+    nk = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(L.hvr_nms(_p(dets), n, float(iou_thr), int(strict_gt), _p(keep), _p(nk), _p(ws), wsb, _stream()), 'hvr_nms')
+    return keep[:int(nk.item())]
+
+
+def rpn_proposals(cls, reg, ld_cls, ld_reg, T, H, W, A, base_anchors, stride, img_shape, nms_pre=6000, nms_post=300,
+                  max_num=300, nms_thr=0.7, want_idx=False):
+    """cls/reg: fp32 CUDA tensors whose data_ptr is element (t=0, cell=0, a=0); see hvr_rpn_proposals.
+    Returns proposals [T,max_num,5], counts [T] int32 (device) (+ anchor indices)."""
+    _need_cuda(cls, reg, base_anchors)
+    L = _lib.lib()
+    dev = cls.device
+    n_anc = H * W * A
+    wsb = L.hvr_rpn_workspace_bytes(T, n_anc, nms_pre)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    props = torch.empty((T, max_num, 5), dtype=torch.float32, device=dev)
+    counts = torch.empty(T, dtype=torch.int32, device=dev)
+    idx = torch.empty((T, max_num), dtype=torch.int32, device=dev) if want_idx else None
+    check(L.hvr_rpn_proposals(_p(cls), ld_cls, _p(reg), ld_reg, T, H, W, A, _p(base_anchors), stride,
+                              float(img_shape[0]), float(img_shape[1]), nms_pre, nms_post, max_num, float(nms_thr),
+                              _p(props), _p(counts), _p(idx), _p(ws), wsb, _stream()), 'hvr_rpn_proposals')
+    return (props, counts, idx) if want_idx else (props, counts)
+
+
+def det_postprocess(rois, cls, reg, img_shape, scale_factor=1.0, rescale=False, stds=(0.1, 0.1, 0.2, 0.2),
+                    score_thr=0.001, iou_thr=0.3, max_per_img=300, n_cls=None):
+    """rois [n,5], cls [n,>=n_cls] fp32, reg [n,>=4] fp32 (row-strided views allowed).
+    Returns dets [max_per_img,5], labels [max_per_img] int64, n_dets [1] int32 (all device)."""
+    _need_cuda(rois, cls, reg)
+    L = _lib.lib()
+    dev = rois.device
+    n = rois.shape[0]
+    n_cls = n_cls or cls.shape[1]
+    rois = rois.contiguous().float()
+    assert cls.stride(1) == 1 and reg.stride(1) == 1
+    wsb = L.hvr_det_workspace_bytes(n, n_cls)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    dets = torch.zeros((max_per_img, 5), dtype=torch.float32, device=dev)
+    labels = torch.zeros(max_per_img, dtype=torch.long, device=dev)
+    nd = torch.zeros(1, dtype=torch.int32, device=dev)
+    stds_c = (ctypes.c_float * 4)(*stds)
+    check(L.hvr_det_postprocess(_p(rois), _p(cls), cls.stride(0), _p(reg), reg.stride(0), n, n_cls, stds_c,
+                                float(img_shape[0]), float(img_shape[1]), float(scale_factor), int(rescale),
+                                float(score_thr), float(iou_thr), int(max_per_img), _p(dets), _p(labels), _p(nd),
+                                _p(ws), wsb, _stream()), 'hvr_det_postprocess')
+    return dets, labels, nd
+
+
+def softmax_rows_split(S, cols, ld_p=None):
+    """S fp32 [rows, ld_s] -> Split P [rows, ld_p], softmax over the first `cols` columns."""
+    _need_cuda(S)
+    rows = S.shape[0]
+    ld_p = ld_p or round_up(cols, 64)
+    P = Split.empty((rows, ld_p), S.device)
+    check(_lib.lib().hvr_softmax_rows_split(_p(S), rows, cols, S.stride(0), _p(P.hi), _p(P.lo), ld_p, _stream()),
+          'hvr_softmax_rows_split')
+    return P
+
+
+def im2col_stem(img):
+    img = img.contiguous().float()
+    B, C, H, W = img.shape
+    assert C == 3
+    oh, ow = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    s = Split.empty((B, oh, ow, 192), img.device)
+    check(_lib.lib().hvr_im2col_stem(_p(img), B, H, W, _p(s.hi), _p(s.lo), oh, ow, _stream()), 'hvr_im2col_stem')
+    return s
+
+
+def maxpool3x3s2(s):
+    B, H, W, C = s.shape
+    oh, ow = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    o = Split.empty((B, oh, ow, C), s.hi.device)
+    check(_lib.lib().hvr_maxpool3x3s2_split(_p(s.hi), _p(s.lo), B, H, W, C, _p(o.hi), _p(o.lo), oh, ow, _stream()),
+          'hvr_maxpool3x3s2_split')
+    return o

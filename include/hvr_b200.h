@@ -1,0 +1,214 @@
+/* hvr_b200.h - C ABI of the B200-native (sm_100a) HVRNet per-key-frame inference hot path.
+ *
+ * Drop-in boundary.  The reference (youthHan/HVRNet, an mmdetection-v1 fork) crosses into
+ * native code through pybind11 functions that take at::Tensor:
+ *     roi_align_cuda.forward   mmdet/ops/roi_align/src/roi_align_cuda.cpp:27-53,82-85
+ *     nms_cuda.nms             mmdet/ops/nms/src/nms_cuda.cpp:1-16  (nms_kernel.cu:71-136)
+ *     nms_cpu.nms              mmdet/ops/nms/src/nms_cpu.cpp:61-67
+ * and through library calls (cuDNN conv / cuBLAS gemm) behind nn.Conv2d / nn.Linear /
+ * torch.bmm / torch.mm (mmdet/models/utils/conv_module.py:9-13,
+ * mmdet/models/bbox_heads/hrnmp_bbox_head.py:140-186,293,342).  This header is what a
+ * replacement binds instead: plain pointers and sizes, no torch types.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in _host;
+ *  - the caller owns every buffer (torch's caching allocator on the Python side);
+ *  - `stream` is a cudaStream_t passed as void* (the caller's current stream); no entry
+ *    point synchronises the device or the stream unless its comment says so;
+ *  - return value: 0 = HVR_OK, negative = error (hvr_strerror); nothing exits the process
+ *    (cf. the exit() in roi_align_kernel.cu:269-272);
+ *  - "split" tensors are the storage format of every activation that feeds a tensor-core
+ *    contraction: a pair of bf16 arrays (hi, lo) with  x ~= float(hi) + float(lo),
+ *    hi = bf16_rn(x), lo = bf16_rn(x - float(hi))  (16+ mantissa bits).  Contractions are
+ *    evaluated as  hi*hi + hi*lo + lo*hi  on tcgen05 with fp32 accumulation in TMEM.
+ *  - feature maps are NHWC inside the library; NCHW only at the reference-facing edge.
+ */
+#ifndef HVR_B200_H_
+#define HVR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HVR_OK 0
+#define HVR_ERR_ARG (-1)      /* bad argument (shape, alignment, null pointer)          */
+#define HVR_ERR_CUDA (-2)     /* a CUDA runtime / driver call failed (hvr_last_cuda_error) */
+#define HVR_ERR_WORKSPACE (-3) /* workspace too small                                     */
+#define HVR_ERR_UNSUPPORTED (-4)
+
+typedef uint16_t hvr_bf16;    /* raw bfloat16 bits */
+
+const char* hvr_strerror(int code);
+/* cudaError_t of the last failing CUDA call made by this library on this thread. */
+int hvr_last_cuda_error(void);
+/* ABI version, bumped on any signature change. */
+int hvr_abi_version(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+uint64_t hvr_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Split-bf16 storage
+ * ---------------------------------------------------------------------------------- */
+int hvr_split_f32(const float* x, size_t n, hvr_bf16* hi, hvr_bf16* lo, void* stream);
+int hvr_merge_f32(const hvr_bf16* hi, const hvr_bf16* lo, size_t n, float* out, void* stream);
+/* 2-D variant with leading dimensions (elements): x[rows, ld_in] -> hi/lo[rows, ld_out],
+ * columns [cols, ld_out) are zero-filled. */
+int hvr_split_f32_2d(const float* x, int rows, int cols, int ld_in, hvr_bf16* hi, hvr_bf16* lo,
+                     int ld_out, void* stream);
+/* NCHW fp32 (the reference's layout) -> NHWC split, and back. */
+int hvr_nchw_to_nhwc_split(const float* x, int B, int C, int H, int W, hvr_bf16* hi, hvr_bf16* lo,
+                           void* stream);
+int hvr_nhwc_split_to_nchw(const hvr_bf16* hi, const hvr_bf16* lo, int B, int C, int H, int W,
+                           float* out, void* stream);
+int hvr_nchw_to_nhwc_f32(const float* x, int B, int C, int H, int W, float* out, void* stream);
+int hvr_nhwc_to_nchw_f32(const float* x, int B, int C, int H, int W, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Implicit GEMM on tcgen05 (replaces the cuDNN / cuBLAS calls behind nn.Conv2d, nn.Linear,
+ * torch.bmm, torch.mm on the path: resnet.py:222-257, res_layer.py:67-74, rpn_head.py:30-35,
+ * hrnmp_bbox_head.py:283-294,342-350,827-906).
+ *
+ *   D[m, n] = alpha * sum_{tap, c} A[pixel(m) + off(tap), c] * Wt[n, tap*C + c]
+ *   y       = D + bias[n] + residual[m, n];  y = relu ? max(y,0) : y
+ *
+ * A is a 4-D strided view (C, W, H, B) of a split NHWC tensor; rows m enumerate the output
+ * pixels (b, y, x) of an (out_w, out_h, batch) grid and read A at (x + dx, y + dy); reads
+ * outside [0,W)x[0,H) are zero (conv padding).  A plain GEMM is W = M, H = B = 1, 1 tap.
+ * Wt is [N, ntaps*C] K-major split (BN already folded in).  C must be a multiple of 8
+ * (16-byte rows); K tiles of 64 are zero-filled past C.
+ * ---------------------------------------------------------------------------------- */
+typedef struct HvrIGemm {
+  /* A operand view, element strides (bf16 elements); stride of C is 1 */
+  const hvr_bf16* a_hi;
+  const hvr_bf16* a_lo;
+  int a_c, a_w, a_h, a_b;                 /* sizes of the view                          */
+  int64_t a_stride_w, a_stride_h, a_stride_b;
+  /* taps */
+  int ntaps;
+  int tap_dx[9], tap_dy[9];
+  /* output pixel grid and M tiling: tile = tile_w x tile_h pixels, tile_w*tile_h == 128 */
+  int out_w, out_h, batch;
+  int tile_w, tile_h;
+  /* B operand: weights [n, ntaps*a_c] K-major, leading dimension ldb (elements) */
+  const hvr_bf16* b_hi;
+  const hvr_bf16* b_lo;
+  int n;
+  int64_t ldb;
+  /* epilogue */
+  float alpha;
+  const float* bias;                      /* [n] or NULL                                */
+  const hvr_bf16* res_hi;                 /* residual [rows, ld_res] split, or NULL     */
+  const hvr_bf16* res_lo;
+  int64_t ld_res;
+  int relu;
+  hvr_bf16* out_hi;                       /* [rows, ld_out] split, or NULL              */
+  hvr_bf16* out_lo;
+  int64_t ld_out;
+  float* out_f32;                         /* [rows, ld_f32] fp32, or NULL               */
+  int64_t ld_f32;
+  hvr_bf16* outT_hi;                      /* transposed [n, ld_outT] split, or NULL     */
+  hvr_bf16* outT_lo;
+  int64_t ld_outT;
+  int passes;                             /* 3 = hi*hi+hi*lo+lo*hi (default), 1 = hi*hi */
+} HvrIGemm;
+
+/* tcgen05 / TMEM / TMA kernel.  rows = batch*out_h*out_w. */
+int hvr_igemm(const HvrIGemm* g, void* stream);
+/* fp32 SIMT evaluation of the same descriptor (one thread per output, fmaf in k order):
+ * the on-device cross-check used by the tests at sizes the CPU oracle cannot reach. */
+int hvr_igemm_check(const HvrIGemm* g, void* stream);
+
+/* Stem helpers (resnet.py:522-527): 7x7/2 pad 3 conv as im2col (K = 147 -> 192, zero padded)
+ * feeding hvr_igemm, and the 3x3/2 pad 1 max-pool on split NHWC. */
+int hvr_im2col_stem(const float* img_nchw, int B, int H, int W, hvr_bf16* hi, hvr_bf16* lo,
+                    int out_h, int out_w, void* stream);
+int hvr_maxpool3x3s2_split(const hvr_bf16* hi, const hvr_bf16* lo, int B, int H, int W, int C,
+                           hvr_bf16* ohi, hvr_bf16* olo, int out_h, int out_w, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * RoIAlign forward.  Replaces roi_align_cuda.forward (roi_align_cuda.cpp:27-53) /
+ * ROIAlignForward (roi_align_kernel.cu:63-118): legacy geometry (roi_end = (x2+1)*scale,
+ * no half-pixel shift), sample_num^2 bilinear samples per bin, strict IEEE fp32 in the
+ * reference's operation order.
+ *   feat  : NHWC fp32 [n_imgs, H, W, C] (feat_nhwc=1) or NCHW fp32 (feat_nhwc=0; transposed
+ *           into `ws`, which must hold n_imgs*H*W*C floats)
+ *   rois  : [n_rois, 5] = (batch_idx, x1, y1, x2, y2)
+ *   out   : out_layout 0 -> [n_rois, C, ph, pw] fp32 (the reference's layout)
+ *           out_layout 1 -> [n_rois, ph, pw, C] fp32
+ *   out_hi/out_lo (optional, out_layout 1 order, row pitch ld_split elements): split copy
+ *           feeding fc_new_1 directly.
+ * Returns HVR_ERR_ARG for a roi whose batch index is outside [0, n_imgs) only in the
+ * debug build; the release kernel clamps (the reference reads out of bounds).
+ * ---------------------------------------------------------------------------------- */
+int hvr_roi_align_fwd(const float* feat, int feat_nhwc, const float* rois, int n_rois, int n_imgs,
+                      int C, int H, int W, int ph, int pw, float spatial_scale, int sample_num,
+                      float* out, int out_layout, hvr_bf16* out_hi, hvr_bf16* out_lo,
+                      int64_t ld_split, float* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * NMS.  Replaces nms_cuda.nms (nms_kernel.cu:71-136, strict `>`; strict_gt=0 gives
+ * nms_cpu.cpp:55's `>=`).  Device-resident: no D2H copy, no host scan.
+ *   dets    : [n, 5] (x1,y1,x2,y2,score) fp32
+ *   keep    : [n] int64, receives kept ORIGINAL indices, ascending (nms_kernel.cu:132-135)
+ *   n_keep  : device int32
+ *   total order of the internal sort: score descending, index ascending.
+ *   ws      : hvr_nms_workspace_bytes(n) bytes
+ * ---------------------------------------------------------------------------------- */
+size_t hvr_nms_workspace_bytes(int n);
+int hvr_nms(const float* dets, int n, float iou_thr, int strict_gt, int64_t* keep, int* n_keep,
+            void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * RPN proposal generation for T frames in one call.  Replaces the per-frame Python loop
+ * AnchorHead.get_bboxes / RPNHead.get_bboxes_single (anchor_head.py:209-278,
+ * rpn_head.py:55-104) incl. AnchorGenerator.grid_anchors (anchor_generator.py:66-83),
+ * delta2bbox (transforms.py:34-111) and nms (nms_kernel.cu).
+ *   cls     : [T, H*W*A] fp32 logits, order (y, x, a)   (= permute(1,2,0) of the reference)
+ *   reg     : [T, H*W*A, 4] fp32 deltas, same order; ld_cls / ld_reg = row pitch in floats
+ *             of one (y,x) cell (A resp. 4A when dense) so NHWC conv outputs with padded
+ *             channel counts can be passed as they are
+ *   base_anchors : [A,4] fp32 (rounded base anchors), stride = anchor stride
+ *   img_h/img_w  : clamp shape (img_shape, unpadded)
+ *   proposals    : [T, max_num, 5] (x1,y1,x2,y2,score), score-ordered; rows >= count are 0
+ *   counts       : [T] int32
+ *   top_idx (optional) : [T, max_num] int32 anchor index of every proposal (tests)
+ * ---------------------------------------------------------------------------------- */
+size_t hvr_rpn_workspace_bytes(int T, int n_anchors, int nms_pre);
+int hvr_rpn_proposals(const float* cls, int64_t ld_cls, const float* reg, int64_t ld_reg, int T,
+                      int H, int W, int A, const float* base_anchors, int stride, float img_h,
+                      float img_w, int nms_pre, int nms_post, int max_num, float nms_thr,
+                      float* proposals, int* counts, int* top_idx, void* ws, size_t ws_bytes,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Detection post-processing for one head output.  Replaces BBoxHead.get_det_bboxes
+ * (hrnmp_bbox_head.py:1009-1052, bbox_head.py:132-169) + multiclass_nms
+ * (core/post_processing/bbox_nms.py:6-66): softmax over classes, class-agnostic
+ * delta2bbox (stds given), optional division by scale_factor, per-class NMS (score > thr,
+ * IoU > iou_thr), concatenation by class with rows in ascending roi order, top max_per_img
+ * by score (score desc, position asc).
+ *   rois [n,5] (batch,x1,y1,x2,y2); cls [n, n_cls] (ld_cls); reg [n,4] (ld_reg)
+ *   dets [max_per_img, 5], labels [max_per_img] int64 (0-based class), n_dets device int32
+ * ---------------------------------------------------------------------------------- */
+size_t hvr_det_workspace_bytes(int n, int n_cls);
+int hvr_det_postprocess(const float* rois, const float* cls, int64_t ld_cls, const float* reg,
+                        int64_t ld_reg, int n, int n_cls, const float* stds4_host, float img_h,
+                        float img_w, float scale_factor, int rescale, float score_thr,
+                        float iou_thr, int max_per_img, float* dets, int64_t* labels, int* n_dets,
+                        void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Relation-head row softmax (hrnmp_bbox_head.py:332): P = softmax(S, dim=keys), written
+ * as split bf16 for the P.V contraction.  S [rows, ld_s] fp32, P [rows, ld_p].
+ * Columns [cols, ld_p) of P are zero-filled.
+ * ---------------------------------------------------------------------------------- */
+int hvr_softmax_rows_split(const float* S, int rows, int cols, int64_t ld_s, hvr_bf16* p_hi,
+                           hvr_bf16* p_lo, int64_t ld_p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HVR_B200_H_ */

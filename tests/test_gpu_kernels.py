@@ -1,0 +1,302 @@
+"""Kernel-level parity on the GPU: every C-ABI entry point against the CPU oracle
+(oracle/) on the same seeded inputs.  Integer / index outputs are compared bit-exactly,
+fp32 outputs within the tolerance written next to each assert."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# ---------------------------------------------------------------------------------------
+# split-bf16 storage
+# ---------------------------------------------------------------------------------------
+def test_split_merge_roundtrip(cuda):
+    from hvrnet_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(100003, generator=g) * torch.logspace(-3, 3, 100003)).to(cuda)
+    s = ops.split(x)
+    y = ops.merge(s)
+    # hi + lo carries >= 16 mantissa bits: relative error <= 2^-16 per element
+    assert float(((y - x).abs() / x.abs().clamp_min(1e-30)).max()) < 2.0 ** -16
+    assert torch.equal(s.hi, x.to(torch.bfloat16))
+
+
+def test_layout_roundtrip(cuda):
+    from hvrnet_b200 import ops
+    x = torch.randn(2, 37, 5, 9, device=cuda)
+    assert torch.equal(ops.nhwc_to_nchw(ops.nchw_to_nhwc(x)), x)
+    s = ops.nchw_to_nhwc_split(x)
+    assert s.hi.shape == (2, 5, 9, 37)
+    y = ops.nhwc_split_to_nchw(s)
+    assert _rel(y, x) < 2.0 ** -16
+
+
+# ---------------------------------------------------------------------------------------
+# implicit GEMM (tcgen05) against fp64 torch on the merged operands
+# ---------------------------------------------------------------------------------------
+def _ref_linear(a, w, n, bias, res, relu, alpha):
+    A = a.float().double().cpu()
+    W = w.float().double().cpu()[:n, :A.shape[1]]
+    y = alpha * (A @ W.t())
+    if bias is not None:
+        y = y + bias.double().cpu()[:n]
+    if res is not None:
+        y = y + res.float().double().cpu()[:, :n]
+    if relu:
+        y = y.clamp_min(0)
+    return y
+
+
+@pytest.mark.parametrize('M,K,N,relu,use_res,use_bias', [
+    (128, 64, 64, False, False, False),        # one tile, one K step
+    (300, 1024, 1024, True, True, True),       # relation-head shape
+    (257, 12544, 128, False, False, True),     # fc_new_1 K
+    (200, 1024, 64, False, False, True),       # narrow N (fc_cls|fc_reg padded)
+    (333, 448, 300, False, False, False),      # ragged M and N, 7 K steps
+])
+def test_igemm_linear(cuda, M, K, N, relu, use_res, use_bias):
+    from hvrnet_b200 import ops
+    g = torch.Generator().manual_seed(M + K + N)
+    a = ops.split(torch.randn(M, K, generator=g).to(cuda))
+    w = ops.split((torch.randn(ops.round_up(N, 64), K, generator=g) / math.sqrt(K)).to(cuda))
+    bias = torch.randn(ops.round_up(N, 64), generator=g).to(cuda) if use_bias else None
+    res = ops.split(torch.randn(M, ops.round_up(N, 8), generator=g).to(cuda)) if use_res else None
+    out, of, oT = ops.linear(a, w, N, bias=bias, relu=relu, res=res, alpha=0.5, want_split=True, want_f32=True,
+                             want_T=True)
+    torch.cuda.synchronize()
+    ref = _ref_linear(a, w, N, bias, res, relu, 0.5)
+    got = of[:, :N].double().cpu()
+    err = float((got - ref).abs().max() / ref.abs().max())
+    # three-product split-bf16: dropped lo*lo and a_3 terms ~2^-16 per product, fp32 accumulation
+    assert err < 3e-5, err
+    assert _rel(ops.merge(Split_rows(out))[:, :N].double().cpu(), ref) < 3e-5
+    assert _rel(ops.merge(Split_rows(oT))[:N, :M].t().double().cpu(), ref) < 3e-5
+    # the SIMT cross-check kernel evaluates the same descriptor
+    _, of2, _ = ops.linear(a, w, N, bias=bias, relu=relu, res=res, alpha=0.5, want_split=False, want_f32=True,
+                           check_kernel=True)
+    assert _rel(of2[:, :N].double().cpu(), ref) < 1e-5
+
+
+def Split_rows(s):
+    from hvrnet_b200.ops import Split
+    return Split(s.hi.contiguous(), s.lo.contiguous())
+
+
+def test_igemm_k_tail_and_single_pass(cuda):
+    """K = 200 is not a multiple of the 64-wide K tile: TMA zero-fills the tail (the P.V
+    contraction has K = number of proposals)."""
+    from hvrnet_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    M, K, N = 150, 200, 96
+    A = torch.zeros(M, 256)
+    A[:, :K] = torch.randn(M, K, generator=g)
+    B = torch.zeros(128, 256)
+    B[:N, :K] = torch.randn(N, K, generator=g)
+    a, b = ops.split(A.to(cuda)), ops.split(B.to(cuda))
+    from hvrnet_b200.ops import Split
+    av = Split(a.hi[:, :K], a.lo[:, :K])
+    bv = Split(b.hi[:, :K], b.lo[:, :K])
+    _, of, _ = ops.linear(av, bv, N, want_split=False, want_f32=True)
+    ref = (A[:, :K].double() @ B[:N, :K].double().t())
+    assert _rel(of[:, :N].double().cpu(), ref) < 3e-5
+    _, o1, _ = ops.linear(av, bv, N, want_split=False, want_f32=True, passes=1)
+    refh = a.hi[:, :K].double().cpu() @ b.hi[:N, :K].double().cpu().t()
+    assert _rel(o1[:, :N].double().cpu(), refh) < 1e-5      # single product: exact up to fp32 accumulation
+
+
+@pytest.mark.parametrize('B,H,W,C,N,k,dil,stride', [
+    (2, 38, 63, 128, 64, 3, 2, 1),      # layer4-style dilated 3x3
+    (1, 19, 31, 64, 128, 3, 1, 1),      # 3x3 pad 1
+    (2, 38, 63, 256, 128, 1, 1, 2),     # strided 1x1 (caffe bottleneck conv1 / downsample)
+    (1, 20, 24, 64, 64, 1, 1, 1),
+])
+def test_igemm_conv(cuda, B, H, W, C, N, k, dil, stride):
+    import torch.nn.functional as F
+    from hvrnet_b200 import engine, ops
+    g = torch.Generator().manual_seed(B * H + C + N + k)
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(N, C, k, k, generator=g) / math.sqrt(C * k * k)
+    bias = torch.randn(N, generator=g)
+    xs = ops.nchw_to_nhwc_split(x.to(cuda))
+    cp = engine.ConvP(engine.pack_conv(w, None, cuda), bias.to(cuda), N, k, C, dil)
+    res = torch.randn(B, N, (H - 1) // stride + 1, (W - 1) // stride + 1, generator=g)
+    rs = ops.nchw_to_nhwc_split(res.to(cuda))
+    out, of = engine.conv(xs, cp, stride=stride, relu=True, res=rs, want_f32=True)
+    torch.cuda.synchronize()
+    xm = ops.nhwc_split_to_nchw(xs).double().cpu()
+    wm = ops.merge(cp.w).double().cpu()[:N].view(N, k, k, C).permute(0, 3, 1, 2)
+    ref = F.conv2d(xm, wm, bias.double(), stride=stride, padding=dil * (k // 2), dilation=dil)
+    ref = (ref + ops.nhwc_split_to_nchw(rs).double().cpu()).clamp_min(0)
+    got = of[..., :N].permute(0, 3, 1, 2).double().cpu()
+    assert float((got - ref).abs().max() / ref.abs().max()) < 3e-5
+    got2 = ops.nhwc_split_to_nchw(out).double().cpu()
+    assert float((got2 - ref).abs().max() / ref.abs().max()) < 3e-5
+
+
+def test_stem_and_maxpool(cuda):
+    import torch.nn.functional as F
+    from hvrnet_b200 import engine, ops
+    g = torch.Generator().manual_seed(3)
+    img = torch.randn(1, 3, 70, 90, generator=g) * 50
+    w = torch.randn(64, 3, 7, 7, generator=g) * 0.02
+    col = ops.im2col_stem(img.to(cuda))
+    wp = engine.pack_matrix(w.permute(0, 2, 3, 1).reshape(64, 147), cuda, 64, 192)
+    cp = engine.ConvP(wp, None, 64, 1, 192)
+    x, _ = engine.conv(col, cp, relu=True)
+    y = ops.maxpool3x3s2(x)
+    ref = F.max_pool2d(F.relu(F.conv2d(img.double(), w.double(), stride=2, padding=3)), 3, 2, 1)
+    got = ops.nhwc_split_to_nchw(y).double().cpu()
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max() / ref.abs().max()) < 5e-5
+
+
+# ---------------------------------------------------------------------------------------
+# RoIAlign: bit-exact against the C oracle
+# ---------------------------------------------------------------------------------------
+def _rois(g, n, n_imgs, w=1000., h=600.):
+    x1 = torch.rand(n, generator=g) * w
+    y1 = torch.rand(n, generator=g) * h
+    bw = torch.rand(n, generator=g) ** 2 * w * 0.6
+    bh = torch.rand(n, generator=g) ** 2 * h * 0.6
+    r = torch.stack([torch.randint(0, n_imgs, (n,), generator=g).float(), x1, y1,
+                     (x1 + bw).clamp(max=w - 1), (y1 + bh).clamp(max=h - 1)], 1)
+    r[0, 1:] = torch.tensor([-40., -30., 10., 12.])          # partly outside: OOB samples
+    r[1, 1:] = torch.tensor([990., 590., 1050., 640.])       # beyond the map: all-zero bins
+    r[2, 1:] = torch.tensor([100., 100., 100., 100.])        # degenerate 1-pixel roi
+    r[3, 1:] = torch.tensor([300., 200., 200., 100.])        # x2 < x1: width clamps to 0
+    return r
+
+
+def test_roi_align_bit_exact(cuda):
+    from hvrnet_b200 import ops
+    from oracle import cref
+    g = torch.Generator().manual_seed(11)
+    feat = torch.randn(3, 256, 38, 63, generator=g)
+    rois = _rois(g, 120, 3)
+    ref = cref.roi_align(feat, rois)
+    out = ops.roi_align(feat.to(cuda), rois.to(cuda))
+    assert torch.equal(out.cpu(), ref)
+    # NHWC in / NHWC out + split copy (the pipeline's variant)
+    fn = ops.nchw_to_nhwc(feat.to(cuda))
+    o2, sp = ops.roi_align(fn, rois.to(cuda), feat_nhwc=True, out_nhwc=True, want_split=True)
+    assert torch.equal(o2.permute(0, 3, 1, 2).cpu(), ref)
+    m = ops.merge(sp).view(-1, 7, 7, 256).permute(0, 3, 1, 2).cpu()
+    assert float((m - ref).abs().max()) <= float(ref.abs().max()) * 2.0 ** -16
+
+
+def test_roi_align_gradcheck_recipe_and_empty(cuda):
+    """Input recipe of mmdet/ops/roi_align/gradcheck.py:11-30 (15x15 maps, scale 1/8)."""
+    from hvrnet_b200 import ops
+    from oracle import cref
+    g = torch.Generator().manual_seed(2)
+    feat = torch.randn(2, 16, 15, 15, generator=g)
+    rois = torch.tensor([[0, 0, 0, 50, 50], [0, 10, 30, 43, 55], [1, 67, 40, 110, 120]], dtype=torch.float32)
+    ref = cref.roi_align(feat, rois, out_size=2, spatial_scale=1 / 8., sample_num=2)
+    out = ops.roi_align(feat.to(cuda), rois.to(cuda), out_size=2, spatial_scale=1 / 8., sample_num=2)
+    assert torch.equal(out.cpu(), ref)
+    ref0 = cref.roi_align(feat, rois, out_size=3, spatial_scale=1 / 8., sample_num=0)     # adaptive sampling
+    out0 = ops.roi_align(feat.to(cuda), rois.to(cuda), out_size=3, spatial_scale=1 / 8., sample_num=0)
+    assert torch.equal(out0.cpu(), ref0)
+    e = ops.roi_align(feat.to(cuda), rois[:0].to(cuda))
+    assert e.shape == (0, 16, 7, 7)
+
+
+# ---------------------------------------------------------------------------------------
+# NMS: bit-exact indices
+# ---------------------------------------------------------------------------------------
+def _dets(g, n, spread=400.):
+    c = torch.rand(n, 2, generator=g) * spread
+    wh = torch.rand(n, 2, generator=g) * 120 + 4
+    s = torch.rand(n, generator=g)
+    return torch.cat([c - wh / 2, c + wh / 2, s[:, None]], 1)
+
+
+def test_nms_doctest(cuda):
+    """mmdet/ops/nms/nms_wrapper.py:25-35."""
+    from hvrnet_b200 import ops
+    d = torch.tensor([[49.1, 32.4, 51.0, 35.9, 0.9], [49.3, 32.9, 51.0, 35.3, 0.9], [49.2, 31.8, 51.0, 35.4, 0.5],
+                      [35.1, 11.5, 39.1, 15.7, 0.5], [35.6, 11.8, 39.3, 14.2, 0.5], [35.3, 11.5, 39.9, 14.5, 0.4],
+                      [35.2, 11.7, 39.7, 15.7, 0.3]])
+    assert ops.nms(d.to(cuda), 0.7).cpu().tolist() == [0, 3, 4]
+    assert ops.nms(d[:0].to(cuda), 0.7).numel() == 0
+
+
+@pytest.mark.parametrize('n,thr', [(1, 0.5), (63, 0.3), (64, 0.5), (65, 0.7), (1000, 0.3), (6000, 0.7)])
+def test_nms_bit_exact(cuda, n, thr):
+    from hvrnet_b200 import ops
+    from oracle import cref
+    g = torch.Generator().manual_seed(n)
+    d = _dets(g, n, spread=300. if n < 2000 else 900.)
+    d[::7, 4] = d[0, 4]                                   # score ties: total order = index ascending
+    for strict in (True, False):
+        ref = cref.nms(d, thr, strict_gt=strict)
+        got = ops.nms(d.to(cuda), thr, strict_gt=strict).cpu()
+        assert torch.equal(got, ref)
+
+
+# ---------------------------------------------------------------------------------------
+# RPN proposals: bit-exact anchor indices, boxes to 1e-4 px
+# ---------------------------------------------------------------------------------------
+def test_rpn_proposals(cuda):
+    from hvrnet_b200 import ops
+    from oracle import ref_torch as R
+    g = torch.Generator().manual_seed(21)
+    T, H, W, A = 3, 38, 63, 12
+    cls = torch.randn(T, A, H, W, generator=g) * 3
+    reg = torch.randn(T, 4 * A, H, W, generator=g) * 0.3
+    cls[0, :, :4, :4] = 40.0                              # saturated sigmoid: ties in score, not in logit order
+    base = R.gen_base_anchors(16, (4, 8, 16, 32), (0.5, 1.0, 2.0))
+    anchors = R.grid_anchors(base, (H, W), 16)
+    packed = torch.cat([cls.permute(0, 2, 3, 1), reg.permute(0, 2, 3, 1),
+                        torch.zeros(T, H, W, 4)], -1).contiguous().to(cuda)      # [T,H,W,64] like the RPN GEMM output
+    props, counts, idx = ops.rpn_proposals(packed, packed.view(-1)[A:], 64, 64, T, H, W, A, base.to(cuda), 16,
+                                           (600, 1000), want_idx=True)
+    for t in range(T):
+        ref, ridx = R.rpn_proposals_single(cls[t], reg[t], anchors, (600, 1000), return_aux=True)
+        k = int(counts[t])
+        assert k == ref.shape[0]
+        assert torch.equal(idx[t, :k].cpu().long(), ridx)
+        assert float((props[t, :k].cpu() - ref).abs().max()) < 1e-3
+        assert float((props[t, :k, 4].cpu() - ref[:, 4]).abs().max()) < 1e-6
+        assert float(props[t, k:].abs().sum()) == 0
+
+
+# ---------------------------------------------------------------------------------------
+# detection post-processing
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n,scale,rescale,boost', [(300, 1.0, False, 0.0), (300, 1.6, True, 0.0), (37, 1.0, True, 0.0),
+                                                   (300, 1.0, False, 6.0)])
+def test_det_postprocess(cuda, n, scale, rescale, boost):
+    from hvrnet_b200 import ops
+    from oracle import ref_torch as R
+    g = torch.Generator().manual_seed(n + int(scale * 10))
+    d = _dets(g, n, spread=500.)
+    rois = torch.cat([torch.zeros(n, 1), d[:, :4]], 1)
+    cls = torch.randn(n, 31, generator=g) * 2
+    cls[:, 1:] += boost - 3.0            # boost>0: many classes pass the threshold -> >300 candidates -> top-k branch
+    reg = torch.randn(n, 4, generator=g) * 0.5
+    dets_ref, labels_ref = R.get_det_bboxes(rois, [cls], [reg], (600, 1000), scale, rescale)
+    dets, labels, nd = ops.det_postprocess(rois.to(cuda), cls.to(cuda), reg.to(cuda), (600, 1000), scale, rescale)
+    k = int(nd)
+    assert k == dets_ref[0].shape[0]
+    assert torch.equal(labels[:k].cpu(), labels_ref[0])
+    assert float((dets[:k, :4].cpu() - dets_ref[0][:, :4]).abs().max()) < 1e-3
+    assert float((dets[:k, 4].cpu() - dets_ref[0][:, 4]).abs().max()) < 1e-6
+
+
+def test_softmax_rows(cuda):
+    from hvrnet_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    for rows, cols in [(5, 17), (300, 4500), (7, 9000)]:
+        S = torch.randn(rows, ops.round_up(cols, 4), generator=g) * 3
+        P = ops.softmax_rows_split(S.to(cuda), cols)
+        ref = torch.softmax(S[:, :cols].double(), 1)
+        got = ops.merge(P)[:, :cols].double().cpu()
+        assert float((got - ref).abs().max() / ref.max()) < 1e-5
+        assert float(ops.merge(P)[:, cols:].abs().sum()) == 0

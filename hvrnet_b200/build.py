@@ -14,7 +14,7 @@ OBJ = os.path.join(HERE, 'csrc', '_obj')
 LIB = os.path.join(HERE, 'libhvr_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
-COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden',
+COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC',
           '--expt-relaxed-constexpr']
 # file -> extra flags.  -fmad=false: the parity contract of RoIAlign / box decoding / IoU is
 # "every product and sum rounded once" (oracle/c/hvr_oracle.c is built with -ffp-contract=off).

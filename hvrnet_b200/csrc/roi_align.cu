@@ -197,13 +197,13 @@ extern "C" int hvr_roi_align_fwd(const float* feat, int feat_nhwc, const float* 
                                  int H, int W, int ph, int pw, float spatial_scale, int sample_num, float* out,
                                  int out_layout, hvr_bf16* out_hi, hvr_bf16* out_lo, int64_t ld_split, float* ws,
                                  void* stream) {
+  if (n_rois == 0) return HVR_OK;   // empty in, empty out (the caller's output tensor has no rows)
   if (!feat || !rois || n_rois < 0 || n_imgs < 1 || C < 1 || H < 1 || W < 1 || ph < 1 || pw < 1) return HVR_ERR_ARG;
   if (!out && !out_hi) return HVR_ERR_ARG;
   if ((out_hi == nullptr) != (out_lo == nullptr)) return HVR_ERR_ARG;
   if (out_layout != 0 && out_layout != 1) return HVR_ERR_ARG;
   if (out_hi && (out_layout != 1 || ld_split < (int64_t)ph * pw * C || ld_split % 4 != 0)) return HVR_ERR_ARG;
   if ((size_t)H * W * C >= (1u << 31)) return HVR_ERR_ARG;
-  if (n_rois == 0) return HVR_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (!feat_nhwc) {
     if (!ws) return HVR_ERR_WORKSPACE;

@@ -206,7 +206,7 @@ def linear(a, w, n, bias=None, relu=False, res=None, alpha=1.0, want_split=True,
 # ----------------------------------------------------------------------------------------
 
 def roi_align(feat, rois, out_size=7, spatial_scale=1 / 16., sample_num=2, feat_nhwc=False, out_nhwc=False,
-              want_split=False, ld_split=None):
+              want_split=False, ld_split=None, want_f32=True):
     """feat fp32 NCHW (reference layout) or NHWC; rois [n,5].  Returns fp32 output in the
     reference layout [n,C,ph,pw] (or [n,ph,pw,C] when out_nhwc), plus an optional Split
     [n, ld_split] copy in NHWC order."""
@@ -220,7 +220,9 @@ def roi_align(feat, rois, out_size=7, spatial_scale=1 / 16., sample_num=2, feat_
     n = rois.shape[0]
     ph = pw = int(out_size)
     dev = feat.device
-    out = torch.empty((n, ph, pw, C) if out_nhwc else (n, C, ph, pw), dtype=torch.float32, device=dev)
+    out = None
+    if want_f32:
+        out = torch.empty((n, ph, pw, C) if out_nhwc else (n, C, ph, pw), dtype=torch.float32, device=dev)
     sp = None
     if want_split:
         assert out_nhwc

@@ -181,9 +181,26 @@ def igemm_desc(a, b, n, *, taps=((0, 0),), a_view=None, out_whb=None, tile=None,
     return g
 
 
+# When set to a list, every hvr_igemm launch is bracketed by CUDA events on the launching
+# stream and (start, end, algorithmic_flops) is appended (bench.py's roofline leg).
+PROFILE = None
+
+
+def igemm_flops(g):
+    """Algorithmic FLOPs of one descriptor: 2 * rows * n * (ntaps * C)  (FLOP = 2 MAC)."""
+    return 2.0 * g.batch * g.out_h * g.out_w * g.n * g.ntaps * g.a_c
+
+
 def igemm_run(g, check_kernel=False):
     fn = _lib.lib().hvr_igemm_check if check_kernel else _lib.lib().hvr_igemm
+    if PROFILE is None:
+        check(fn(ctypes.byref(g), _stream()), 'hvr_igemm')
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(fn(ctypes.byref(g), _stream()), 'hvr_igemm')
+    e1.record()
+    PROFILE.append((e0, e1, igemm_flops(g)))
 
 
 def linear(a, w, n, bias=None, relu=False, res=None, alpha=1.0, want_split=True, want_f32=False, want_T=False,

@@ -6,14 +6,17 @@
 // the reference hot path (resnet.py:222-257, res_layer.py:67-74, rpn_head.py:30-35,
 // hrnmp_bbox_head.py:283-294,342-350,827-906).  See include/hvr_b200.h (HvrIGemm).
 //
-// One CTA = one 128 x BN output tile.  6 warps:
+// Persistent CTAs (one per SM) walk 128 x BN output tiles (BN = 64 / 128 / 256), N-fastest.  6 warps:
 //   warp 0    TMA producer (one lane): per K step loads A_hi, A_lo (4-D box = tile_w x tile_h
 //             pixels x 64 channels at the tap's offset; out-of-range pixels arrive as zeros =
 //             conv padding) and B_hi, B_lo (BN x 64) into a STAGES-deep ring
 //   warp 1    TMEM allocator + MMA issuer (one lane): 4 x UMMA_K=16 per 64-wide K step, three
 //             products per step, tcgen05.commit frees the stage / signals the epilogue
 //   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns -> alpha, bias, residual, ReLU ->
-//             split-bf16 / fp32 / transposed stores
+//             split-bf16 / fp32 / transposed stores; two TMEM accumulator buffers, so the
+//             epilogue of tile i overlaps the main loop of tile i+1
+// Launched with programmatic stream serialization (PDL): barrier init / TMEM alloc / descriptor
+// prefetch overlap the tail of the previous kernel.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -37,7 +40,7 @@ struct alignas(64) KParams {
   int C, cblocks;
   int tile_w, tile_h, tiles_x, tiles_y;
   int out_w, out_h, batch;
-  int n;
+  int n, n_tiles;
   int passes;
   int relu;
   float alpha;
@@ -61,6 +64,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (BN == 64) ? 4 : (BN == 128 ? 3 : 2);
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BN;   // two accumulator buffers: epilogue(i) overlaps mainloop(i+1)
 };
 
 // Epilogue for 32 consecutive columns of one output row.
@@ -165,6 +169,9 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t 
   }
 }
 
+// Persistent kernel: grid = min(#tiles, #SMs); CTA c processes tiles c, c+grid, ...  Tile index
+// runs N-fastest so the CTAs in flight share the same A (activation) tiles through L2 while
+// the (small) weight matrix stays L2-resident.
 template <int BN>
 __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant__ KParams p) {
   using C_ = Cfg<BN>;
@@ -176,21 +183,16 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
   uint8_t* tiles = smem_raw + pad;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + STAGES * C_::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  const int m_tile = blockIdx.x;
-  const int tx = m_tile % p.tiles_x;
-  const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-  const int bimg = m_tile / (p.tiles_x * p.tiles_y);
-  const int x0 = tx * p.tile_w;
-  const int y0 = ty * p.tile_h;
-  const int n0 = blockIdx.y * BN;
   const int total_k = p.ntaps * p.cblocks;
   const bool three = p.passes >= 3;
+  const int n_tiles = p.n_tiles;
+  const int num_tiles = p.tiles_x * p.tiles_y * p.batch * n_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA_hi);
@@ -203,38 +205,53 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 4);   // one arrival per epilogue warp
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, BN);
+    tmem_alloc(tmem_ptr_smem, C_::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // Programmatic dependent launch: everything above overlapped the previous kernel's tail;
+  // from here on we touch global memory it may have produced.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       const uint32_t stage_tx = three ? (uint32_t)C_::STAGE_BYTES : (uint32_t)(A_BYTES + C_::B_BYTES);
       int it = 0;
-      for (int tap = 0; tap < p.ntaps; ++tap) {
-        const int ax = x0 + p.tap_dx[tap];
-        const int ay = y0 + p.tap_dy[tap];
-        for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (uint32_t)((it / STAGES) & 1);
-          mbar_wait(&empty_bar[s], ph ^ 1u);
-          uint8_t* st = tiles + s * C_::STAGE_BYTES;
-          mbar_expect_tx(&full_bar[s], stage_tx);
-          const int kc = cb * BK;
-          tma_load_4d(st, &p.tmA_hi, &full_bar[s], kc, ax, ay, bimg);
-          tma_load_2d(st + 2 * A_BYTES, &p.tmB_hi, &full_bar[s], tap * p.C + kc, n0);
-          if (three) {
-            tma_load_4d(st + A_BYTES, &p.tmA_lo, &full_bar[s], kc, ax, ay, bimg);
-            tma_load_2d(st + 2 * A_BYTES + C_::B_BYTES, &p.tmB_lo, &full_bar[s], tap * p.C + kc, n0);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % n_tiles;
+        const int m_tile = tile / n_tiles;
+        const int tx = m_tile % p.tiles_x;
+        const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+        const int bimg = m_tile / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * p.tile_w, y0 = ty * p.tile_h, n0 = nt * BN;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int ax = x0 + p.tap_dx[tap];
+          const int ay = y0 + p.tap_dy[tap];
+          for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            uint8_t* st = tiles + s * C_::STAGE_BYTES;
+            mbar_expect_tx(&full_bar[s], stage_tx);
+            const int kc = cb * BK;
+            tma_load_4d(st, &p.tmA_hi, &full_bar[s], kc, ax, ay, bimg);
+            tma_load_2d(st + 2 * A_BYTES, &p.tmB_hi, &full_bar[s], tap * p.C + kc, n0);
+            if (three) {
+              tma_load_4d(st + A_BYTES, &p.tmA_lo, &full_bar[s], kc, ax, ay, bimg);
+              tma_load_2d(st + 2 * A_BYTES + C_::B_BYTES, &p.tmB_lo, &full_bar[s], tap * p.C + kc, n0);
+            }
           }
         }
       }
@@ -242,53 +259,74 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
   } else if (warp == 1) {
     // ================= MMA issuer =================
     constexpr uint32_t idesc = umma_idesc_bf16(BN);
-    for (int it = 0; it < total_k; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)((it / STAGES) & 1);
-      mbar_wait(&full_bar[s], ph);
+    int it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int ab = lt & 1;
+      const uint32_t aph = (uint32_t)((lt >> 1) & 1);
+      mbar_wait(&tmem_empty_bar[ab], aph ^ 1u);          // epilogue has drained this accumulator
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t st = smem_u32(tiles + s * C_::STAGE_BYTES);
-        const uint64_t a_hi = umma_desc_k_sw128(st);
-        const uint64_t a_lo = umma_desc_k_sw128(st + A_BYTES);
-        const uint64_t b_hi = umma_desc_k_sw128(st + 2 * A_BYTES);
-        const uint64_t b_lo = umma_desc_k_sw128(st + 2 * A_BYTES + C_::B_BYTES);
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(ab * BN);
+      for (int kk = 0; kk < total_k; ++kk, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = smem_u32(tiles + s * C_::STAGE_BYTES);
+          const uint64_t a_hi = umma_desc_k_sw128(st);
+          const uint64_t a_lo = umma_desc_k_sw128(st + A_BYTES);
+          const uint64_t b_hi = umma_desc_k_sw128(st + 2 * A_BYTES);
+          const uint64_t b_lo = umma_desc_k_sw128(st + 2 * A_BYTES + C_::B_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advancing 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in the (addr>>4) field
-          const uint64_t ko = (uint64_t)(k * 2);
-          tc_mma_f16(tmem_base, a_hi + ko, b_hi + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          if (three) {
-            tc_mma_f16(tmem_base, a_hi + ko, b_lo + ko, idesc, 1u);
-            tc_mma_f16(tmem_base, a_lo + ko, b_hi + ko, idesc, 1u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // advancing 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in the (addr>>4) field
+            const uint64_t ko = (uint64_t)(k * 2);
+            tc_mma_f16(tmem_acc, a_hi + ko, b_hi + ko, idesc, (kk > 0 || k > 0) ? 1u : 0u);
+            if (three) {
+              tc_mma_f16(tmem_acc, a_hi + ko, b_lo + ko, idesc, 1u);
+              tc_mma_f16(tmem_acc, a_lo + ko, b_hi + ko, idesc, 1u);
+            }
           }
+          tc_commit(&empty_bar[s]);                             // frees the stage when the MMAs retire
+          if (kk == total_k - 1) tc_commit(&tmem_full_bar[ab]);  // accumulator complete
         }
-        tc_commit(&empty_bar[s]);                       // frees the stage when the MMAs retire
-        if (it == total_k - 1) tc_commit(tmem_full_bar);  // accumulator complete
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ================= epilogue =================
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int m = q * 32 + lane;
-    const int px = x0 + m % p.tile_w;
-    const int py = y0 + m / p.tile_w;
-    const bool row_ok = (px < p.out_w) && (py < p.out_h);
-    const long long row = ((long long)bimg * p.out_h + py) * p.out_w + px;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int nt = tile % n_tiles;
+      const int m_tile = tile / n_tiles;
+      const int tx = m_tile % p.tiles_x;
+      const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+      const int bimg = m_tile / (p.tiles_x * p.tiles_y);
+      const int px = tx * p.tile_w + m % p.tile_w;
+      const int py = ty * p.tile_h + m / p.tile_w;
+      const bool row_ok = (px < p.out_w) && (py < p.out_h);
+      const long long row = ((long long)bimg * p.out_h + py) * p.out_w + px;
+      const int ab = lt & 1;
+      const uint32_t aph = (uint32_t)((lt >> 1) & 1);
+      mbar_wait(&tmem_full_bar[ab], aph);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t acc[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
-      tmem_ld_wait();
-      epilogue_chunk(p, acc, row, n0 + c0, row_ok);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0), acc);
+        tmem_ld_wait();
+        epilogue_chunk(p, acc, row, nt * BN + c0, row_ok);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[ab]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (warp == 1) tmem_dealloc(tmem_base, C_::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------
@@ -417,6 +455,8 @@ int validate(const HvrIGemm* g) {
   return HVR_OK;
 }
 
+int g_force_bn = 0;   // test hook (hvr_debug_force_bn): 0 = heuristic
+
 template <int BN>
 int launch(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
   static bool attr_set = false;
@@ -434,8 +474,25 @@ int launch(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
     rc = make_map(&kp.tmB_lo, g->b_lo, 2, bdims, bstr, bbox);
     if (rc) return rc;
   }
-  dim3 grid(kp.tiles_x * kp.tiles_y * kp.batch, hvr_cdiv(g->n, BN));
-  igemm_tc_kernel<BN><<<grid, 192, Cfg<BN>::SMEM, st>>>(kp);
+  kp.n_tiles = hvr_cdiv(g->n, BN);
+  const long long num_tiles = (long long)kp.tiles_x * kp.tiles_y * kp.batch * kp.n_tiles;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    HVR_CUDA(cudaGetDevice(&dev));
+    HVR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(num_tiles < num_sms ? num_tiles : num_sms));
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = Cfg<BN>::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  HVR_CUDA(cudaLaunchKernelEx(&cfg, igemm_tc_kernel<BN>, kp));
   HVR_LAUNCHED();
   return HVR_OK;
 }
@@ -487,8 +544,25 @@ extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
   kp.outT_lo = reinterpret_cast<__nv_bfloat16*>(g->outT_lo);
   kp.ld_outT = g->ld_outT;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (g->n <= 64) return launch<64>(g, kp, st);
+  // Tile width: 256 when the problem still fills the machine (halves the A traffic per FLOP),
+  // 64 for narrow outputs or when 128-wide tiles would leave most SMs idle.
+  const long long m_tiles = (long long)kp.tiles_x * kp.tiles_y * kp.batch;
+  int bn = g_force_bn;
+  if (bn == 0) {
+    if (g->n <= 64) bn = 64;
+    else if (g->n % 256 == 0 && m_tiles * (g->n / 256) >= 2 * 148) bn = 256;
+    else if (m_tiles * hvr_cdiv(g->n, 128) < 100 && g->n >= 128) bn = 64;
+    else bn = 128;
+  }
+  if (bn == 64) return launch<64>(g, kp, st);
+  if (bn == 256) return launch<256>(g, kp, st);
   return launch<128>(g, kp, st);
+}
+
+extern "C" int hvr_debug_force_bn(int bn) {
+  if (bn != 0 && bn != 64 && bn != 128 && bn != 256) return HVR_ERR_ARG;
+  g_force_bn = bn;
+  return HVR_OK;
 }
 
 extern "C" int hvr_igemm_check(const HvrIGemm* g, void* stream) {

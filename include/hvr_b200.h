@@ -117,6 +117,8 @@ typedef struct HvrIGemm {
 
 /* tcgen05 / TMEM / TMA kernel.  rows = batch*out_h*out_w. */
 int hvr_igemm(const HvrIGemm* g, void* stream);
+/* Test hook: force the N tile width of hvr_igemm (64, 128, 256; 0 = heuristic). */
+int hvr_debug_force_bn(int bn);
 /* fp32 SIMT evaluation of the same descriptor (one thread per output, fmaf in k order):
  * the on-device cross-check used by the tests at sizes the CPU oracle cannot reach. */
 int hvr_igemm_check(const HvrIGemm* g, void* stream);

@@ -83,6 +83,26 @@ def test_igemm_linear(cuda, M, K, N, relu, use_res, use_bias):
     assert _rel(of2[:, :N].double().cpu(), ref) < 1e-5
 
 
+@pytest.mark.parametrize('bn', [64, 128, 256])
+def test_igemm_tile_widths(cuda, bn):
+    """Every N-tile instantiation of the persistent kernel on a multi-tile, multi-wave problem
+    (more tiles than SMs, so each CTA walks several tiles through both TMEM buffers)."""
+    from hvrnet_b200 import _lib, ops
+    g = torch.Generator().manual_seed(bn)
+    M, K, N = 128 * 41 + 17, 320, 768
+    a = ops.split(torch.randn(M, K, generator=g).to(cuda))
+    w = ops.split((torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda))
+    bias = torch.randn(N, generator=g).to(cuda)
+    assert _lib.lib().hvr_debug_force_bn(bn) == 0
+    try:
+        _, of, _ = ops.linear(a, w, N, bias=bias, relu=True, want_split=False, want_f32=True)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().hvr_debug_force_bn(0)
+    ref = _ref_linear(a, w, N, bias, None, True, 1.0)
+    assert _rel(of.double().cpu(), ref) < 3e-5
+
+
 def Split_rows(s):
     from hvrnet_b200.ops import Split
     return Split(s.hi.contiguous(), s.lo.contiguous())

@@ -39,6 +39,8 @@ def parse():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='hrnmp', choices=['hrnmp', 'selsa', 'faster_rcnn'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--eager', action='store_true', help='disable CUDA graphs (per-kernel Python launches)')
+    ap.add_argument('--gemm-report', default=None, help='write a per-shape table of the igemm launches (csv)')
     return ap.parse_args()
 
 
@@ -190,13 +192,18 @@ def main():
         return dq
 
     def step(dq, i, from_host):
-        img = host[T + i % pool].to(dev, non_blocking=True) if from_host else devf[T + i % pool]
+        if from_host:
+            img = host[T + i % pool] if model._runner is not None else host[T + i % pool].to(dev, non_blocking=True)
+        else:
+            img = devf[T + i % pool]
         if args.workload == 'faster_rcnn':
             return model(img=[img], img_meta=[[metas[0]]], return_loss=False, rescale=True)
         dq.append(model(img=img, img_meta=[metas[0]], backbone_feat=True)[0])
         return model(x=list(dq), img=None, img_meta=metas, forward_feat=True, return_loss=False, rescale=True)
 
     def timed(from_host, K, W, profile=False):
+        # the roofline leg brackets individual launches with events, which needs the eager path
+        model.enable_cuda_graphs(not (profile or args.eager) and args.workload != 'faster_rcnn')
         dq = prefill()
         for i in range(W):
             res = step(dq, i, from_host)
@@ -206,7 +213,7 @@ def main():
         torch.cuda.synchronize()
         if profile:
             ops.PROFILE = []
-        l0 = _lib.launch_count()
+        l0 = _lib.launch_count() + (model._runner.replayed_launches if model._runner is not None else 0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(K):
@@ -217,7 +224,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        launches = _lib.launch_count() - l0
+        launches = _lib.launch_count() + (model._runner.replayed_launches if model._runner is not None else 0) - l0
         prof, ops.PROFILE = ops.PROFILE, None
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -239,8 +246,18 @@ def main():
     fps = world * K / (ms / 1e3)
     fps_e2e = world * K / (ms_e2e / 1e3)
     # roofline of the dominant kernel (igemm_tc_kernel): algorithmic FLOPs / summed launch durations
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
-    gemm_flops = sum(f for _, _, f in prof)
+    gemm_ms = sum(p[0].elapsed_time(p[1]) for p in prof)
+    gemm_flops = sum(p[2] for p in prof)
+    if args.gemm_report and rank == 0:
+        import collections
+        agg = collections.OrderedDict()
+        for e0_, e1_, f_, shp in prof:
+            a_ = agg.setdefault(shp, [0, 0.0, 0.0])
+            a_[0] += 1; a_[1] += e0_.elapsed_time(e1_); a_[2] += f_
+        with open(args.gemm_report, 'w') as fh:
+            fh.write('M,N,K,launches_per_step,ms_per_step,algorithmic_TFLOPs\n')
+            for shp, (n_, t_, f_) in agg.items():
+                fh.write('%d,%d,%d,%.1f,%.4f,%.1f\n' % (shp[0], shp[1], shp[2], n_ / K, t_ / K, f_ / t_ / 1e9))
     peaks, peak_src = None, 'fallback (B200_PROFILING.md: 1590 TFLOP/s burst)'
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -258,7 +275,8 @@ def main():
         'config': {'workload': workload_name(args.workload, T), 'frames_per_window': T, 'proposals_per_frame': 300,
                    'input': '1x3x608x1008 fp32 per step', 'l2': 'working set (305 MB split weights + >1 GB '
                    'activations per step) exceeds the 126 MB L2; no explicit flush',
-                   'parallelism': 'replicas over videos, dp%d' % world},
+                   'parallelism': 'replicas over videos, dp%d' % world,
+                   'launch': 'eager' if (args.eager or args.workload == 'faster_rcnn') else 'cuda graphs (trunk + window)'},
         'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': frame_bytes, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': ms_e2e / K},
         'gpu_launches': int(launches),

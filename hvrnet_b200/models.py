@@ -503,8 +503,20 @@ class TwoStageDetector(nn.Module):
     def init_weights(self, pretrained=None):
         pass
 
+    _runner = None
+
+    def enable_cuda_graphs(self, flag=True):
+        """Run the trunk and the window stage through captured CUDA graphs (runtime.GraphRunner):
+        same kernels and results, two graph launches and one device->host read per key frame."""
+        from .runtime import GraphRunner
+        self._runner = GraphRunner(self) if flag else None
+        return self
+
     def extract_feat(self, img):
-        """two_stage.py:91-97 -> (C4,)."""
+        """two_stage.py:91-97 -> (C4,).  `img` may live in pinned host memory when CUDA graphs
+        are enabled (it is copied straight into the trunk graph's input buffer)."""
+        if self._runner is not None:
+            return self._runner.extract(img)
         if not img.is_cuda:
             raise HvrError('hvrnet_b200 has no CPU path: move the model inputs to a CUDA device')
         return self.backbone(img)
@@ -601,6 +613,11 @@ class _WindowRCNN(TwoStageDetector):
         if isinstance(x, abc.Sequence):
             assert len(x) == len(img_meta)
             assert isinstance(x[0], torch.Tensor)
+        if (self._runner is not None and proposals is None and support is None and not return_aux
+                and not isinstance(x, torch.Tensor) and all(hasattr(t, '_hvr_split') for t in x)):
+            out = self._runner.detect([t._hvr_split for t in x], img_meta, rescale)
+            if out is not None:
+                return [bbox2result(d, l, self.bbox_head.num_classes) for d, l in out]
         c4 = self._window_split(x)
         rois, cnt, rows, aux = self._rois_and_feats(c4, img_meta, proposals)
         cur_range = self._key_range(cnt)

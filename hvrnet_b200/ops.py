@@ -200,7 +200,7 @@ def igemm_run(g, check_kernel=False):
     e0.record()
     check(fn(ctypes.byref(g), _stream()), 'hvr_igemm')
     e1.record()
-    PROFILE.append((e0, e1, igemm_flops(g)))
+    PROFILE.append((e0, e1, igemm_flops(g), (g.batch * g.out_h * g.out_w, g.n, g.ntaps * g.a_c)))
 
 
 def linear(a, w, n, bias=None, relu=False, res=None, alpha=1.0, want_split=True, want_f32=False, want_T=False,

@@ -39,6 +39,7 @@ def parse():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='hrnmp', choices=['hrnmp', 'selsa', 'faster_rcnn'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--videos-per-gpu', type=int, default=1, help='key frames (of different videos) batched per step')
     ap.add_argument('--eager', action='store_true', help='disable CUDA graphs (per-kernel Python launches)')
     ap.add_argument('--gemm-report', default=None, help='write a per-shape table of the igemm launches (csv)')
     return ap.parse_args()
@@ -178,24 +179,45 @@ def main():
     model, sd, w = configs.build_workload(args.workload, dev)
     T = w['t_dim']
     metas = [synth.make_img_meta() for _ in range(T)]
+    V = args.videos_per_gpu if args.workload != 'faster_rcnn' else 1
     pool = 4                                             # distinct "new" frames cycled through
-    frames = synth.make_frames(T + pool, seed=rank)      # every rank streams its own synthetic video
+    frames = synth.make_frames(T + pool, seed=rank)      # every rank streams its own synthetic video(s)
     host = [frames[i:i + 1].contiguous().pin_memory() for i in range(T + pool)]
     devf = [h.to(dev) for h in host]
-    frame_bytes = host[0].numel() * 4
+    # V videos per GPU: video v is the same synthetic clip shifted by v frames
+    hostV = [torch.cat([frames[(i + v) % (T + pool)][None] for v in range(V)]).contiguous().pin_memory()
+             for i in range(T + pool)] if V > 1 else None
+    devV = [h.to(dev) for h in hostV] if V > 1 else None
+    frame_bytes = host[0].numel() * 4 * V
+    from hvrnet_b200.runtime import GraphRunner
 
     def prefill():
         from collections import deque
-        dq = deque(maxlen=T)
+        dqs = [deque(maxlen=T) for _ in range(V)]
         for i in range(T):
-            dq.append(model(img=devf[i], img_meta=[metas[0]], backbone_feat=True)[0])
-        return dq
+            if V == 1:
+                dqs[0].append(model(img=devf[i], img_meta=[metas[0]], backbone_feat=True)[0])
+            else:
+                c4 = model(img=devV[i], img_meta=[metas[0]] * V, backbone_feat=True)[0]
+                for v, t in enumerate(GraphRunner.per_frame(c4)):
+                    dqs[v].append(t)
+        return dqs
 
-    def step(dq, i, from_host):
+    def step(dqs, i, from_host):
+        j = T + i % pool
+        if V > 1:
+            img = hostV[j] if from_host else devV[j]
+            if from_host and model._runner is None:
+                img = img.to(dev, non_blocking=True)
+            c4 = model(img=img, img_meta=[metas[0]] * V, backbone_feat=True)[0]
+            for v, t in enumerate(GraphRunner.per_frame(c4)):
+                dqs[v].append(t)
+            return model.forward_feat_batch([list(d) for d in dqs], metas, rescale=True)
+        dq = dqs[0]
         if from_host:
-            img = host[T + i % pool] if model._runner is not None else host[T + i % pool].to(dev, non_blocking=True)
+            img = host[j] if model._runner is not None else host[j].to(dev, non_blocking=True)
         else:
-            img = devf[T + i % pool]
+            img = devf[j]
         if args.workload == 'faster_rcnn':
             return model(img=[img], img_meta=[[metas[0]]], return_loss=False, rescale=True)
         dq.append(model(img=img, img_meta=[metas[0]], backbone_feat=True)[0])
@@ -230,7 +252,9 @@ def main():
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        d2h = sum(int(a.nbytes) for out in (res if isinstance(res[0], list) else [res]) for a in out)
+        def nbytes(r):
+            return int(r.nbytes) if hasattr(r, 'nbytes') else sum(nbytes(x) for x in r)
+        d2h = nbytes(res)
         return ms, launches, prof, d2h
 
     K, W = args.steps, max(args.warmup, 3)
@@ -243,8 +267,8 @@ def main():
     # host work)
     ms_prof, _, prof, _ = timed(False, K, W, profile=True)
 
-    fps = world * K / (ms / 1e3)
-    fps_e2e = world * K / (ms_e2e / 1e3)
+    fps = world * V * K / (ms / 1e3)
+    fps_e2e = world * V * K / (ms_e2e / 1e3)
     # roofline of the dominant kernel (igemm_tc_kernel): algorithmic FLOPs / summed launch durations
     gemm_ms = sum(p[0].elapsed_time(p[1]) for p in prof)
     gemm_flops = sum(p[2] for p in prof)
@@ -273,7 +297,8 @@ def main():
         'vs_baseline': None, 'dtype': 'bf16x3 (split-bf16 operands, 3 tcgen05 products, fp32 accumulate)',
         'data': 'synthetic',
         'config': {'workload': workload_name(args.workload, T), 'frames_per_window': T, 'proposals_per_frame': 300,
-                   'input': '1x3x608x1008 fp32 per step', 'l2': 'working set (305 MB split weights + >1 GB '
+                   'videos_per_gpu': V, 'key_frames_per_step': V,
+                   'input': '%dx3x608x1008 fp32 per step' % V, 'l2': 'working set (305 MB split weights + >1 GB '
                    'activations per step) exceeds the 126 MB L2; no explicit flush',
                    'parallelism': 'replicas over videos, dp%d' % world,
                    'launch': 'eager' if (args.eager or args.workload == 'faster_rcnn') else 'cuda graphs (trunk + window)'},

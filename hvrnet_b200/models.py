@@ -615,7 +615,7 @@ class _WindowRCNN(TwoStageDetector):
             assert isinstance(x[0], torch.Tensor)
         if (self._runner is not None and proposals is None and support is None and not return_aux
                 and not isinstance(x, torch.Tensor) and all(hasattr(t, '_hvr_split') for t in x)):
-            out = self._runner.detect([t._hvr_split for t in x], img_meta, rescale)
+            out = self._runner.detect([[t._hvr_split for t in x]], img_meta, rescale)[0]
             if out is not None:
                 return [bbox2result(d, l, self.bbox_head.num_classes) for d, l in out]
         c4 = self._window_split(x)
@@ -632,6 +632,27 @@ class _WindowRCNN(TwoStageDetector):
         if return_aux:
             aux.update(rois=rois, counts=cnt, cls=cls, reg=reg, dets=outs, start=s, length=n)
             return res, aux
+        return res
+
+    def forward_feat_batch(self, xs, img_meta, rescale=False):
+        """Throughput extension (not in the reference, whose driver handles one video per
+        process): V windows of V different videos in one call -> list of V forward_feat results.
+        Each video's arithmetic is exactly forward_feat's; with CUDA graphs enabled the V*T frames
+        share the C5 / RPN / RoIAlign launches."""
+        if self._runner is not None and all(hasattr(t, '_hvr_split') for x in xs for t in x):
+            outs = self._runner.detect([[t._hvr_split for t in x] for x in xs], img_meta, rescale)
+        else:
+            outs = [None] * len(xs)
+        res = []
+        for x, out in zip(xs, outs):
+            if out is None:
+                runner, self._runner = self._runner, None
+                try:
+                    res.append(self.forward_feat(x=x, img_meta=img_meta, rescale=rescale))
+                finally:
+                    self._runner = runner
+            else:
+                res.append([bbox2result(d, l, self.bbox_head.num_classes) for d, l in out])
         return res
 
     def simple_test(self, img, img_meta, proposals=None, rescale=False):

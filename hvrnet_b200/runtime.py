@@ -70,62 +70,78 @@ class GraphRunner:
         out._hvr_split = ops.Split(s.hi.clone(), s.lo.clone())
         return (out,)
 
-    # ------------------------------------------------------------------ window
-    def detect(self, parts, img_meta, rescale):
-        """parts: list of T per-frame C4 Splits [1,h,w,C].  Returns the list of per-output
-        (dets, labels) host tensors, or None when the speculation failed (caller goes eager)."""
+    @staticmethod
+    def per_frame(c4):
+        """Split a batched C4 (B frames) into B single-frame tensors that keep their split view."""
+        outs = []
+        for i in range(c4.shape[0]):
+            t = c4[i:i + 1]
+            t._hvr_split = c4._hvr_split[i:i + 1]
+            outs.append(t)
+        return outs
+
+    # ------------------------------------------------------------------ window(s)
+    def detect(self, windows, img_meta, rescale):
+        """windows: list of V windows, each a list of T per-frame C4 Splits [1,h,w,C] (V key
+        frames of V different videos are batched through one graph: C5 / RPN / proposals /
+        RoIAlign run over all V*T frames at once, the relation head once per video).
+        Returns, per video, the list of per-output (dets, labels) host tensors, or None for
+        the videos whose speculation (every frame yields max_num proposals) failed."""
         m = self.m
-        T = len(parts)
+        V, T = len(windows), len(windows[0])
         meta = img_meta[0]
         sf = meta['scale_factor']
         sf = float(sf if not hasattr(sf, '__len__') else sf[0])
-        key = (T, tuple(parts[0].shape), tuple(meta['img_shape'][:2]), sf, bool(rescale), m.key_dim)
+        key = (V, T, tuple(windows[0][0].shape), tuple(meta['img_shape'][:2]), sf, bool(rescale), m.key_dim)
         c = self._window.get(key)
+        P = m.test_cfg.rpn['max_num']
+        M = m.test_cfg.rcnn['max_per_img']
+
+        def fill(win):
+            torch.cat([p.hi for w in windows for p in w], 0, out=win.hi)
+            torch.cat([p.lo for w in windows for p in w], 0, out=win.lo)
+
         if c is None:
-            dev = parts[0].hi.device
-            _, h, w, C = parts[0].shape
-            win = ops.Split.zeros((T, h, w, C), dev)
-            P = m.test_cfg.rpn['max_num']
+            dev = windows[0][0].hi.device
+            _, h, w, C = windows[0][0].shape
+            win = ops.Split.zeros((V * T, h, w, C), dev)
 
             def fn():
                 c5 = m.shared_head.forward_nhwc(win) if m.feat_from_shared_head else ops.merge(win)
                 props, counts = m.rpn_head.get_proposals(win, meta['img_shape'], m.test_cfg.rpn)
-                fidx = torch.arange(T, device=dev, dtype=torch.float32).view(T, 1, 1).expand(T, P, 1)
+                fidx = torch.arange(V * T, device=dev, dtype=torch.float32).view(V * T, 1, 1).expand(V * T, P, 1)
                 rois = torch.cat([fidx, props[..., :4]], -1).view(-1, 5).contiguous()
                 rows = m.bbox_roi_extractor.roi_layers[0].forward_nhwc_split(c5, rois)
-                s = m.key_dim * P
-                cls, reg = m._head(rows, [dict(start=s, length=P)], None)
-                rois_key = rois[s:s + P].clone()
-                rois_key[:, 0] = 0
-                outs = m.bbox_head.get_det_bboxes(rois_key, cls, reg, meta['img_shape'], sf, rescale=rescale,
-                                                  cfg=m.test_cfg.rcnn)
                 flat = [counts.float()]
-                for d, l, k in outs:
-                    flat += [k.float(), d.reshape(-1), l.float()]
+                s = m.key_dim * P
+                for v in range(V):
+                    o = v * T * P
+                    cls, reg = m._head(rows[o:o + T * P], [dict(start=s, length=P)], None)
+                    rois_key = rois[o + s:o + s + P].clone()
+                    rois_key[:, 0] = 0
+                    outs = m.bbox_head.get_det_bboxes(rois_key, cls, reg, meta['img_shape'], sf, rescale=rescale,
+                                                      cfg=m.test_cfg.rcnn)
+                    for d, l, k in outs:
+                        flat += [k.float(), d.reshape(-1), l.float()]
                 return torch.cat(flat)
-            for p in parts:                             # real data for the warm-up pass
-                pass
-            torch.cat([p.hi for p in parts], 0, out=win.hi)
-            torch.cat([p.lo for p in parts], 0, out=win.lo)
+            fill(win)                                   # real data for the warm-up pass
             c = self._capture(fn)
             c.inputs = win
             self._window[key] = c
-        win = c.inputs
-        torch.cat([p.hi for p in parts], 0, out=win.hi)
-        torch.cat([p.lo for p in parts], 0, out=win.lo)
+        fill(c.inputs)
         c.graph.replay()
         self.replayed_launches += c.launches
-        host = c.outputs.cpu()                          # the one device->host read of the key frame
-        P = m.test_cfg.rpn['max_num']
-        if not bool((host[:T] == P).all()):
-            return None
-        M = m.test_cfg.rcnn['max_per_img']
-        res, o = [], T
-        n_out = (host.numel() - T) // (1 + 6 * M)
-        for _ in range(n_out):
-            k = int(host[o])
-            d = host[o + 1:o + 1 + 5 * M].view(M, 5)[:k]
-            l = host[o + 1 + 5 * M:o + 1 + 6 * M][:k].long()
-            res.append((d, l))
-            o += 1 + 6 * M
+        host = c.outputs.cpu()                          # the one device->host read of the step
+        n_out = (host.numel() - V * T) // (V * (1 + 6 * M))
+        res, o = [], V * T
+        for v in range(V):
+            ok = bool((host[v * T:(v + 1) * T] == P).all())
+            outs = []
+            for _ in range(n_out):
+                k = int(host[o])
+                d = host[o + 1:o + 1 + 5 * M].view(M, 5)[:k]
+                l = host[o + 1 + 5 * M:o + 1 + 6 * M][:k].long()
+                outs.append((d, l))
+                o += 1 + 6 * M
+            res.append(outs if ok else None)
         return res

@@ -468,7 +468,7 @@ def shared_fc_forward(sd, roi_feats, prefix='bbox_head.'):
 # ----------------------------------------------------------------------------
 
 
-def multiclass_nms(boxes, scores, score_thr=0.001, iou_thr=0.3, max_num=300):
+def multiclass_nms(boxes, scores, score_thr=0.001, iou_thr=0.3, max_num=300, strict_gt=True):
     """boxes (n,4) class-agnostic, scores (n,C) with column 0 = background.
     Returns (k,5), (k,) int64 labels (0-based).  Per class: rows with score > thr
     (:36), NMS with kept rows in ascending row order (nms_wrapper.py:61), label
@@ -480,7 +480,7 @@ def multiclass_nms(boxes, scores, score_thr=0.001, iou_thr=0.3, max_num=300):
         if not m.any():
             continue
         d = torch.cat([boxes[m], scores[m, c][:, None]], dim=1)
-        keep = nms(d, iou_thr, strict_gt=True)
+        keep = nms(d, iou_thr, strict_gt=strict_gt)
         dets.append(d[keep])
         labels.append(torch.full((keep.shape[0],), c - 1, dtype=torch.long))
     if not dets:

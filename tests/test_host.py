@@ -1,0 +1,168 @@
+"""Host-side logic on the CPU: the plugin surface (Registry / build_from_cfg / Config), module
+construction from the reference's config files, parameter names, and that the C-ABI library
+loads and exports every symbol include/hvr_b200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_CFG = '/root/reference/configs'
+
+
+def test_registry_semantics():
+    """mmdet/utils/registry.py:6-76."""
+    from hvrnet_b200.registry import Registry, build_from_cfg
+    R = Registry('thing')
+
+    @R.register_module
+    class A(object):
+        def __init__(self, x, y=2):
+            self.x, self.y = x, y
+
+    assert R.get('A') is A and R.get('nope') is None and R.name == 'thing' and 'A' in R.module_dict
+    with pytest.raises(KeyError):
+        R.register_module(A)                              # duplicate name
+    with pytest.raises(TypeError):
+        R.register_module(lambda: 0)                      # not a class
+    cfg = dict(type='A', x=1)
+    obj = build_from_cfg(cfg, R, default_args=dict(y=5, x=9))
+    assert (obj.x, obj.y) == (1, 5) and cfg == dict(type='A', x=1)          # cfg untouched, setdefault semantics
+    assert build_from_cfg(dict(type=A, x=3), R).x == 3                      # a class as type
+    with pytest.raises(KeyError, match='B is not in the thing registry'):
+        build_from_cfg(dict(type='B'), R)
+    with pytest.raises(TypeError):
+        build_from_cfg(dict(type=3), R)
+    with pytest.raises(AssertionError):
+        build_from_cfg(dict(x=1), R)
+
+
+def test_builder_list_gives_sequential():
+    """mmdet/models/builder.py:8-15."""
+    from hvrnet_b200 import models  # noqa: F401
+    from hvrnet_b200.builder import build
+    from hvrnet_b200.registry import LOSSES
+    seq = build([dict(type='SmoothL1Loss', beta=1.0), dict(type='CrossEntropyLoss')], LOSSES)
+    assert isinstance(seq, torch.nn.Sequential) and len(seq) == 2
+
+
+def test_config_loader_attr_access(tmp_path):
+    from hvrnet_b200.config import Config
+    f = tmp_path / 'cfg.py'
+    f.write_text("a = 3\nif a > 2:\n    t = 'X'\nmodel = dict(type=t, sub=dict(k=[dict(z=1)]))\ntest_cfg = dict(rpn=dict(nms_pre=6000))\n")
+    cfg = Config.fromfile(str(f))
+    assert cfg.model.type == 'X' and cfg.model.sub.k[0].z == 1 and cfg.test_cfg.rpn.nms_pre == 6000
+    assert cfg.test_cfg.rpn.get('missing', 7) == 7 and not hasattr(cfg.test_cfg.rpn, 'missing')
+    c = cfg.test_cfg.rpn.copy()
+    assert c.pop('nms_pre') == 6000 and cfg.test_cfg.rpn.nms_pre == 6000
+    with pytest.raises(FileNotFoundError):
+        Config.fromfile(str(tmp_path / 'nope.py'))
+
+
+def _param_names(m):
+    return [k for k in m.state_dict() if 'num_batches_tracked' not in k]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CFG), reason='reference tree not present (GPU box)')
+@pytest.mark.parametrize('name,det,head,stages', [('faster_rcnn_r101_hrnmp_c5.py', 'HNMBRCNN', 'HRNMPBBoxHead', 4),
+                                                  ('faster_rcnn_r101_selsa_c5.py', 'SelsaRCNN', 'SelsaBBoxHead', 2)])
+def test_reference_configs_build_unchanged(name, det, head, stages):
+    """The reference's own config files drive build_detector unchanged."""
+    from hvrnet_b200 import models  # noqa: F401
+    from hvrnet_b200.builder import build_detector
+    from hvrnet_b200.config import Config
+    cfg = Config.fromfile(os.path.join(REF_CFG, name))
+    m = build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg)
+    assert type(m).__name__ == det and type(m.bbox_head).__name__ == head
+    assert m.key_dim == 10 and m.bbox_head.t_dim == 21 and m.bbox_head.sampler_num == 300
+    assert m.feat_from_shared_head is True
+    names = set(_param_names(m))
+    for k in ['backbone.conv1.weight', 'backbone.bn1.running_var', 'backbone.layer1.0.downsample.0.weight',
+              'backbone.layer3.22.conv3.weight', 'shared_head.layer4.0.downsample.1.bias',
+              'shared_head.new_layer_1.conv.bias', 'rpn_head.rpn_conv.weight', 'rpn_head.rpn_cls.bias',
+              'rpn_head.rpn_reg.weight', 'bbox_head.fc_new_1.weight', 'bbox_head.fc_cls.weight',
+              'bbox_head.fc_reg.bias'] + \
+             ['bbox_head.selsa_%d.%s_%d.%s' % (s, n, s, p) for s in range(1, stages + 1)
+              for n in ('q_data_fc', 'k_data_fc', 'linear_out') for p in ('weight', 'bias')]:
+        assert k in names, k
+    assert ('bbox_head.fc_cls_2.weight' in names) == (stages == 4)
+    assert m.state_dict()['bbox_head.selsa_1.linear_out_1.weight'].shape == (1024, 1024, 1, 1)
+    assert m.state_dict()['bbox_head.fc_new_1.weight'].shape == (1024, 12544)
+    assert m.rpn_head.base_anchors.shape == (12, 4)
+
+
+def test_workload_configs_and_synthetic_weights_load():
+    from hvrnet_b200 import configs, synth
+    for name, w in configs.WORKLOADS.items():
+        if 'support_videos' in w:
+            continue
+        cfg = configs.model_cfg(w['net_type'], w['t_dim'], w['key_dim'])
+        from hvrnet_b200.builder import build_detector
+        m = build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg)
+        sd = synth.make_state_dict(w['head'])
+        r = m.load_state_dict(sd, strict=False)
+        assert not r.unexpected_keys and all('num_batches_tracked' in k for k in r.missing_keys), name
+        assert set(_param_names(m)) == set(sd.keys())
+
+
+def test_no_cpu_path():
+    """The product fails loudly on CPU tensors (no fallback to torch ops or to the oracle)."""
+    from hvrnet_b200 import configs, ops
+    from hvrnet_b200._lib import HvrError
+    with pytest.raises(HvrError):
+        ops.split(torch.zeros(4))
+    with pytest.raises(NotImplementedError):               # as the reference: roi_align.py:24-28
+        from hvrnet_b200.models import RoIAlign
+        RoIAlign(7, 1 / 16., 2)(torch.zeros(1, 4, 8, 8), torch.zeros(1, 5))
+    cfg = configs.model_cfg('FasterRCNN', 1, 0)
+    from hvrnet_b200.builder import build_detector
+    m = build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg)
+    with pytest.raises(HvrError):
+        m(img=torch.zeros(1, 3, 64, 64), img_meta=[dict()], backbone_feat=True)
+    with pytest.raises(HvrError):
+        m(img=torch.zeros(1, 3, 64, 64), img_meta=[dict()], return_loss=True)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'hvrnet_b200')
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.cpp', '.h')):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), f
+                assert 'libhvr_oracle' not in src and not re.search(r'\boracle\.(cref|ref_torch|build)\b', src), f
+
+
+def test_abi_library_exports_every_declared_symbol():
+    from hvrnet_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'hvr_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(hvr_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 20
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    L = _lib.lib()                                        # loads the .so, resolves all of them
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert getattr(raw, name) is not None
+    assert L.hvr_abi_version() == 1
+    assert L.hvr_strerror(0) == b'ok' and L.hvr_strerror(-3) == b'workspace too small'
+    assert L.hvr_nms_workspace_bytes(6000) > 6000 * 94 * 8
+    assert ctypes.sizeof(_lib.HvrIGemm) % 8 == 0
+
+
+def test_igemm_struct_layout_matches_header():
+    """Field order of the ctypes mirror == field order of struct HvrIGemm in the header."""
+    from hvrnet_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'hvr_b200.h')).read()
+    body = hdr[hdr.index('typedef struct HvrIGemm {') + len('typedef struct HvrIGemm {'):hdr.index('} HvrIGemm;')]
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    names = []
+    for decl in body.split(';'):
+        decl = decl.strip()
+        if not decl or decl.startswith('typedef'):
+            continue
+        for part in decl.split(','):
+            names.append(re.sub(r'\[.*\]', '', part.strip().split()[-1].lstrip('*')))
+    assert names == [f[0] for f in _lib.HvrIGemm._fields_]

@@ -291,9 +291,9 @@ def relation(P, idx, X, XT, q_range=None, res=None, relu=True, extra=None, **kw)
     return out
 
 
-def hrnmp_forward_test(P, roi_feats, start, length, support=None, **kw):
-    """roi_feats Split [N, 12544] (NHWC-flattened).  Returns fp32 (out1 [len, 64], out2 [len, 64]):
-    columns [0,n_cls) class logits, [n_cls, n_cls+4) box deltas; plus f4[key] Split."""
+def hrnmp_stage123(P, roi_feats, start, length, **kw):
+    """Stages 1-3 + fc_new_4 of forward_test (hrnmp_bbox_head.py:827-889).  Returns
+    (out1 fp32 [len, 64] = branch [cls | reg], f4 Split [N, D], f4^T Split [D, ld])."""
     s, e = start, start + length
     f1, _, f1T = lin(roi_feats, P['fc1'], want_T=True, **kw)
     a1 = relation(P, 1, f1, f1T, res=f1, **kw)
@@ -305,9 +305,24 @@ def hrnmp_forward_test(P, roi_feats, start, length, support=None, **kw):
     f3, _, f3T = lin(x3, P['fc3'], want_T=True, **kw)
     a3 = relation(P, 3, f3, f3T, res=f3, **kw)
     f4, _, f4T = lin(a3, P['fc4'], want_T=True, **kw)
+    return out1, f4, f4T
+
+
+def hrnmp_stage4(P, f4, f4T, start, length, support=None, **kw):
+    """Stage 4 (hrnmp_bbox_head.py:888-906): key-row queries over all rows of the window plus
+    optional inter-video support rows (post-fc_new_4 key rows of other videos)."""
+    s, e = start, start + length
     a4 = relation(P, 4, f4, f4T, q_range=(s, length), res=f4[s:e], extra=support, **kw)
     _, out2, _ = lin(a4, P['out2'], want_split=False, want_f32=True, **kw)
-    return out1, out2, f4[s:e]
+    return out2
+
+
+def hrnmp_forward_test(P, roi_feats, start, length, support=None, **kw):
+    """roi_feats Split [N, 12544] (NHWC-flattened).  Returns fp32 (out1 [len, 64], out2 [len, 64]):
+    columns [0,n_cls) class logits, [n_cls, n_cls+4) box deltas; plus f4[key] Split."""
+    out1, f4, f4T = hrnmp_stage123(P, roi_feats, start, length, **kw)
+    out2 = hrnmp_stage4(P, f4, f4T, start, length, support, **kw)
+    return out1, out2, f4[start:start + length]
 
 
 def selsa_forward(P, roi_feats, start, length, **kw):

@@ -680,6 +680,42 @@ class HNMBRCNN(_WindowRCNN):
         return self.bbox_head.forward_test(rows, cur_range, key_dim=self.key_dim, all_res=False, support=support)
 
 
+    def forward_feat_intervideo(self, xs, img_meta, n_support=4, rescale=False, group=None, return_aux=False,
+                                proposals=None):
+        """BASELINE.json configs 4-5 (oracle-defined, parity unpinned by the
+        reference): V local key frames, one window each; stage 4 of every key frame also attends
+        to the post-fc_new_4 key rows of `n_support` other key frames (ring order over all ranks,
+        intervideo.support_indices) gathered with ONE all-gather.  Every frame must yield the same
+        number of proposals P (the all-gather is fixed-size); otherwise a ValueError is raised."""
+        from . import intervideo
+        P = self.test_cfg.rpn['max_num']
+        head = self.bbox_head
+        per_video, z = [], []
+        for vi, x in enumerate(xs):
+            c4 = self._window_split(x)
+            rois, cnt, rows, _ = self._rois_and_feats(c4, img_meta, None if proposals is None else proposals[vi])
+            if any(c != P for c in cnt):
+                raise ValueError('inter-video exchange needs %d proposals per frame, got %s' % (P, cnt))
+            s = self.key_dim * P
+            packed = head.packed(rows.hi.device)
+            out1, f4, f4T = engine.hrnmp_stage123(packed, rows, s, P)
+            per_video.append((rois[s:s + P].clone(), out1, f4, f4T, s))
+            z.append(f4[s:s + P])
+        z_local = ops.Split(torch.cat([t.hi for t in z], 0), torch.cat([t.lo for t in z], 0))
+        supports = intervideo.gather_support(z_local, P, n_support, group)
+        m = img_meta[0]
+        results, aux = [], []
+        for (rois_key, out1, f4, f4T, s), sup in zip(per_video, supports):
+            out2 = engine.hrnmp_stage4(head.packed(f4.hi.device), f4, f4T, s, P, sup if sup.hi.shape[0] else None)
+            rois_key[:, 0] = 0
+            (c1, r1), (c2, r2) = head._split_out(out1), head._split_out(out2)
+            outs = head.get_det_bboxes(rois_key, [c1, c2], [r1, r2], m['img_shape'], m['scale_factor'],
+                                       rescale=rescale, cfg=self.test_cfg.rcnn)
+            results.append([_result_from_device(d, l, k, head.num_classes) for d, l, k in outs])
+            aux.append(dict(cls=[c1, c2], reg=[r1, r2], support=sup))
+        return (results, aux) if return_aux else results
+
+
 @DETECTORS.register_module
 class SelsaRCNN(_WindowRCNN):
     """mmdet/models/detectors/selsa_rcnn.py:18-83,281-317."""

@@ -1,0 +1,84 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: sharding of key frames over
+ranks, the single all-gather of inter-video support rows and the ring selection."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, V, P, D, n_support, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from hvrnet_b200 import intervideo
+        from hvrnet_b200.ops import Split
+        # row r of global key frame g carries the value g*16 + r (exact in bf16) in hi and its negative in lo
+        rows = []
+        for v in range(V):
+            g = rank * V + v
+            rows.append(torch.arange(P, dtype=torch.float32).view(P, 1).expand(P, D) + 16.0 * g)
+        z = torch.cat(rows, 0)
+        zl = Split(z.to(torch.bfloat16), (-z).to(torch.bfloat16))
+        sup = intervideo.gather_support(zl, P, n_support)
+        ok = len(sup) == V
+        for v in range(V):
+            g = rank * V + v
+            idx = intervideo.support_indices(g, world * V, n_support)
+            exp = torch.cat([(torch.arange(P, dtype=torch.float32) + 16.0 * i).view(P, 1).expand(P, D) for i in idx], 0)
+            ok = ok and torch.equal(sup[v].hi, exp.to(torch.bfloat16)) and torch.equal(sup[v].lo, (-exp).to(torch.bfloat16))
+        pool = intervideo.all_gather_rows(zl)
+        ok = ok and pool.hi.shape == (world * V * P, D) and float(pool.hi[(world * V - 1) * P, 0]) == 16.0 * (world * V - 1)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('V,n_support', [(3, 4), (1, 4), (2, 1)])
+def test_support_exchange_world2(V, n_support):
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, V, 4, 8, n_support, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=150)
+    assert [p.exitcode for p in procs] == [0] * world
+    res = dict(q.get(timeout=10) for _ in range(world))
+    assert res == {0: True, 1: True}
+
+
+def test_ring_rule_and_sharding():
+    from hvrnet_b200 import intervideo as iv
+    assert iv.support_indices(0, 256, 4) == [1, 2, 3, 4]
+    assert iv.support_indices(254, 256, 4) == [255, 0, 1, 2]          # (g*32+b+1..+4) mod 256, SURVEY.md 8d
+    assert iv.support_indices(0, 1, 4) == []                          # no other video: degenerates to forward_test
+    assert iv.support_indices(1, 3, 4) == [2, 0]                      # never includes itself
+    cover = []
+    for r in range(8):
+        lo, hi = iv.shard_range(555, 8, r)
+        cover += list(range(lo, hi))
+        assert 69 <= hi - lo <= 70
+    assert cover == list(range(555))
+
+
+def test_single_process_is_identity():
+    from hvrnet_b200 import intervideo as iv
+    from hvrnet_b200.ops import Split
+    z = Split(torch.randn(6, 4).to(torch.bfloat16), torch.randn(6, 4).to(torch.bfloat16))
+    assert iv.all_gather_rows(z) is z
+    sup = iv.gather_support(z, 2, 4)
+    assert [tuple(s.hi.shape) for s in sup] == [(4, 4)] * 3
+    assert torch.equal(sup[2].hi, torch.cat([z.hi[0:2], z.hi[2:4]]))

@@ -172,3 +172,35 @@ def test_cuda_graph_runner_matches_eager(world):
         assert m._runner.replayed_launches > 0
     finally:
         m.enable_cuda_graphs(False)
+
+
+def test_intervideo_stage4_world1(world):
+    """BASELINE.json config 4 (1 key + support videos on one GPU): stage 4 attends to the
+    post-fc_new_4 key rows of the other videos in ring order.  Oracle-defined,
+    parity unpinned by the reference.  Oracle proposals are forced in so both sides pool the
+    same rows."""
+    from oracle import cref, ref_torch as R
+    m, dev, sd = world['model'], world['dev'], world['sd']
+    c4 = world['c4_ref']
+    orders = [[0, 1, 2], [1, 2, 0], [2, 0, 1]]                      # three "videos" from the same 3 frames
+    with torch.no_grad():
+        auxs = [R.hnmb_forward_feat(sd, [c4[i:i + 1] for i in o], world['metas'], 1, roi_align_fn=cref.roi_align,
+                                    return_aux=True)[1] for o in orders]
+        z = [R.hrnmp_stage123_key_feats(sd, a['roi_feats'], a['start'], a['length']) for a in auxs]
+        refs = []
+        for v, a in enumerate(auxs):
+            sup = torch.cat([z[(v + 1) % 3], z[(v + 2) % 3]], 0)     # support_indices(v, 3, 4) = [v+1, v+2]
+            refs.append(R.hrnmp_forward_test(sd, a['roi_feats'], a['start'], a['length'], support_rows=sup))
+    xs = [[c4[i:i + 1].to(dev) for i in o] for o in orders]
+    res, aux = m.forward_feat_intervideo(xs, world['metas'], n_support=4, rescale=True, return_aux=True,
+                                         proposals=[[p.to(dev) for p in a['proposals']] for a in auxs])
+    assert len(res) == 3 and len(res[0]) == 2
+    for v in range(3):
+        assert aux[v]['support'].hi.shape[0] == 600
+        for a, b in zip(aux[v]['cls'] + aux[v]['reg'], refs[v][0] + refs[v][1]):
+            assert _rel(a.cpu(), b) < 1e-3
+    # with no other video the exchange degenerates to forward_test
+    res1, aux1 = m.forward_feat_intervideo(xs[:1], world['metas'], n_support=4, rescale=True, return_aux=True,
+                                           proposals=[[p.to(dev) for p in auxs[0]['proposals']]])
+    for a, b in zip(aux1[0]['cls'] + aux1[0]['reg'], auxs[0]['cls'] + auxs[0]['reg']):
+        assert _rel(a.cpu(), b) < 1e-3

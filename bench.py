@@ -37,9 +37,9 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='hrnmp', choices=['hrnmp', 'selsa', 'faster_rcnn'])
+    ap.add_argument('--workload', default='hrnmp', choices=['hrnmp', 'selsa', 'faster_rcnn', 'hrnmp_inter'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--videos-per-gpu', type=int, default=1, help='key frames (of different videos) batched per step')
+    ap.add_argument('--videos-per-gpu', type=int, default=0, help='key frames (of different videos) batched per step')
     ap.add_argument('--eager', action='store_true', help='disable CUDA graphs (per-kernel Python launches)')
     ap.add_argument('--gemm-report', default=None, help='write a per-shape table of the igemm launches (csv)')
     return ap.parse_args()
@@ -48,6 +48,8 @@ def parse():
 def workload_name(w, T):
     return {'hrnmp': 'HVRNet intra-video (faster_rcnn_r101_hrnmp_c5), 1 key + %d ref frames, 300 proposals' % (T - 1),
             'selsa': 'SELSA R101 (faster_rcnn_r101_selsa_c5), 1 key + %d ref frames, 300 proposals' % (T - 1),
+            'hrnmp_inter': 'HVRNet intra+inter-video, 1 key + %d ref frames + 4 inter-video support videos, '
+                           '300 proposals each' % (T - 1),
             'faster_rcnn': 'Faster-RCNN R101-C5, single 600x1000 frame'}[w]
 
 
@@ -63,6 +65,8 @@ def cpu_key_frame_seconds(workload, max_seconds=200.0, steps=1, warm=True):
     torch.set_num_threads(os.cpu_count())
     w = configs.WORKLOADS[workload]
     T, key = w['t_dim'], w['key_dim']
+    # hrnmp_inter: the CPU arm times the intra-video key frame; the 1200 extra stage-4 key rows add
+    # 4 GFLOP to ~2100, i.e. < 0.2 %
     sd = synth.make_state_dict(w['head'])
     frames = synth.make_frames(2, seed=0)
     metas = [synth.make_img_meta() for _ in range(T)]
@@ -179,15 +183,18 @@ def main():
     model, sd, w = configs.build_workload(args.workload, dev)
     T = w['t_dim']
     metas = [synth.make_img_meta() for _ in range(T)]
-    V = args.videos_per_gpu if args.workload != 'faster_rcnn' else 1
+    V = args.videos_per_gpu or (5 if args.workload == 'hrnmp_inter' else 1)
+    if args.workload == 'faster_rcnn':
+        V = 1
+    inter = args.workload == 'hrnmp_inter'
     pool = 4                                             # distinct "new" frames cycled through
     frames = synth.make_frames(T + pool, seed=rank)      # every rank streams its own synthetic video(s)
     host = [frames[i:i + 1].contiguous().pin_memory() for i in range(T + pool)]
     devf = [h.to(dev) for h in host]
     # V videos per GPU: video v is the same synthetic clip shifted by v frames
     hostV = [torch.cat([frames[(i + v) % (T + pool)][None] for v in range(V)]).contiguous().pin_memory()
-             for i in range(T + pool)] if V > 1 else None
-    devV = [h.to(dev) for h in hostV] if V > 1 else None
+             for i in range(T + pool)] if (V > 1 or inter) else None
+    devV = [h.to(dev) for h in hostV] if hostV is not None else None
     frame_bytes = host[0].numel() * 4 * V
     from hvrnet_b200.runtime import GraphRunner
 
@@ -195,7 +202,7 @@ def main():
         from collections import deque
         dqs = [deque(maxlen=T) for _ in range(V)]
         for i in range(T):
-            if V == 1:
+            if V == 1 and not inter:
                 dqs[0].append(model(img=devf[i], img_meta=[metas[0]], backbone_feat=True)[0])
             else:
                 c4 = model(img=devV[i], img_meta=[metas[0]] * V, backbone_feat=True)[0]
@@ -205,13 +212,15 @@ def main():
 
     def step(dqs, i, from_host):
         j = T + i % pool
-        if V > 1:
+        if V > 1 or inter:
             img = hostV[j] if from_host else devV[j]
             if from_host and model._runner is None:
                 img = img.to(dev, non_blocking=True)
             c4 = model(img=img, img_meta=[metas[0]] * V, backbone_feat=True)[0]
             for v, t in enumerate(GraphRunner.per_frame(c4)):
                 dqs[v].append(t)
+            if inter:   # configs 4-5: one all-gather of the post-fc_new_4 key rows, ring-order supports
+                return model.forward_feat_intervideo([list(d) for d in dqs], metas, n_support=4, rescale=True)
             return model.forward_feat_batch([list(d) for d in dqs], metas, rescale=True)
         dq = dqs[0]
         if from_host:
@@ -225,7 +234,7 @@ def main():
 
     def timed(from_host, K, W, profile=False):
         # the roofline leg brackets individual launches with events, which needs the eager path
-        model.enable_cuda_graphs(not (profile or args.eager) and args.workload != 'faster_rcnn')
+        model.enable_cuda_graphs(not (profile or args.eager) and args.workload != 'faster_rcnn')   # inter: trunk graph only
         dq = prefill()
         for i in range(W):
             res = step(dq, i, from_host)

@@ -330,6 +330,183 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs owns a 256 x BN tile.  Each
+// CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows); the leader's single MMA
+// thread issues M=256 instructions that read A and B halves from both CTAs' shared memory and
+// write each CTA's 128 accumulator rows into its own TMEM.  Per-SM operand ingest per K step
+// drops from 32+64 KB to 32+32 KB (BN=256) - the L2->SM path (~42 B/clk/SM) is what limits
+// the 3-product kernel - at unchanged tensor work.
+// Barriers: full[s] lives in the leader (both CTAs' TMA loads complete_tx on it; the leader
+// arms it with the bytes of both); empty[s] / tmem_full[b] are per CTA, signalled by multicast
+// tcgen05.commit; tmem_empty[b] lives in the leader and counts the 8 epilogue warps of the pair.
+// ------------------------------------------------------------------------------------
+template <int BN>
+struct Cfg2 {
+  static constexpr int BH_BYTES = (BN / 2) * BK * 2;              // this CTA's half of one B tile
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;  // A hi/lo + B-half hi/lo
+  static constexpr int STAGES = (BN == 256) ? 3 : 4;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+    igemm_tc2_kernel(const __grid_constant__ KParams p) {
+  using C_ = Cfg2<BN>;
+  constexpr int STAGES = C_::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* tiles = smem_raw + pad;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + STAGES * C_::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int total_k = p.ntaps * p.cblocks;
+  const int n_tiles = p.n_tiles;
+  const int m_tiles = p.tiles_x * p.tiles_y * p.batch;
+  const int m_pairs = (m_tiles + 1) >> 1;
+  const int num_tiles = m_pairs * n_tiles;           // pair tiles
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA_hi);
+    tma_prefetch_desc(&p.tmB_hi);
+    tma_prefetch_desc(&p.tmA_lo);
+    tma_prefetch_desc(&p.tmB_lo);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 8);   // 4 epilogue warps x 2 CTAs (used in the leader only)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(tmem_ptr_smem, C_::TMEM_COLS);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                    // barrier inits visible to the peer before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs) =================
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int nt = tile % n_tiles;
+        const int m_tile = 2 * (tile / n_tiles) + (int)rank;
+        const int tx = m_tile % p.tiles_x;
+        const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+        const int bimg = m_tile / (p.tiles_x * p.tiles_y);   // >= batch for the odd tail: TMA zero-fills
+        const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
+        const int n0 = nt * BN + (int)rank * (BN / 2);
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int ax = x0 + p.tap_dx[tap];
+          const int ay = y0 + p.tap_dy[tap];
+          for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            uint8_t* st = tiles + s * C_::STAGE_BYTES;
+            if (leader) mbar_expect_tx(&full_bar[s], 2u * (uint32_t)C_::STAGE_BYTES);
+            const int kc = cb * BK;
+            tma2_load_4d(st, &p.tmA_hi, &full_bar[s], kc, ax, ay, bimg);
+            tma2_load_2d(st + 2 * A_BYTES, &p.tmB_hi, &full_bar[s], tap * p.C + kc, n0);
+            tma2_load_4d(st + A_BYTES, &p.tmA_lo, &full_bar[s], kc, ax, ay, bimg);
+            tma2_load_2d(st + 2 * A_BYTES + C_::BH_BYTES, &p.tmB_lo, &full_bar[s], tap * p.C + kc, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BN, 256);
+      int it = 0, lt = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
+        const int ab = lt & 1;
+        const uint32_t aph = (uint32_t)((lt >> 1) & 1);
+        mbar_wait(&tmem_empty_bar[ab], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(ab * BN);
+        for (int kk = 0; kk < total_k; ++kk, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t st = smem_u32(tiles + s * C_::STAGE_BYTES);
+            const uint64_t a_hi = umma_desc_k_sw128(st);
+            const uint64_t a_lo = umma_desc_k_sw128(st + A_BYTES);
+            const uint64_t b_hi = umma_desc_k_sw128(st + 2 * A_BYTES);
+            const uint64_t b_lo = umma_desc_k_sw128(st + 2 * A_BYTES + C_::BH_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t ko = (uint64_t)(k * 2);
+              tc_mma2_f16(tmem_acc, a_hi + ko, b_hi + ko, idesc, (kk > 0 || k > 0) ? 1u : 0u);
+              tc_mma2_f16(tmem_acc, a_hi + ko, b_lo + ko, idesc, 1u);
+              tc_mma2_f16(tmem_acc, a_lo + ko, b_hi + ko, idesc, 1u);
+            }
+            tc_commit2(&empty_bar[s]);
+            if (kk == total_k - 1) tc_commit2(&tmem_full_bar[ab]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ================= epilogue (both CTAs, own 128 rows) =================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    int lt = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
+      const int nt = tile % n_tiles;
+      const int m_tile = 2 * (tile / n_tiles) + (int)rank;
+      const int tx = m_tile % p.tiles_x;
+      const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+      const int bimg = m_tile / (p.tiles_x * p.tiles_y);
+      const int px = tx * p.tile_w + m % p.tile_w;
+      const int py = ty * p.tile_h + m / p.tile_w;
+      const bool row_ok = (px < p.out_w) && (py < p.out_h) && (bimg < p.batch);
+      const long long row = ((long long)bimg * p.out_h + py) * p.out_w + px;
+      const int ab = lt & 1;
+      const uint32_t aph = (uint32_t)((lt >> 1) & 1);
+      mbar_wait(&tmem_full_bar[ab], aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0), acc);
+        tmem_ld_wait();
+        epilogue_chunk(p, acc, row, nt * BN + c0, row_ok);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[ab]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                    // neither CTA leaves while the other may still touch it
+  if (warp == 1) tmem_dealloc2(tmem_base, C_::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------
 // fp32 SIMT evaluation of the same descriptor (cross-check).
 // ------------------------------------------------------------------------------------
 __global__ void igemm_check_kernel(HvrIGemm g, long long rows) {
@@ -497,6 +674,46 @@ int launch(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
   return HVR_OK;
 }
 
+template <int BN>
+int launch2(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    HVR_CUDA(cudaFuncSetAttribute(igemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::SMEM));
+    attr_set = true;
+  }
+  const uint64_t ktot = (uint64_t)g->ntaps * g->a_c;
+  const uint64_t bdims[2] = {ktot, (uint64_t)g->n};
+  const uint64_t bstr[1] = {(uint64_t)g->ldb * 2};
+  const uint32_t bbox[2] = {BK, BN / 2};
+  int rc = make_map(&kp.tmB_hi, g->b_hi, 2, bdims, bstr, bbox);
+  if (rc) return rc;
+  rc = make_map(&kp.tmB_lo, g->b_lo, 2, bdims, bstr, bbox);
+  if (rc) return rc;
+  kp.n_tiles = hvr_cdiv(g->n, BN);
+  const long long m_tiles = (long long)kp.tiles_x * kp.tiles_y * kp.batch;
+  const long long pair_tiles = ((m_tiles + 1) / 2) * kp.n_tiles;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    HVR_CUDA(cudaGetDevice(&dev));
+    HVR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long long clusters = pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * clusters));
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = Cfg2<BN>::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  HVR_CUDA(cudaLaunchKernelEx(&cfg, igemm_tc2_kernel<BN>, kp));
+  HVR_LAUNCHED();
+  return HVR_OK;
+}
+
 }  // namespace
 
 extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
@@ -548,6 +765,9 @@ extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
   // 64 for narrow outputs or when 128-wide tiles would leave most SMs idle.
   const long long m_tiles = (long long)kp.tiles_x * kp.tiles_y * kp.batch;
   int bn = g_force_bn;
+  // CTA pairs (256-row tiles, B split across the pair) once there is a full machine of pair tiles
+  const long long pair_tiles = ((m_tiles + 1) / 2) * hvr_cdiv(g->n, 256);
+  if (g->passes >= 3 && g->n >= 128 && ((bn == 0 && pair_tiles >= 74) || bn == 512)) return launch2<256>(g, kp, st);
   if (bn == 0) {
     if (g->n <= 64) bn = 64;
     else if (g->n % 256 == 0 && m_tiles * (g->n / 256) >= 2 * 148) bn = 256;
@@ -560,7 +780,7 @@ extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
 }
 
 extern "C" int hvr_debug_force_bn(int bn) {
-  if (bn != 0 && bn != 64 && bn != 128 && bn != 256) return HVR_ERR_ARG;
+  if (bn != 0 && bn != 64 && bn != 128 && bn != 256 && bn != 512) return HVR_ERR_ARG;   // 512 = CTA-pair kernel
   g_force_bn = bn;
   return HVR_OK;
 }

@@ -57,7 +57,9 @@ out = open(sys.argv[1], 'w') if len(sys.argv) > 1 else sys.stdout
 out.write('case,bn,passes,us,algorithmic_TFLOPs\n')
 for name, mk in CASES:
     for passes in (3, 1):
-        for bn in (64, 128, 256):
+        for bn in (64, 128, 256, 512):
+            if bn == 512 and passes != 3:
+                continue
             fn, flops = mk(passes)
             _lib.lib().hvr_debug_force_bn(bn)
             try:

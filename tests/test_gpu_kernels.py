@@ -83,10 +83,11 @@ def test_igemm_linear(cuda, M, K, N, relu, use_res, use_bias):
     assert _rel(of2[:, :N].double().cpu(), ref) < 1e-5
 
 
-@pytest.mark.parametrize('bn', [64, 128, 256])
+@pytest.mark.parametrize('bn', [64, 128, 256, 512])
 def test_igemm_tile_widths(cuda, bn):
-    """Every N-tile instantiation of the persistent kernel on a multi-tile, multi-wave problem
-    (more tiles than SMs, so each CTA walks several tiles through both TMEM buffers)."""
+    """Every N-tile instantiation of the persistent kernel (512 = the cta_group::2 pair kernel) on a
+    multi-tile, multi-wave problem (more tiles than SMs, so each CTA walks several tiles through
+    both TMEM buffers)."""
     from hvrnet_b200 import _lib, ops
     g = torch.Generator().manual_seed(bn)
     M, K, N = 128 * 41 + 17, 320, 768
@@ -101,6 +102,49 @@ def test_igemm_tile_widths(cuda, bn):
         _lib.lib().hvr_debug_force_bn(0)
     ref = _ref_linear(a, w, N, bias, None, True, 1.0)
     assert _rel(of.double().cpu(), ref) < 3e-5
+
+
+@pytest.mark.parametrize('M,K,N', [(128 * 43, 320, 768), (100, 64, 128), (128 * 3 + 5, 1024, 4500)])
+def test_igemm_cta_pair_odd_tiles(cuda, M, K, N):
+    """cta_group::2 kernel: odd number of 128-row tiles (the peer CTA of the last pair runs on
+    zero-filled rows), ragged N (last B half-tile out of range), residual + transposed outputs."""
+    from hvrnet_b200 import _lib, ops
+    g = torch.Generator().manual_seed(M + N)
+    a = ops.split(torch.randn(M, K, generator=g).to(cuda))
+    w = ops.split((torch.randn(ops.round_up(N, 64), K, generator=g) / math.sqrt(K)).to(cuda))
+    bias = torch.randn(ops.round_up(N, 64), generator=g).to(cuda)
+    res = ops.split(torch.randn(M, ops.round_up(N, 8), generator=g).to(cuda))
+    assert _lib.lib().hvr_debug_force_bn(512) == 0
+    try:
+        out, of, oT = ops.linear(a, w, N, bias=bias, relu=False, res=res, want_split=True, want_f32=True, want_T=True)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().hvr_debug_force_bn(0)
+    ref = _ref_linear(a, w, N, bias, res, False, 1.0)
+    assert _rel(of[:, :N].double().cpu(), ref) < 3e-5
+    assert _rel(ops.merge(Split_rows(out))[:, :N].double().cpu(), ref) < 3e-5
+    assert _rel(ops.merge(Split_rows(oT))[:N, :M].t().double().cpu(), ref) < 3e-5
+
+
+def test_igemm_cta_pair_conv(cuda):
+    import torch.nn.functional as F
+    from hvrnet_b200 import _lib, engine, ops
+    g = torch.Generator().manual_seed(8)
+    B, H, W, C, N, k, dil = 3, 38, 63, 128, 256, 3, 2
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(N, C, k, k, generator=g) / math.sqrt(C * k * k)
+    xs = ops.nchw_to_nhwc_split(x.to(cuda))
+    cp = engine.ConvP(engine.pack_conv(w, None, cuda), torch.zeros(N, device=cuda), N, k, C, dil)
+    _lib.lib().hvr_debug_force_bn(512)
+    try:
+        out, _ = engine.conv(xs, cp, relu=True)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().hvr_debug_force_bn(0)
+    xm = ops.nhwc_split_to_nchw(xs).double().cpu()
+    wm = ops.merge(cp.w).double().cpu()[:N].view(N, k, k, C).permute(0, 3, 1, 2)
+    ref = F.conv2d(xm, wm, padding=dil, dilation=dil).clamp_min(0)
+    assert _rel(ops.nhwc_split_to_nchw(out).double().cpu(), ref) < 3e-5
 
 
 def Split_rows(s):

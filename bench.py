@@ -300,6 +300,39 @@ def main():
     if peaks and 'bf16_tflops_sustained' in peaks:
         peak, peak_src = float(peaks['bf16_tflops_sustained']), 'MEASURED_PEAKS.json bf16_tflops_sustained'
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+
+    # second named figure of the metric: RoIAlign achieved HBM GB/s on the step's batched launch
+    # (T frames x 300 proposals, 256-channel 38x63 maps, NHWC in -> split rows out)
+    def roi_align_roofline():
+        g = torch.Generator().manual_seed(5)
+        Tn = T * V
+        feat = torch.randn(Tn, 38, 63, 256, generator=g).to(dev)
+        x1 = torch.rand(Tn * 300, generator=g) * 800
+        y1 = torch.rand(Tn * 300, generator=g) * 450
+        wh = torch.rand(Tn * 300, 2, generator=g) * 380 + 16
+        rois = torch.stack([(torch.arange(Tn * 300) // 300).float(), x1, y1, (x1 + wh[:, 0]).clamp(max=999),
+                            (y1 + wh[:, 1]).clamp(max=599)], 1).to(dev)
+        fn = lambda: ops.roi_align(feat, rois, feat_nhwc=True, out_nhwc=True, want_split=True, want_f32=False)
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        reps = 10
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        us = a.elapsed_time(b) / reps * 1e3
+        nbytes = 17510256.0 * Tn           # write 15 052 800 + map 2 451 456 + rois 6 000 per frame
+        hbm_peak, src = 6650.0, 'fallback (B200_PROFILING.md: 6.65 TB/s)'
+        if peaks and 'hbm_gbs' in peaks:
+            hbm_peak, src = float(peaks['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs'
+        gbs = nbytes / us / 1e3
+        return {'bound': 'hbm', 'kernel': 'roi_samples_kernel + roi_align_resident_kernel', 'frames': Tn,
+                'rois': Tn * 300, 'us_per_launch': us, 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': gbs / hbm_peak, 'peak_source': src, 'algorithmic_bytes': nbytes}
+    roi_rf = roi_align_roofline()
     line = {
         'metric': 'VID key frames/sec (1000x600, 300 proposals)', 'value': fps, 'unit': 'frames/s', 'n_gpus': world,
         'steps': K, 'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak',
@@ -324,6 +357,7 @@ def main():
                      'note': 'achieved counts algorithmic fp32-equivalent FLOPs; the kernel issues 3 bf16 MMAs per '
                              'product (tensor-pipe work = 3x), so frac <= 1/3 by construction'},
     }
+    line['roi_align'] = roi_rf
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             sec, done = cpu_key_frame_seconds(args.workload, max_seconds=60.0, steps=1)

@@ -118,21 +118,22 @@ __global__ void __launch_bounds__(128) nms_scan_kernel(const unsigned long long*
 // Box j (score order) survives iff no already-kept box i has IoU(i, j) > thr - the same
 // decision the mask + scan pair takes, but only the pairs (candidate, kept) are ever
 // evaluated and the walk stops after max_keep survivors: ~n_visited * max_keep IoUs instead of
-// n^2 / 2 (300-of-6000 proposals: ~30x less work, no mask in HBM).  512 threads; per chunk of
-// 64 candidates: (1) all threads test candidates against the kept list, (2) all threads
-// build the 64x64 in-chunk mask, (3) one thread resolves the chunk serially.
-__global__ void __launch_bounds__(512) nms_greedy_kernel(const float4* __restrict__ boxes, int n_cap, float thr,
-                                                         int strict_gt, int max_keep, int* __restrict__ keep_sorted,
-                                                         int* __restrict__ n_keep) {
+// n^2 / 2 (300-of-6000 proposals: ~30x less work, no mask in HBM).  1024 threads; per chunk of
+// 64 candidates: (1) 16 slices of the kept list tested in parallel per candidate, (2) the 64x64
+// in-chunk mask, (3) one thread resolves the chunk with one iteration per survivor.
+__global__ void __launch_bounds__(1024) nms_greedy_kernel(const float4* __restrict__ boxes, int n_cap, float thr,
+                                                          int strict_gt, int max_keep, int* __restrict__ keep_sorted,
+                                                          int* __restrict__ n_keep) {
   extern __shared__ float4 kept[];   // [max_keep]
   __shared__ float4 cand[64];
   __shared__ unsigned long long diag[64];
-  __shared__ int sflag[64];
+  __shared__ unsigned long long supp;
   __shared__ int nk_s;
   const int seg = blockIdx.x;
   const float4* bx = boxes + (size_t)seg * n_cap;
   int* ks = keep_sorted + (size_t)seg * n_cap;
   const int tid = threadIdx.x;
+  const int c = tid & 63, sl = tid >> 6;             // candidate, slice (16 slices)
   if (tid == 0) nk_s = 0;
   __syncthreads();
   for (int base = 0; base < n_cap; base += 64) {
@@ -140,22 +141,22 @@ __global__ void __launch_bounds__(512) nms_greedy_kernel(const float4* __restric
     if (tid < 64) {
       if (tid < lim) cand[tid] = bx[base + tid];
       diag[tid] = 0ULL;
-      sflag[tid] = 0;
+      if (tid == 0) supp = 0ULL;
     }
     __syncthreads();
     const int nk = nk_s;
-    const int c = tid & 63;
     if (c < lim) {
       const float4 cb = cand[c];
+      // (1) candidate c against the kept list, 16 slices of the list in parallel
       bool sup = false;
-      for (int k = tid >> 6; k < nk && !sup; k += 8) {
+      for (int k = sl; k < nk; k += 16) {
         const float v = dev_iou(kept[k], cb);
-        sup = strict_gt ? (v > thr) : (v >= thr);
+        if (strict_gt ? (v > thr) : (v >= thr)) { sup = true; break; }
       }
-      if (sup) sflag[c] = 1;
-      // in-chunk pairs (c, j), j > c: 8 slices of j per candidate
+      if (sup) atomicOr(&supp, 1ULL << c);
+      // (2) in-chunk pairs (c, j), j > c
       unsigned long long bits = 0;
-      for (int j = c + 1 + (tid >> 6); j < lim; j += 8) {
+      for (int j = c + 1 + sl; j < lim; j += 16) {
         const float v = dev_iou(cb, cand[j]);
         if (strict_gt ? (v > thr) : (v >= thr)) bits |= 1ULL << j;
       }
@@ -163,14 +164,16 @@ __global__ void __launch_bounds__(512) nms_greedy_kernel(const float4* __restric
     }
     __syncthreads();
     if (tid == 0) {
-      unsigned long long rm = 0;
+      // (3) serial resolve, one iteration per SURVIVOR of the chunk
+      unsigned long long alive = ~supp;
+      if (lim < 64) alive &= (1ULL << lim) - 1ULL;
       int k = nk;
-      for (int b = 0; b < lim && k < max_keep; ++b) {
-        if (sflag[b] || ((rm >> b) & 1ULL)) continue;
+      while (alive && k < max_keep) {
+        const int b = __ffsll((long long)alive) - 1;
         kept[k] = cand[b];
         ks[k] = base + b;
         ++k;
-        rm |= diag[b];
+        alive &= ~(diag[b] | (1ULL << b));
       }
       nk_s = k;
     }
@@ -480,7 +483,7 @@ extern "C" int hvr_rpn_proposals(const float* cls, int64_t ld_cls, const float* 
     HVR_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr = true;
   }
-  nms_greedy_kernel<<<T, 512, (size_t)cap * sizeof(float4), st>>>(boxes, npre, nms_thr, 1, cap, keep_sorted, n_keep);
+  nms_greedy_kernel<<<T, 1024, (size_t)cap * sizeof(float4), st>>>(boxes, npre, nms_thr, 1, cap, keep_sorted, n_keep);
   HVR_LAUNCHED();
   rpn_emit_kernel<<<T, 128, 0, st>>>(keep_sorted, n_keep, boxes, scores, idx_out, n_anc, npre, max_num, proposals,
                                      counts, top_idx);

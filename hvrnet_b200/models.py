@@ -232,16 +232,23 @@ class RPNHead(_Packed):
         P['base'] = self.base_anchors.to(device)
         return P
 
-    def get_proposals(self, c4_split, img_shape, cfg, want_idx=False):
-        """All frames in one pass -> proposals [T,max_num,5], counts [T] (device)."""
-        P = self.packed(c4_split.hi.device)
-        o = engine.rpn_forward(P, c4_split)                      # [T,h,w,64]
+    def forward_maps(self, c4_split):
+        """rpn_head.py:30-35 for all frames -> fp32 [T,h,w,64]: columns [0,A) logits, [A,5A) deltas."""
+        return engine.rpn_forward(self.packed(c4_split.hi.device), c4_split)
+
+    def proposals_from_maps(self, o, img_shape, cfg, want_idx=False):
+        """anchor_head.py:209-278 + rpn_head.py:55-104, all frames in one pass ->
+        proposals [T,max_num,5], counts [T] (device)."""
+        P = self.packed(o.device)
         T, h, w, ld = o.shape
         A = self.num_anchors
         assert not cfg.get('nms_across_levels', False) and cfg.get('min_bbox_size', 0) == 0
         return ops.rpn_proposals(o, o.view(-1)[A:], ld, ld, T, h, w, A, P['base'], self.anchor_strides[0],
                                  img_shape[:2], cfg['nms_pre'], cfg['nms_post'], cfg['max_num'], cfg['nms_thr'],
                                  want_idx=want_idx)
+
+    def get_proposals(self, c4_split, img_shape, cfg, want_idx=False):
+        return self.proposals_from_maps(self.forward_maps(c4_split), img_shape, cfg, want_idx)
 
 
 class RoIAlign(nn.Module):

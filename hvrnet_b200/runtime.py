@@ -106,24 +106,43 @@ class GraphRunner:
             _, h, w, C = windows[0][0].shape
             win = ops.Split.zeros((V * T, h, w, C), dev)
 
+            side = [torch.cuda.Stream(), torch.cuda.Stream()]
+
             def fn():
+                main = torch.cuda.current_stream()
+                # RPN maps first; proposal generation (sort + decode + greedy NMS: 15 busy CTAs, latency
+                # bound) then runs on a forked branch UNDER the C5 convolutions instead of after them
+                maps = m.rpn_head.forward_maps(win)
+                side[0].wait_stream(main)
+                with torch.cuda.stream(side[0]):
+                    props, counts = m.rpn_head.proposals_from_maps(maps, meta['img_shape'], m.test_cfg.rpn)
                 c5 = m.shared_head.forward_nhwc(win) if m.feat_from_shared_head else ops.merge(win)
-                props, counts = m.rpn_head.get_proposals(win, meta['img_shape'], m.test_cfg.rpn)
+                main.wait_stream(side[0])
                 fidx = torch.arange(V * T, device=dev, dtype=torch.float32).view(V * T, 1, 1).expand(V * T, P, 1)
                 rois = torch.cat([fidx, props[..., :4]], -1).view(-1, 5).contiguous()
                 rows = m.bbox_roi_extractor.roi_layers[0].forward_nhwc_split(c5, rois)
                 flat = [counts.float()]
+                keep = [maps, props, counts, c5, rois, rows]
                 s = m.key_dim * P
                 for v in range(V):
                     o = v * T * P
                     cls, reg = m._head(rows[o:o + T * P], [dict(start=s, length=P)], None)
                     rois_key = rois[o + s:o + s + P].clone()
                     rois_key[:, 0] = 0
-                    outs = m.bbox_head.get_det_bboxes(rois_key, cls, reg, meta['img_shape'], sf, rescale=rescale,
-                                                      cfg=m.test_cfg.rcnn)
+                    # the head outputs are post-processed on parallel branches (tiny, latency-bound kernels)
+                    outs = []
+                    for j, (c_, r_) in enumerate(zip(cls, reg)):
+                        st = side[j % 2]
+                        st.wait_stream(main)
+                        with torch.cuda.stream(st):
+                            outs.append(m.bbox_head.get_det_bboxes(rois_key, c_, r_, meta['img_shape'], sf,
+                                                                   rescale=rescale, cfg=m.test_cfg.rcnn))
+                    for st in side:
+                        main.wait_stream(st)
+                    keep += [cls, reg, rois_key, outs]
                     for d, l, k in outs:
                         flat += [k.float(), d.reshape(-1), l.float()]
-                return torch.cat(flat)
+                return torch.cat(flat), keep
             fill(win)                                   # real data for the warm-up pass
             c = self._capture(fn)
             c.inputs = win
@@ -131,7 +150,7 @@ class GraphRunner:
         fill(c.inputs)
         c.graph.replay()
         self.replayed_launches += c.launches
-        host = c.outputs.cpu()                          # the one device->host read of the step
+        host = c.outputs[0].cpu()                       # the one device->host read of the step
         n_out = (host.numel() - V * T) // (V * (1 + 6 * M))
         res, o = [], V * T
         for v in range(V):

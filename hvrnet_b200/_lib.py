@@ -51,7 +51,7 @@ SIGNATURES = {
     'hvr_im2col_stem': (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp]),
     'hvr_maxpool3x3s2_split': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp]),
     'hvr_roi_align_fwd': (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_int,
-                                  c_vp, c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+                                  c_vp, c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),
     'hvr_nms_workspace_bytes': (c_sz, [c_int]),
     'hvr_nms': (c_int, [c_vp, c_int, c_f32, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'hvr_rpn_workspace_bytes': (c_sz, [c_int, c_int, c_int]),

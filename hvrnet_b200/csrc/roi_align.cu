@@ -155,136 +155,6 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const float* __restrict_
   }
 }
 
-// ------------------------------------------------------------------------------------
-// Map-resident variant (the pipeline's path: NHWC in, NHWC / split out).
-// With 7x7x4 samples spread over a large RoI every bilinear tap is a distinct pixel, so the
-// per-RoI kernel above pulls 16 tap vectors through the L2->SM path per output vector
-// (3.6 GB per 4500-RoI launch: L2-bandwidth bound at ~12 TB/s, not HBM bound).  Here a CTA
-// owns (image, 16-channel slice): the whole H*W x 16ch slice of the map (153 KB for 38x63) is
-// staged in shared memory ONCE and every RoI of that image is served from it, so L2->SM
-// traffic falls to ~the map + the sample records and the kernel becomes write-bound.
-//   kernel 1  roi_samples_kernel: one 16-byte record per (roi, bin, sample): the 4 tap pixel
-//             indices + (ly, lx); computed once instead of once per channel slice
-//   kernel 2  roi_align_resident_kernel: grid (C/16, n_imgs, splits); item = (roi, bin,
-//             4-channel quad); weights are rebuilt as hy*hx ... exactly like make_tap, so the
-//             result stays bit-identical to the per-RoI kernel and to the oracle.
-// ------------------------------------------------------------------------------------
-struct SampleRec {
-  unsigned short p0, p1, p2, p3;   // pixel indices (y*W + x) of lt, rt, lb, rb; p0 == 0xFFFF: sample is 0
-  float ly, lx;
-};
-
-__global__ void roi_samples_kernel(const float* __restrict__ rois, int n_rois, int n_imgs, int H, int W, int ph,
-                                   int pw, float scale, int sn, SampleRec* __restrict__ recs) {
-  const int ns = sn * sn, per_roi = ph * pw * ns;
-  const long long total = (long long)n_rois * per_roi;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int roi = (int)(i / per_roi), k = (int)(i % per_roi);
-    const int s = k % ns, bin = k / ns;
-    const int ix = s % sn, iy = s / sn;
-    const int q = bin % pw, p = bin / pw;
-    const RoiGeom g = roi_geom(rois + (size_t)roi * 5, scale, ph, pw, n_imgs);
-    float y = g.sh + (float)p * g.bh + ((float)iy + 0.5f) * g.bh / (float)sn;
-    float x = g.sw + (float)q * g.bw + ((float)ix + 0.5f) * g.bw / (float)sn;
-    SampleRec r;
-    if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) {
-      r.p0 = r.p1 = r.p2 = r.p3 = 0xFFFF;
-      r.ly = r.lx = 0.f;
-    } else {
-      if (y <= 0) y = 0;
-      if (x <= 0) x = 0;
-      int yl = (int)y, xl = (int)x, yh, xh;
-      if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else { yh = yl + 1; }
-      if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else { xh = xl + 1; }
-      r.ly = y - (float)yl;
-      r.lx = x - (float)xl;
-      r.p0 = (unsigned short)(yl * W + xl); r.p1 = (unsigned short)(yl * W + xh);
-      r.p2 = (unsigned short)(yh * W + xl); r.p3 = (unsigned short)(yh * W + xh);
-    }
-    recs[i] = r;
-  }
-}
-
-constexpr int RA_CH = 16;        // channels per CTA slice
-constexpr int RA_THREADS = 512;
-
-__global__ void __launch_bounds__(RA_THREADS, 1)
-    roi_align_resident_kernel(const float* __restrict__ feat, const float* __restrict__ rois,
-                              const SampleRec* __restrict__ recs, int n_rois, int n_imgs, int C, int HW, int nbins,
-                              int ns, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
-                              __nv_bfloat16* __restrict__ out_lo, long long ld_split) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  float4* map = reinterpret_cast<float4*>(smem);                       // [HW][4] float4 = 16 channels / pixel
-  int* list = reinterpret_cast<int*>(smem + (size_t)HW * RA_CH * 4);   // rois of this image (this split)
-  __shared__ int n_list;
-  const int c0 = blockIdx.x * RA_CH, img = blockIdx.y, split = blockIdx.z, nsplit = gridDim.z;
-  const int tid = threadIdx.x;
-  // ---- stage the map slice: 4 lanes fetch the 64 contiguous bytes of one pixel
-  const float* fm = feat + (size_t)img * HW * C + c0;
-  for (int i = tid; i < HW * 4; i += RA_THREADS)
-    map[i] = __ldg(reinterpret_cast<const float4*>(fm + (size_t)(i >> 2) * C) + (i & 3));
-  // ---- rois of this image, round-robin over the splits (warp-aggregated compaction)
-  if (tid == 0) n_list = 0;
-  __syncthreads();
-  int seen = 0;   // per-thread running index is not needed: round-robin on the compacted position
-  for (int base = 0; base < n_rois; base += RA_THREADS) {
-    const int r = base + tid;
-    bool mine = false;
-    if (r < n_rois) {
-      int b = (int)rois[(size_t)r * 5];
-      b = b < 0 ? 0 : (b >= n_imgs ? n_imgs - 1 : b);
-      mine = (b == img) && ((r % nsplit) == split);
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, mine);
-    int pos = 0;
-    if ((tid & 31) == 0 && m) pos = atomicAdd(&n_list, __popc(m));
-    pos = __shfl_sync(0xffffffffu, pos, 0);
-    if (mine) list[pos + __popc(m & ((1u << (tid & 31)) - 1u))] = r;
-  }
-  (void)seen;
-  __syncthreads();
-  const int nl = n_list;
-  const float cnt = (float)ns;
-  const int items = nl * nbins * 4;
-  for (int it = tid; it < items; it += RA_THREADS) {
-    const int quad = it & 3;
-    const int bin = (it >> 2) % nbins;
-    const int roi = list[(it >> 2) / nbins];
-    const SampleRec* rp = recs + ((size_t)roi * nbins + bin) * ns;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < ns; ++s) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(rp + s));
-      const unsigned p0 = raw.x & 0xFFFFu, p1 = raw.x >> 16, p2 = raw.y & 0xFFFFu, p3 = raw.y >> 16;
-      if (p0 == 0xFFFFu) continue;
-      const float ly = __uint_as_float(raw.z), lx = __uint_as_float(raw.w);
-      const float hy = 1.0f - ly, hx = 1.0f - lx;
-      const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-      const float4 a = map[p0 * 4 + quad], b = map[p1 * 4 + quad], c = map[p2 * 4 + quad], d = map[p3 * 4 + quad];
-      acc.x = acc.x + (((w1 * a.x + w2 * b.x) + w3 * c.x) + w4 * d.x);
-      acc.y = acc.y + (((w1 * a.y + w2 * b.y) + w3 * c.y) + w4 * d.y);
-      acc.z = acc.z + (((w1 * a.z + w2 * b.z) + w3 * c.z) + w4 * d.z);
-      acc.w = acc.w + (((w1 * a.w + w2 * b.w) + w3 * c.w) + w4 * d.w);
-    }
-    acc.x = acc.x / cnt; acc.y = acc.y / cnt; acc.z = acc.z / cnt; acc.w = acc.w / cnt;
-    const int ch = c0 + quad * 4;
-    if (out) *reinterpret_cast<float4*>(out + ((size_t)roi * nbins + bin) * C + ch) = acc;
-    if (out_hi) {
-      __nv_bfloat16 h[4], l[4];
-      split2(acc.x, h[0], l[0]); split2(acc.y, h[1], l[1]);
-      split2(acc.z, h[2], l[2]); split2(acc.w, h[3], l[3]);
-      const size_t o = (size_t)roi * ld_split + (size_t)bin * C + ch;
-      uint2 hv, lv;
-      hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
-      hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
-      lv.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
-      lv.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
-      *reinterpret_cast<uint2*>(out_hi + o) = hv;
-      *reinterpret_cast<uint2*>(out_lo + o) = lv;
-    }
-  }
-}
-
 // Generic path (adaptive sample_num == 0, or very large sampling grids): reference-style, one
 // thread per output element, NHWC or NCHW output.
 __global__ void roi_align_generic_kernel(const float* __restrict__ feat, const float* __restrict__ rois, int n_rois,
@@ -326,7 +196,7 @@ __global__ void roi_align_generic_kernel(const float* __restrict__ feat, const f
 extern "C" int hvr_roi_align_fwd(const float* feat, int feat_nhwc, const float* rois, int n_rois, int n_imgs, int C,
                                  int H, int W, int ph, int pw, float spatial_scale, int sample_num, float* out,
                                  int out_layout, hvr_bf16* out_hi, hvr_bf16* out_lo, int64_t ld_split, float* ws,
-                                 void* ws_samples, void* stream) {
+                                 void* stream) {
   if (n_rois == 0) return HVR_OK;   // empty in, empty out (the caller's output tensor has no rows)
   if (!feat || !rois || n_rois < 0 || n_imgs < 1 || C < 1 || H < 1 || W < 1 || ph < 1 || pw < 1) return HVR_ERR_ARG;
   if (!out && !out_hi) return HVR_ERR_ARG;
@@ -350,37 +220,6 @@ extern "C" int hvr_roi_align_fwd(const float* feat, int feat_nhwc, const float* 
     if (blocks > 148 * 64) blocks = 148 * 64;
     roi_align_generic_kernel<<<(int)blocks, 256, 0, st>>>(feat, rois, n_rois, n_imgs, C, H, W, ph, pw, spatial_scale,
                                                           sample_num, out, out_layout == 0);
-    HVR_LAUNCHED();
-    return HVR_OK;
-  }
-  const size_t res_smem = (size_t)H * W * RA_CH * 4 + (size_t)n_rois * 4;
-  if (out_layout == 1 && C % RA_CH == 0 && H * W < 65535 && res_smem <= 220 * 1024 && ws_samples && n_rois >= 64) {
-    SampleRec* recs = reinterpret_cast<SampleRec*>(ws_samples);
-    const long long total = (long long)n_rois * nsamp;
-    long long blocks = (total + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    roi_samples_kernel<<<(int)blocks, 256, 0, st>>>(rois, n_rois, n_imgs, H, W, ph, pw, spatial_scale, sample_num,
-                                                    recs);
-    HVR_LAUNCHED();
-    static bool attr2 = false;
-    if (!attr2) {
-      HVR_CUDA(cudaFuncSetAttribute(roi_align_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    220 * 1024));
-      attr2 = true;
-    }
-    // splits: fill the 148 SMs with (C/16 * n_imgs * splits) single-CTA-per-SM blocks, few idle slots
-    const int base_ctas = (C / RA_CH) * n_imgs;
-    int best_s = 1;
-    double best_eff = 0.0;
-    for (int sp = 1; sp <= 12; ++sp) {
-      const int ctas = base_ctas * sp;
-      const int waves = (ctas + 147) / 148;
-      const double eff = (double)ctas / (waves * 148.0) - 0.01 * sp;   // mild penalty: every split re-stages the map
-      if (eff > best_eff) { best_eff = eff; best_s = sp; }
-    }
-    roi_align_resident_kernel<<<dim3(C / RA_CH, n_imgs, best_s), RA_THREADS, res_smem, st>>>(
-        feat, rois, recs, n_rois, n_imgs, C, H * W, ph * pw, sample_num * sample_num, out, (__nv_bfloat16*)out_hi,
-        (__nv_bfloat16*)out_lo, ld_split);
     HVR_LAUNCHED();
     return HVR_OK;
   }

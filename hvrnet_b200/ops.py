@@ -223,7 +223,7 @@ def linear(a, w, n, bias=None, relu=False, res=None, alpha=1.0, want_split=True,
 # ----------------------------------------------------------------------------------------
 
 def roi_align(feat, rois, out_size=7, spatial_scale=1 / 16., sample_num=2, feat_nhwc=False, out_nhwc=False,
-              want_split=False, ld_split=None, want_f32=True, resident=True):
+              want_split=False, ld_split=None, want_f32=True):
     """feat fp32 NCHW (reference layout) or NHWC; rois [n,5].  Returns fp32 output in the
     reference layout [n,C,ph,pw] (or [n,ph,pw,C] when out_nhwc), plus an optional Split
     [n, ld_split] copy in NHWC order."""
@@ -246,13 +246,10 @@ def roi_align(feat, rois, out_size=7, spatial_scale=1 / 16., sample_num=2, feat_
         ld_split = ld_split or ph * pw * C
         sp = Split.empty((n, ld_split), dev)
     ws = None if feat_nhwc else torch.empty(feat.numel(), dtype=torch.float32, device=dev)
-    wss = None
-    if resident and out_nhwc and sample_num > 0 and n > 0:       # sample records of the map-resident kernel
-        wss = torch.empty(n * ph * pw * sample_num * sample_num * 16, dtype=torch.uint8, device=dev)
     check(_lib.lib().hvr_roi_align_fwd(_p(feat), int(feat_nhwc), _p(rois), n, B, C, H, W, ph, pw, float(spatial_scale),
                                        int(sample_num), _p(out), 1 if out_nhwc else 0,
                                        _p(sp.hi) if sp else None, _p(sp.lo) if sp else None,
-                                       ld_split or 0, _p(ws), _p(wss), _stream()), 'hvr_roi_align_fwd')
+                                       ld_split or 0, _p(ws), _stream()), 'hvr_roi_align_fwd')
     return (out, sp) if want_split else out
 
 

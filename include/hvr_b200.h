@@ -142,15 +142,12 @@ int hvr_maxpool3x3s2_split(const hvr_bf16* hi, const hvr_bf16* lo, int B, int H,
  *           out_layout 1 -> [n_rois, ph, pw, C] fp32
  *   out_hi/out_lo (optional, out_layout 1 order, row pitch ld_split elements): split copy
  *           feeding fc_new_1 directly.
- *   ws_samples (optional): n_rois*ph*pw*sample_num^2*16 bytes.  When given with out_layout 1
- *           the map-resident kernel is used (each 16-channel slice of an image's map is staged in
- *           shared memory once and serves all of that image's RoIs); results are bit-identical.
  * A roi whose batch index is outside [0, n_imgs) is clamped (the reference reads out of bounds).
  * ---------------------------------------------------------------------------------- */
 int hvr_roi_align_fwd(const float* feat, int feat_nhwc, const float* rois, int n_rois, int n_imgs,
                       int C, int H, int W, int ph, int pw, float spatial_scale, int sample_num,
                       float* out, int out_layout, hvr_bf16* out_hi, hvr_bf16* out_lo,
-                      int64_t ld_split, float* ws, void* ws_samples, void* stream);
+                      int64_t ld_split, float* ws, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * NMS.  Replaces nms_cuda.nms (nms_kernel.cu:71-136, strict `>`; strict_gt=0 gives

@@ -32,11 +32,6 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
-// epilogue staging: per epilogue warp a 32-row transpose buffer (row pitch 144 B: conflict-free
-// 16-byte accesses both row-wise and segment-wise) + the 32 global row indices of its rows
-constexpr int EPI_STAGE_BYTES = 32 * 144;
-constexpr int EPI_WARP_BYTES = EPI_STAGE_BYTES + 32 * 8;
-constexpr int EPI_SMEM = 4 * EPI_WARP_BYTES;
 
 struct alignas(64) KParams {
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
@@ -48,7 +43,6 @@ struct alignas(64) KParams {
   int n, n_tiles;
   int passes;
   int relu;
-  int coalesce;   // all leading dimensions / pointers allow 16-byte row segments: staged epilogue
   float alpha;
   const float* bias;
   const __nv_bfloat16* res_hi;
@@ -69,13 +63,32 @@ struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (BN == 64) ? 4 : (BN == 128 ? 3 : 2);
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_SMEM;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;   // two accumulator buffers: epilogue(i) overlaps mainloop(i+1)
 };
 
 // Epilogue for 32 consecutive columns of one output row.
+struct ResRegs {
+  uint4 h[4], l[4];
+  bool valid;     // registers hold the residual of this chunk (fast path), else epilogue_chunk loads it itself
+};
+// Issue the residual loads of one 32-column chunk (16-byte vectors along the row).  Called one
+// chunk ahead so the L2/HBM latency hides behind the previous chunk's tcgen05.ld + math + stores.
+__device__ __forceinline__ void prefetch_res(const KParams& p, long long row, int n_base, bool row_ok, ResRegs& r) {
+  r.valid = false;
+  if (!p.res_hi || !row_ok || p.n - n_base < 32 || (p.ld_res % 8) != 0) return;
+  const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + row * p.ld_res + n_base);
+  const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + row * p.ld_res + n_base);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    r.h[j] = __ldg(rh + j);
+    r.l[j] = __ldg(rl + j);
+  }
+  r.valid = true;
+}
+
 __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t (&acc)[32], long long row,
-                                               int n_base, bool row_ok) {
+                                               int n_base, bool row_ok, const ResRegs& pre) {
   if (!row_ok) return;
   const int n_left = p.n - n_base;
   if (n_left <= 0) return;
@@ -99,11 +112,11 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t 
   if (p.res_hi) {
     const __nv_bfloat16* rh = p.res_hi + row * p.ld_res + n_base;
     const __nv_bfloat16* rl = p.res_lo + row * p.ld_res + n_base;
-    if (full && (p.ld_res % 8 == 0)) {
+    if (pre.valid) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
-        const uint4 h = __ldg(reinterpret_cast<const uint4*>(rh + j));
-        const uint4 l = __ldg(reinterpret_cast<const uint4*>(rl + j));
+        const uint4 h = pre.h[j / 8];
+        const uint4 l = pre.l[j / 8];
         const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
         const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
@@ -175,118 +188,6 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t 
   }
 }
 
-// Coalesced epilogue for 32 full columns: the thread-per-row register layout that tcgen05.ld
-// delivers is transposed through a per-warp shared-memory buffer so that global accesses are
-// row-contiguous (8 lanes x 16 B = one 128-byte line segment per row) instead of 32 different
-// rows per instruction.  Cuts the L1/L2 wavefronts of the epilogue 4-8x; the K<=512, N=2048
-// residual convolutions were epilogue-bound (33 % tensor-pipe) without it.
-__device__ __forceinline__ void epilogue_chunk_co(const KParams& p, const uint32_t (&acc)[32], int n_base,
-                                                  uint8_t* stage, const long long* rowidx, int lane, long long row,
-                                                  bool row_ok) {
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * p.alpha;
-  if (p.bias) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + j));
-      v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-    }
-  }
-  uint8_t* mine = stage + lane * 80;       // bf16 chunk: 64 B per row, pitch 80 B
-  if (p.res_hi) {
-    uint32_t hw[16];
-#pragma unroll
-    for (int arr = 0; arr < 2; ++arr) {
-      const __nv_bfloat16* src = arr == 0 ? p.res_hi : p.res_lo;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = 8 * i + (lane >> 2), seg = lane & 3;
-        const long long ro = rowidx[r];
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (ro >= 0) val = __ldg(reinterpret_cast<const uint4*>(src + ro * p.ld_res + n_base + seg * 8));
-        *reinterpret_cast<uint4*>(stage + r * 80 + seg * 16) = val;
-      }
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 w = *reinterpret_cast<const uint4*>(mine + j * 16);
-        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (arr == 0) {
-            hw[4 * j + q] = ww[q];
-          } else {
-            v[8 * j + 2 * q] += __fadd_rn(bf16bits_to_f32(hw[4 * j + q] & 0xFFFFu), bf16bits_to_f32(ww[q] & 0xFFFFu));
-            v[8 * j + 2 * q + 1] += __fadd_rn(bf16bits_to_f32(hw[4 * j + q] >> 16), bf16bits_to_f32(ww[q] >> 16));
-          }
-        }
-      }
-      __syncwarp();
-    }
-  }
-  if (p.relu) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-  }
-  if (p.out_f32) {
-    uint8_t* minef = stage + lane * 144;   // fp32 chunk: 128 B per row, pitch 144 B
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      *reinterpret_cast<float4*>(minef + j * 16) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = 4 * i + (lane >> 3), seg = lane & 7;
-      const long long ro = rowidx[r];
-      if (ro >= 0)
-        *reinterpret_cast<float4*>(p.out_f32 + ro * p.ld_f32 + n_base + seg * 4) =
-            *reinterpret_cast<const float4*>(stage + r * 144 + seg * 16);
-    }
-    __syncwarp();
-  }
-  if (p.out_hi || p.outT_hi) {
-    uint32_t hp[16], lp[16];
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split2(v[j], h0, l0);
-      split2(v[j + 1], h1, l1);
-      hp[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-      lp[j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-    }
-    if (p.out_hi) {
-#pragma unroll
-      for (int arr = 0; arr < 2; ++arr) {
-        __nv_bfloat16* dst = arr == 0 ? p.out_hi : p.out_lo;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(mine + j * 16) =
-              arr == 0 ? make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3])
-                       : make_uint4(lp[4 * j], lp[4 * j + 1], lp[4 * j + 2], lp[4 * j + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = 8 * i + (lane >> 2), seg = lane & 3;
-          const long long ro = rowidx[r];
-          if (ro >= 0)
-            *reinterpret_cast<uint4*>(dst + ro * p.ld_out + n_base + seg * 8) =
-                *reinterpret_cast<const uint4*>(stage + r * 80 + seg * 16);
-        }
-        __syncwarp();
-      }
-    }
-    if (p.outT_hi && row_ok) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const long long o = (long long)(n_base + j) * p.ld_outT + row;
-        p.outT_hi[o] = __ushort_as_bfloat16((unsigned short)((hp[j / 2] >> (16 * (j & 1))) & 0xFFFFu));
-        p.outT_lo[o] = __ushort_as_bfloat16((unsigned short)((lp[j / 2] >> (16 * (j & 1))) & 0xFFFFu));
-      }
-    }
-  }
-}
-
 // Persistent kernel: grid = min(#tiles, #SMs); CTA c processes tiles c, c+grid, ...  Tile index
 // runs N-fastest so the CTAs in flight share the same A (activation) tiles through L2 while
 // the (small) weight matrix stays L2-resident.
@@ -304,7 +205,6 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
   uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  uint8_t* epi_smem = reinterpret_cast<uint8_t*>(tmem_empty_bar + 2) + 64;   // 16-byte aligned (ring is 1024-aligned)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -429,22 +329,22 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
       const long long row = ((long long)bimg * p.out_h + py) * p.out_w + px;
       const int ab = lt & 1;
       const uint32_t aph = (uint32_t)((lt >> 1) & 1);
-      uint8_t* stage = epi_smem + (warp - 2) * EPI_WARP_BYTES;
-      long long* rowidx = reinterpret_cast<long long*>(stage + EPI_STAGE_BYTES);
-      if (p.coalesce) {
-        rowidx[lane] = row_ok ? row : -1;
-        __syncwarp();
-      }
+      ResRegs ra, rb;
+      prefetch_res(p, row, nt * BN, row_ok, ra);        // issued before the accumulator is even ready
       mbar_wait(&tmem_full_bar[ab], aph);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < BN; c0 += 64) {             // two chunks per trip: residual registers ping-pong
         uint32_t acc[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0), acc);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0);
+        tmem_ld_32x32b_x32(taddr, acc);
+        prefetch_res(p, row, nt * BN + c0 + 32, row_ok, rb);
         tmem_ld_wait();
-        const int nb = nt * BN + c0;
-        if (p.coalesce && p.n - nb >= 32) epilogue_chunk_co(p, acc, nb, stage, rowidx, lane, row, row_ok);
-        else epilogue_chunk(p, acc, row, nb, row_ok);
+        epilogue_chunk(p, acc, row, nt * BN + c0, row_ok, ra);
+        tmem_ld_32x32b_x32(taddr + 32, acc);
+        if (c0 + 64 < BN) prefetch_res(p, row, nt * BN + c0 + 64, row_ok, ra);
+        tmem_ld_wait();
+        epilogue_chunk(p, acc, row, nt * BN + c0 + 32, row_ok, rb);
       }
       tc_fence_before();
       __syncwarp();
@@ -472,7 +372,7 @@ struct Cfg2 {
   static constexpr int BH_BYTES = (BN / 2) * BK * 2;              // this CTA's half of one B tile
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;  // A hi/lo + B-half hi/lo
   static constexpr int STAGES = (BN == 256) ? 3 : 4;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256 + EPI_SMEM;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
@@ -490,7 +390,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
   uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  uint8_t* epi_smem = reinterpret_cast<uint8_t*>(tmem_empty_bar + 2) + 64;   // 16-byte aligned (ring is 1024-aligned)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -614,22 +513,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
       const long long row = ((long long)bimg * p.out_h + py) * p.out_w + px;
       const int ab = lt & 1;
       const uint32_t aph = (uint32_t)((lt >> 1) & 1);
-      uint8_t* stage = epi_smem + (warp - 2) * EPI_WARP_BYTES;
-      long long* rowidx = reinterpret_cast<long long*>(stage + EPI_STAGE_BYTES);
-      if (p.coalesce) {
-        rowidx[lane] = row_ok ? row : -1;
-        __syncwarp();
-      }
+      ResRegs ra, rb;
+      prefetch_res(p, row, nt * BN, row_ok, ra);        // issued before the accumulator is even ready
       mbar_wait(&tmem_full_bar[ab], aph);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < BN; c0 += 64) {             // two chunks per trip: residual registers ping-pong
         uint32_t acc[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0), acc);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0);
+        tmem_ld_32x32b_x32(taddr, acc);
+        prefetch_res(p, row, nt * BN + c0 + 32, row_ok, rb);
         tmem_ld_wait();
-        const int nb = nt * BN + c0;
-        if (p.coalesce && p.n - nb >= 32) epilogue_chunk_co(p, acc, nb, stage, rowidx, lane, row, row_ok);
-        else epilogue_chunk(p, acc, row, nb, row_ok);
+        epilogue_chunk(p, acc, row, nt * BN + c0, row_ok, ra);
+        tmem_ld_32x32b_x32(taddr + 32, acc);
+        if (c0 + 64 < BN) prefetch_res(p, row, nt * BN + c0 + 64, row_ok, ra);
+        tmem_ld_wait();
+        epilogue_chunk(p, acc, row, nt * BN + c0 + 32, row_ok, rb);
       }
       tc_fence_before();
       __syncwarp();
@@ -769,7 +668,6 @@ int validate(const HvrIGemm* g) {
 }
 
 int g_force_bn = 0;   // test hook (hvr_debug_force_bn): 0 = heuristic
-bool g_coalesce_enabled = true;   // test hook: bit 10 of hvr_debug_force_bn's argument disables the staged epilogue
 
 template <int BN>
 int launch(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
@@ -884,11 +782,6 @@ extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
   kp.n = g->n;
   kp.passes = g->passes >= 3 ? 3 : 1;
   kp.relu = g->relu;
-  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-  kp.coalesce = (!g->out_hi || (g->ld_out % 8 == 0 && al16(g->out_hi) && al16(g->out_lo))) &&
-                (!g->res_hi || (g->ld_res % 8 == 0 && al16(g->res_hi) && al16(g->res_lo))) &&
-                (!g->out_f32 || (g->ld_f32 % 4 == 0 && al16(g->out_f32))) && (!g->bias || al16(g->bias)) &&
-                g_coalesce_enabled;
   kp.alpha = g->alpha;
   kp.bias = g->bias;
   kp.res_hi = reinterpret_cast<const __nv_bfloat16*>(g->res_hi);
@@ -922,8 +815,6 @@ extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
 }
 
 extern "C" int hvr_debug_force_bn(int bn) {
-  g_coalesce_enabled = (bn & 1024) == 0;
-  bn &= ~1024;
   if (bn != 0 && bn != 64 && bn != 128 && bn != 256 && bn != 512) return HVR_ERR_ARG;   // 512 = CTA-pair kernel
   g_force_bn = bn;
   return HVR_OK;

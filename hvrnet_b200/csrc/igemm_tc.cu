@@ -32,9 +32,16 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
+// Epilogue staging per epilogue warp: residual hi|lo and output hi|lo tiles of 32 rows x 32 bf16
+// (64-byte rows, SWIZZLE_64B) = 4 x 2 KB, moved by TMA.
+constexpr int EPI_TILE_BYTES = 32 * 64;
+constexpr int EPI_WARP_BYTES = 4 * EPI_TILE_BYTES;
+constexpr int EPI_SMEM = 4 * EPI_WARP_BYTES;
 
 struct alignas(64) KParams {
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+  CUtensorMap tmO_hi, tmO_lo, tmR_hi, tmR_lo;   // epilogue: split output (TMA store) / residual (TMA load)
+  int tma_epi;                                   // bit 0: output through TMA, bit 1: residual through TMA
   int ntaps;
   int tap_dx[9], tap_dy[9];
   int C, cblocks;
@@ -63,7 +70,7 @@ struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (BN == 64) ? 4 : (BN == 128 ? 3 : 2);
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_SMEM + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;   // two accumulator buffers: epilogue(i) overlaps mainloop(i+1)
 };
 
@@ -87,11 +94,13 @@ __device__ __forceinline__ void prefetch_res(const KParams& p, long long row, in
   r.valid = true;
 }
 
+// `stage_out` != nullptr: the split output of this row is written (swizzled) into the warp's
+// shared-memory tile instead of global memory; the caller ships the tile with one TMA store.
 __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t (&acc)[32], long long row,
-                                               int n_base, bool row_ok, const ResRegs& pre) {
-  if (!row_ok) return;
+                                               int n_base, bool row_ok, const ResRegs& pre, uint8_t* stage_out,
+                                               int lane) {
   const int n_left = p.n - n_base;
-  if (n_left <= 0) return;
+  if (stage_out == nullptr && (!row_ok || n_left <= 0)) return;
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * p.alpha;
@@ -125,7 +134,7 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t 
           v[j + 2 * q + 1] += __fadd_rn(bf16bits_to_f32(hw[q] >> 16), bf16bits_to_f32(lw[q] >> 16));
         }
       }
-    } else {
+    } else if (row_ok) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (j < n_left) v[j] += merge2(rh[j], rl[j]);
@@ -135,7 +144,7 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t 
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
   }
-  if (p.out_f32) {
+  if (p.out_f32 && row_ok && n_left > 0) {
     float* o = p.out_f32 + row * p.ld_f32 + n_base;
     if (full && (p.ld_f32 % 4 == 0)) {
 #pragma unroll
@@ -157,7 +166,17 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t 
       hp[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
       lp[j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
     }
-    if (p.out_hi) {
+    if (stage_out) {
+      // 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
+      uint8_t* mh = stage_out + lane * 64;
+      uint8_t* ml = mh + EPI_TILE_BYTES;
+      const int sw = (lane >> 1) & 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        *reinterpret_cast<uint4*>(mh + ((j ^ sw) << 4)) = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
+        *reinterpret_cast<uint4*>(ml + ((j ^ sw) << 4)) = make_uint4(lp[4 * j], lp[4 * j + 1], lp[4 * j + 2], lp[4 * j + 3]);
+      }
+    } else if (p.out_hi && row_ok && n_left > 0) {
       __nv_bfloat16* oh = p.out_hi + row * p.ld_out + n_base;
       __nv_bfloat16* ol = p.out_lo + row * p.ld_out + n_base;
       if (full && (p.ld_out % 8 == 0)) {
@@ -175,7 +194,7 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t 
           }
       }
     }
-    if (p.outT_hi) {
+    if (p.outT_hi && row_ok) {
       // transposed: element (n, row); consecutive lanes hold consecutive rows -> coalesced
 #pragma unroll
       for (int j = 0; j < 32; ++j)
@@ -200,11 +219,13 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* tiles = smem_raw + pad;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + STAGES * C_::STAGE_BYTES);
+  uint8_t* epi_smem = tiles + STAGES * C_::STAGE_BYTES;          // 4 warps x [res_hi|res_lo|out_hi|out_lo]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + EPI_SMEM);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* res_bar = tmem_empty_bar + 2;            // [4] one per epilogue warp (residual TMA loads)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -228,6 +249,7 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
       mbar_init(&tmem_full_bar[b], 1);
       mbar_init(&tmem_empty_bar[b], 4);   // one arrival per epilogue warp
     }
+    for (int w = 0; w < 4; ++w) mbar_init(&res_bar[w], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -316,6 +338,7 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
     // ================= epilogue =================
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int m = q * 32 + lane;
+    uint32_t res_phase = 0;
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int nt = tile % n_tiles;
@@ -329,27 +352,68 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
       const long long row = ((long long)bimg * p.out_h + py) * p.out_w + px;
       const int ab = lt & 1;
       const uint32_t aph = (uint32_t)((lt >> 1) & 1);
-      ResRegs ra, rb;
-      prefetch_res(p, row, nt * BN, row_ok, ra);        // issued before the accumulator is even ready
+      // TMA epilogue: this warp's 32 rows are the pixel box (bw x bh) at (ox, oy) of image bimg
+      const int ox = tx * p.tile_w + (q * 32) % p.tile_w;
+      const int oy = ty * p.tile_h + (q * 32) / p.tile_w;
+      const bool t_out = (p.tma_epi & 1) != 0, t_res = (p.tma_epi & 2) != 0;
+      uint8_t* ebuf = epi_smem + (warp - 2) * EPI_WARP_BYTES;
+      uint64_t* rbar = &res_bar[warp - 2];
+      if (t_res && lane == 0) {                          // residual of chunk 0: in flight during the main loop
+        mbar_expect_tx(rbar, 2 * EPI_TILE_BYTES);
+        tma_load_4d(ebuf, &p.tmR_hi, rbar, nt * BN, ox, oy, bimg);
+        tma_load_4d(ebuf + EPI_TILE_BYTES, &p.tmR_lo, rbar, nt * BN, ox, oy, bimg);
+      }
       mbar_wait(&tmem_full_bar[ab], aph);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 64) {             // two chunks per trip: residual registers ping-pong
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int nb = nt * BN + c0;
         uint32_t acc[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0);
-        tmem_ld_32x32b_x32(taddr, acc);
-        prefetch_res(p, row, nt * BN + c0 + 32, row_ok, rb);
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0), acc);
+        ResRegs rr;
+        rr.valid = false;
+        if (t_res) {
+          mbar_wait(rbar, res_phase);
+          res_phase ^= 1u;
+          const uint8_t* mh = ebuf + lane * 64;
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            rr.h[j] = *reinterpret_cast<const uint4*>(mh + ((j ^ sw) << 4));
+            rr.l[j] = *reinterpret_cast<const uint4*>(mh + EPI_TILE_BYTES + ((j ^ sw) << 4));
+          }
+          rr.valid = true;
+          __syncwarp();
+          if (c0 + 32 < BN && lane == 0) {               // next chunk's residual lands while this one is processed
+            fence_proxy_async();
+            mbar_expect_tx(rbar, 2 * EPI_TILE_BYTES);
+            tma_load_4d(ebuf, &p.tmR_hi, rbar, nb + 32, ox, oy, bimg);
+            tma_load_4d(ebuf + EPI_TILE_BYTES, &p.tmR_lo, rbar, nb + 32, ox, oy, bimg);
+          }
+        } else {
+          prefetch_res(p, row, nb, row_ok, rr);
+        }
         tmem_ld_wait();
-        epilogue_chunk(p, acc, row, nt * BN + c0, row_ok, ra);
-        tmem_ld_32x32b_x32(taddr + 32, acc);
-        if (c0 + 64 < BN) prefetch_res(p, row, nt * BN + c0 + 64, row_ok, ra);
-        tmem_ld_wait();
-        epilogue_chunk(p, acc, row, nt * BN + c0 + 32, row_ok, rb);
+        if (t_out) {
+          if (lane == 0) bulk_wait_read0();              // the previous chunk's store has drained the tile
+          __syncwarp();
+        }
+        epilogue_chunk(p, acc, row, nb, row_ok, rr, t_out ? ebuf + 2 * EPI_TILE_BYTES : nullptr, lane);
+        if (t_out) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&p.tmO_hi, ebuf + 2 * EPI_TILE_BYTES, nb, ox, oy, bimg);
+            tma_store_4d(&p.tmO_lo, ebuf + 3 * EPI_TILE_BYTES, nb, ox, oy, bimg);
+            bulk_commit();
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[ab]);
     }
+    if ((p.tma_epi & 1) && lane == 0) bulk_wait0();      // all TMA stores of this warp have landed
   }
   tc_fence_before();
   __syncthreads();
@@ -372,7 +436,7 @@ struct Cfg2 {
   static constexpr int BH_BYTES = (BN / 2) * BK * 2;              // this CTA's half of one B tile
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;  // A hi/lo + B-half hi/lo
   static constexpr int STAGES = (BN == 256) ? 3 : 4;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_SMEM + 1024 + 256;
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
@@ -385,11 +449,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* tiles = smem_raw + pad;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + STAGES * C_::STAGE_BYTES);
+  uint8_t* epi_smem = tiles + STAGES * C_::STAGE_BYTES;          // 4 warps x [res_hi|res_lo|out_hi|out_lo]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + EPI_SMEM);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* res_bar = tmem_empty_bar + 2;            // [4] one per epilogue warp (residual TMA loads)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -416,6 +482,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
       mbar_init(&tmem_full_bar[b], 1);
       mbar_init(&tmem_empty_bar[b], 8);   // 4 epilogue warps x 2 CTAs (used in the leader only)
     }
+    for (int w = 0; w < 4; ++w) mbar_init(&res_bar[w], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -500,6 +567,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
     // ================= epilogue (both CTAs, own 128 rows) =================
     const int q = warp & 3;
     const int m = q * 32 + lane;
+    uint32_t res_phase = 0;
     int lt = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
       const int nt = tile % n_tiles;
@@ -513,27 +581,68 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
       const long long row = ((long long)bimg * p.out_h + py) * p.out_w + px;
       const int ab = lt & 1;
       const uint32_t aph = (uint32_t)((lt >> 1) & 1);
-      ResRegs ra, rb;
-      prefetch_res(p, row, nt * BN, row_ok, ra);        // issued before the accumulator is even ready
+      // TMA epilogue: this warp's 32 rows are the pixel box (bw x bh) at (ox, oy) of image bimg
+      const int ox = tx * p.tile_w + (q * 32) % p.tile_w;
+      const int oy = ty * p.tile_h + (q * 32) / p.tile_w;
+      const bool t_out = (p.tma_epi & 1) != 0, t_res = (p.tma_epi & 2) != 0;
+      uint8_t* ebuf = epi_smem + (warp - 2) * EPI_WARP_BYTES;
+      uint64_t* rbar = &res_bar[warp - 2];
+      if (t_res && lane == 0) {                          // residual of chunk 0: in flight during the main loop
+        mbar_expect_tx(rbar, 2 * EPI_TILE_BYTES);
+        tma_load_4d(ebuf, &p.tmR_hi, rbar, nt * BN, ox, oy, bimg);
+        tma_load_4d(ebuf + EPI_TILE_BYTES, &p.tmR_lo, rbar, nt * BN, ox, oy, bimg);
+      }
       mbar_wait(&tmem_full_bar[ab], aph);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 64) {             // two chunks per trip: residual registers ping-pong
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int nb = nt * BN + c0;
         uint32_t acc[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0);
-        tmem_ld_32x32b_x32(taddr, acc);
-        prefetch_res(p, row, nt * BN + c0 + 32, row_ok, rb);
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0), acc);
+        ResRegs rr;
+        rr.valid = false;
+        if (t_res) {
+          mbar_wait(rbar, res_phase);
+          res_phase ^= 1u;
+          const uint8_t* mh = ebuf + lane * 64;
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            rr.h[j] = *reinterpret_cast<const uint4*>(mh + ((j ^ sw) << 4));
+            rr.l[j] = *reinterpret_cast<const uint4*>(mh + EPI_TILE_BYTES + ((j ^ sw) << 4));
+          }
+          rr.valid = true;
+          __syncwarp();
+          if (c0 + 32 < BN && lane == 0) {               // next chunk's residual lands while this one is processed
+            fence_proxy_async();
+            mbar_expect_tx(rbar, 2 * EPI_TILE_BYTES);
+            tma_load_4d(ebuf, &p.tmR_hi, rbar, nb + 32, ox, oy, bimg);
+            tma_load_4d(ebuf + EPI_TILE_BYTES, &p.tmR_lo, rbar, nb + 32, ox, oy, bimg);
+          }
+        } else {
+          prefetch_res(p, row, nb, row_ok, rr);
+        }
         tmem_ld_wait();
-        epilogue_chunk(p, acc, row, nt * BN + c0, row_ok, ra);
-        tmem_ld_32x32b_x32(taddr + 32, acc);
-        if (c0 + 64 < BN) prefetch_res(p, row, nt * BN + c0 + 64, row_ok, ra);
-        tmem_ld_wait();
-        epilogue_chunk(p, acc, row, nt * BN + c0 + 32, row_ok, rb);
+        if (t_out) {
+          if (lane == 0) bulk_wait_read0();              // the previous chunk's store has drained the tile
+          __syncwarp();
+        }
+        epilogue_chunk(p, acc, row, nb, row_ok, rr, t_out ? ebuf + 2 * EPI_TILE_BYTES : nullptr, lane);
+        if (t_out) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&p.tmO_hi, ebuf + 2 * EPI_TILE_BYTES, nb, ox, oy, bimg);
+            tma_store_4d(&p.tmO_lo, ebuf + 3 * EPI_TILE_BYTES, nb, ox, oy, bimg);
+            bulk_commit();
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[ab]);
     }
+    if ((p.tma_epi & 1) && lane == 0) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -609,15 +718,15 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 using MapKey = std::tuple<const void*, int, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t,
-                          uint32_t, uint32_t, uint32_t>;
+                          uint32_t, uint32_t, uint32_t, int>;
 std::map<MapKey, CUtensorMap> g_map_cache;
 std::mutex g_map_mutex;
 
 int make_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-             const uint32_t* box) {
+             const uint32_t* box, int swizzle_bytes = 128) {
   MapKey key{ptr, rank, dims[0], dims[1], rank > 2 ? dims[2] : 0, rank > 3 ? dims[3] : 0,
              strides_bytes[0], rank > 2 ? strides_bytes[1] : 0, rank > 3 ? strides_bytes[2] : 0,
-             box[0], box[1], rank > 2 ? box[2] : 0};
+             box[0], box[1], rank > 2 ? box[2] : 0, swizzle_bytes};
   {
     std::lock_guard<std::mutex> lk(g_map_mutex);
     auto it = g_map_cache.find(key);
@@ -641,7 +750,9 @@ int make_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, 
   }
   for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstr, bx,
-                   es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     g_hvr_last_cuda_error = 100000 + (int)r;
@@ -668,6 +779,7 @@ int validate(const HvrIGemm* g) {
 }
 
 int g_force_bn = 0;   // test hook (hvr_debug_force_bn): 0 = heuristic
+bool g_tma_epilogue = true;   // test hook: bit 10 of hvr_debug_force_bn's argument selects the per-row epilogue
 
 template <int BN>
 int launch(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
@@ -795,6 +907,34 @@ extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
   kp.outT_hi = reinterpret_cast<__nv_bfloat16*>(g->outT_hi);
   kp.outT_lo = reinterpret_cast<__nv_bfloat16*>(g->outT_lo);
   kp.ld_outT = g->ld_outT;
+  // TMA epilogue maps: the [rows, ld] output / residual seen as (C = n, W, H, B) pixel tensors; one
+  // box = one epilogue warp's 32 rows x 32 columns (64-byte rows, SWIZZLE_64B); out-of-range
+  // columns / pixels are clipped (store) or zero-filled (load) by the TMA unit.
+  kp.tma_epi = 0;
+  if (g_tma_epilogue) {
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    const uint32_t bw = g->tile_w < 32 ? (uint32_t)g->tile_w : 32u;
+    const uint32_t ebox[4] = {32, bw, 32 / bw, 1};
+    const uint64_t edims[4] = {(uint64_t)g->n, (uint64_t)g->out_w, (uint64_t)g->out_h, (uint64_t)g->batch};
+    if (g->out_hi && g->ld_out % 8 == 0 && al16(g->out_hi) && al16(g->out_lo)) {
+      const uint64_t es[3] = {(uint64_t)g->ld_out * 2, (uint64_t)g->out_w * g->ld_out * 2,
+                              (uint64_t)g->out_h * g->out_w * g->ld_out * 2};
+      rc = make_map(&kp.tmO_hi, g->out_hi, 4, edims, es, ebox, 64);
+      if (rc) return rc;
+      rc = make_map(&kp.tmO_lo, g->out_lo, 4, edims, es, ebox, 64);
+      if (rc) return rc;
+      kp.tma_epi |= 1;
+    }
+    if (g->res_hi && g->ld_res % 8 == 0 && al16(g->res_hi) && al16(g->res_lo)) {
+      const uint64_t es[3] = {(uint64_t)g->ld_res * 2, (uint64_t)g->out_w * g->ld_res * 2,
+                              (uint64_t)g->out_h * g->out_w * g->ld_res * 2};
+      rc = make_map(&kp.tmR_hi, g->res_hi, 4, edims, es, ebox, 64);
+      if (rc) return rc;
+      rc = make_map(&kp.tmR_lo, g->res_lo, 4, edims, es, ebox, 64);
+      if (rc) return rc;
+      kp.tma_epi |= 2;
+    }
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // Tile width: 256 when the problem still fills the machine (halves the A traffic per FLOP),
   // 64 for narrow outputs or when 128-wide tiles would leave most SMs idle.
@@ -815,6 +955,8 @@ extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
 }
 
 extern "C" int hvr_debug_force_bn(int bn) {
+  g_tma_epilogue = (bn & 1024) == 0;
+  bn &= ~1024;
   if (bn != 0 && bn != 64 && bn != 128 && bn != 256 && bn != 512) return HVR_ERR_ARG;   // 512 = CTA-pair kernel
   g_force_bn = bn;
   return HVR_OK;

@@ -147,6 +147,59 @@ def test_igemm_cta_pair_conv(cuda):
     assert _rel(ops.nhwc_split_to_nchw(out).double().cpu(), ref) < 3e-5
 
 
+@pytest.mark.parametrize('force', [0, 64, 128, 256, 512])
+def test_igemm_tma_epilogue_matches_per_row_epilogue(cuda, force):
+    """The TMA epilogue (residual tiles loaded / split output tiles stored by TMA through swizzled
+    shared memory) writes the same bits as the per-row register epilogue (flag 1024)."""
+    from hvrnet_b200 import _lib, ops
+    g = torch.Generator().manual_seed(77 + force)
+    M, K, N = 128 * 9 + 50, 256, 600          # ragged M and N (N tail: 600 = 18*32 + 24)
+    a = ops.split(torch.randn(M, K, generator=g).to(cuda))
+    w = ops.split((torch.randn(ops.round_up(N, 64), K, generator=g) / math.sqrt(K)).to(cuda))
+    bias = torch.randn(ops.round_up(N, 64), generator=g).to(cuda)
+    res = ops.split(torch.randn(M, ops.round_up(N, 8), generator=g).to(cuda))
+    outs = []
+    for flag in (force, force | 1024):
+        _lib.lib().hvr_debug_force_bn(flag)
+        try:
+            o, of, oT = ops.linear(a, w, N, bias=bias, relu=True, res=res, want_split=True, want_f32=True, want_T=True)
+            torch.cuda.synchronize()
+        finally:
+            _lib.lib().hvr_debug_force_bn(0)
+        outs.append((o.hi[:, :N].clone(), o.lo[:, :N].clone(), of[:, :N].clone(), oT.hi[:N, :M].clone(),
+                     oT.lo[:N, :M].clone()))
+    for x, y in zip(outs[0], outs[1]):
+        assert torch.equal(x, y)
+    ref = _ref_linear(a, w, N, bias, res, True, 1.0)
+    assert _rel(outs[0][2].double().cpu(), ref) < 3e-5
+
+
+@pytest.mark.parametrize('tile', [(16, 8), (8, 16), (32, 4), (64, 2), (128, 1)])
+def test_igemm_conv_tile_shapes(cuda, tile):
+    """Every pixel-box shape of the M tile (and of the TMA epilogue box) on a 3x3 conv with residual."""
+    import torch.nn.functional as F
+    from hvrnet_b200 import engine, ops
+    from hvrnet_b200.ops import Split
+    g = torch.Generator().manual_seed(tile[0])
+    B, H, W, C, N = 2, 21, 37, 64, 96
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(N, C, 3, 3, generator=g) / math.sqrt(C * 9)
+    r = torch.randn(B, N, H, W, generator=g)
+    xs, rs = ops.nchw_to_nhwc_split(x.to(cuda)), ops.nchw_to_nhwc_split(r.to(cuda))
+    wp = engine.pack_conv(w, None, cuda)
+    out = Split.empty((B, H, W, N), cuda)
+    rows = B * H * W
+    gd = ops.igemm_desc(xs, wp, N, taps=engine._taps(3, 1), out_whb=(W, H, B), tile=tile, relu=True,
+                        res=Split(rs.hi.view(rows, N), rs.lo.view(rows, N)),
+                        out=Split(out.hi.view(rows, N), out.lo.view(rows, N)))
+    ops.igemm_run(gd)
+    torch.cuda.synchronize()
+    xm = ops.nhwc_split_to_nchw(xs).double().cpu()
+    wm = ops.merge(wp).double().cpu()[:N].view(N, 3, 3, C).permute(0, 3, 1, 2)
+    ref = (F.conv2d(xm, wm, padding=1) + ops.nhwc_split_to_nchw(rs).double().cpu()).clamp_min(0)
+    assert _rel(ops.nhwc_split_to_nchw(out).double().cpu(), ref) < 3e-5
+
+
 def Split_rows(s):
     from hvrnet_b200.ops import Split
     return Split(s.hi.contiguous(), s.lo.contiguous())

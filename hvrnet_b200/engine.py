@@ -291,11 +291,19 @@ def relation(P, idx, X, XT, q_range=None, res=None, relu=True, extra=None, **kw)
     return out
 
 
-def hrnmp_stage123(P, roi_feats, start, length, **kw):
+def head_fc1(P, roi_feats, **kw):
+    """fc_new_1 on RoI rows (hrnmp_bbox_head.py:827-828): per-row, so a frame's rows can be computed
+    once and reused by every window the frame appears in.  Returns (f1 Split [n,D], f1^T Split [D,ld])."""
+    f1, _, f1T = lin(roi_feats, P['fc1'], want_T=True, **kw)
+    return f1, f1T
+
+
+def hrnmp_stage123(P, roi_feats, start, length, f1=None, f1T=None, **kw):
     """Stages 1-3 + fc_new_4 of forward_test (hrnmp_bbox_head.py:827-889).  Returns
     (out1 fp32 [len, 64] = branch [cls | reg], f4 Split [N, D], f4^T Split [D, ld])."""
     s, e = start, start + length
-    f1, _, f1T = lin(roi_feats, P['fc1'], want_T=True, **kw)
+    if f1 is None:
+        f1, f1T = head_fc1(P, roi_feats, **kw)
     a1 = relation(P, 1, f1, f1T, res=f1, **kw)
     f2, _, f2T = lin(a1, P['fc2'], want_T=True, **kw)
     # only the key rows of stage 2 are ever used (hrnmp_bbox_head.py:865-868): key-only queries
@@ -317,17 +325,19 @@ def hrnmp_stage4(P, f4, f4T, start, length, support=None, **kw):
     return out2
 
 
-def hrnmp_forward_test(P, roi_feats, start, length, support=None, **kw):
+def hrnmp_forward_test(P, roi_feats, start, length, support=None, f1=None, f1T=None, **kw):
     """roi_feats Split [N, 12544] (NHWC-flattened).  Returns fp32 (out1 [len, 64], out2 [len, 64]):
-    columns [0,n_cls) class logits, [n_cls, n_cls+4) box deltas; plus f4[key] Split."""
-    out1, f4, f4T = hrnmp_stage123(P, roi_feats, start, length, **kw)
+    columns [0,n_cls) class logits, [n_cls, n_cls+4) box deltas; plus f4[key] Split.
+    f1/f1T: precomputed fc_new_1 rows of the window (streaming caches), else computed here."""
+    out1, f4, f4T = hrnmp_stage123(P, roi_feats, start, length, f1=f1, f1T=f1T, **kw)
     out2 = hrnmp_stage4(P, f4, f4T, start, length, support, **kw)
     return out1, out2, f4[start:start + length]
 
 
-def selsa_forward(P, roi_feats, start, length, **kw):
+def selsa_forward(P, roi_feats, start, length, f1=None, f1T=None, **kw):
     s, e = start, start + length
-    f1, _, f1T = lin(roi_feats, P['fc1'], want_T=True, **kw)
+    if f1 is None:
+        f1, f1T = head_fc1(P, roi_feats, **kw)
     a1 = relation(P, 1, f1, f1T, res=f1, **kw)
     f2, _, f2T = lin(a1, P['fc2'], want_T=True, **kw)
     a2k = relation(P, 2, f2, f2T, q_range=(s, length), res=f2[s:e], **kw)   # relu after the key slice

@@ -164,3 +164,139 @@ class GraphRunner:
                 o += 1 + 6 * M
             res.append(outs if ok else None)
         return res
+
+
+class StreamGraphRunner:
+    """CUDA-graph executor of the streaming scheduler (streaming.py) for V
+    video streams advanced in lock-step.  Per step: ONE frame graph (trunk, C5, RPN, proposals,
+    RoIAlign, fc_new_1 for the V new frames) and ONE head graph (relation stages, decode, NMS for
+    the V key frames on the cached rows), one device->host read.  Captured for the common case
+    of max_num proposals per frame; a short frame raises (use streaming.StreamingDetector then)."""
+
+    def __init__(self, model, n_videos, window=None):
+        from collections import deque
+        self.m = model
+        self.V = n_videos
+        self.T = int(window or model.bbox_head.t_dim)
+        self.P = model.test_cfg.rpn['max_num']
+        self.cache = [deque(maxlen=self.T) for _ in range(n_videos)]      # per video: (props, f1, f1T)
+        self._frame = None
+        self._head = None
+        self.replayed_launches = 0
+        self._cap = GraphRunner._capture
+
+    def _frame_graph(self, img, meta):
+        m, V, P = self.m, self.V, self.P
+        buf = torch.zeros(img.shape, dtype=torch.float32, device='cuda:%d' % torch.cuda.current_device())
+        dev = buf.device
+
+        def fn():
+            c4 = m.backbone.forward_split(buf)
+            maps = m.rpn_head.forward_maps(c4)
+            props, counts = m.rpn_head.proposals_from_maps(maps, meta['img_shape'], m.test_cfg.rpn)
+            c5 = m.shared_head.forward_nhwc(c4)
+            fidx = torch.arange(V, device=dev, dtype=torch.float32).view(V, 1, 1).expand(V, P, 1)
+            rois = torch.cat([fidx, props[..., :4]], -1).view(-1, 5).contiguous()
+            rows = m.bbox_roi_extractor.roi_layers[0].forward_nhwc_split(c5, rois)
+            f1, f1T = engine_head_fc1(m, rows)
+            return props, counts, f1, f1T, (c4, maps, c5, rois, rows)
+        c = self._cap(self, fn)
+        c.inputs = buf
+        return c
+
+    def _head_graph(self, meta, rescale):
+        m, V, T, P = self.m, self.V, self.T, self.P
+        dev = self._frame.inputs.device
+        D = self._frame.outputs[2].shape[1]
+        N = T * P
+        f1w = [ops.Split.zeros((N, D), dev) for _ in range(V)]
+        f1Tw = [ops.Split.zeros((D, ops.round_up(N, 64)), dev) for _ in range(V)]
+        rk = [torch.zeros((P, 5), device=dev) for _ in range(V)]
+        counts = self._frame.outputs[1]
+        sf = meta['scale_factor']
+        sf = float(sf if not hasattr(sf, '__len__') else sf[0])
+        head = m.bbox_head
+        side = [torch.cuda.Stream(), torch.cuda.Stream()]
+
+        def fn():
+            main = torch.cuda.current_stream()
+            packed = head.packed(dev)
+            flat, keep = [counts.float()], []
+            s = m.key_dim * P
+            from . import engine
+            for v in range(V):
+                if head.kind == 'hrnmp':
+                    o1, o2, _ = engine.hrnmp_forward_test(packed, None, s, P, f1=f1w[v], f1T=f1Tw[v])
+                    outs = [o1, o2]
+                else:
+                    outs = [engine.selsa_forward(packed, None, s, P, f1=f1w[v], f1T=f1Tw[v])]
+                dets = []
+                for j, o in enumerate(outs):
+                    cls, reg = head._split_out(o)
+                    st = side[j % 2]
+                    st.wait_stream(main)
+                    with torch.cuda.stream(st):
+                        dets.append(head.get_det_bboxes(rk[v], cls, reg, meta['img_shape'], sf, rescale=rescale,
+                                                        cfg=m.test_cfg.rcnn))
+                for st in side:
+                    main.wait_stream(st)
+                keep += [outs, dets]
+                for d, l, k in dets:
+                    flat += [k.float(), d.reshape(-1), l.float()]
+            return torch.cat(flat), keep
+        c = self._cap(self, fn)
+        c.inputs = (f1w, f1Tw, rk)
+        return c
+
+    def push(self, img, meta, rescale=True):
+        """img [V,3,H,W] (device or pinned host): the next frame of each of the V streams.
+        Returns None while the windows fill, then a list of V forward_feat-style results."""
+        V, T, P = self.V, self.T, self.P
+        if self._frame is None:
+            self._frame = self._frame_graph(img, meta)
+        fr = self._frame
+        fr.inputs.copy_(img, non_blocking=True)
+        fr.graph.replay()
+        self.replayed_launches += fr.launches
+        props, counts, f1, f1T = fr.outputs[:4]
+        for v in range(V):
+            self.cache[v].append((props[v].clone(), f1.hi[v * P:(v + 1) * P].clone(), f1.lo[v * P:(v + 1) * P].clone(),
+                                  f1T.hi[:, v * P:(v + 1) * P].clone(), f1T.lo[:, v * P:(v + 1) * P].clone()))
+        if len(self.cache[0]) < T:
+            return None
+        if self._head is None:
+            self._head = self._head_graph(meta, rescale)
+        hd = self._head
+        f1w, f1Tw, rk = hd.inputs
+        N = T * P
+        for v in range(V):
+            fl = list(self.cache[v])
+            torch.cat([f[1] for f in fl], 0, out=f1w[v].hi)
+            torch.cat([f[2] for f in fl], 0, out=f1w[v].lo)
+            torch.cat([f[3] for f in fl], 1, out=f1Tw[v].hi[:, :N])
+            torch.cat([f[4] for f in fl], 1, out=f1Tw[v].lo[:, :N])
+            rk[v][:, 1:] = fl[self.m.key_dim][0][:, :4]
+        hd.graph.replay()
+        self.replayed_launches += hd.launches
+        host = hd.outputs[0].cpu()
+        if not bool((host[:V] == P).all()):
+            raise RuntimeError('a frame produced fewer than %d proposals: use streaming.StreamingDetector' % P)
+        M = self.m.test_cfg.rcnn['max_per_img']
+        n_out = (host.numel() - V) // (V * (1 + 6 * M))
+        from .models import bbox2result
+        res, o = [], V
+        for v in range(V):
+            outs = []
+            for _ in range(n_out):
+                k = int(host[o])
+                d = host[o + 1:o + 1 + 5 * M].view(M, 5)[:k]
+                l = host[o + 1 + 5 * M:o + 1 + 6 * M][:k].long()
+                outs.append(bbox2result(d, l, self.m.bbox_head.num_classes))
+                o += 1 + 6 * M
+            res.append(outs)
+        return res
+
+
+def engine_head_fc1(model, rows):
+    from . import engine
+    return engine.head_fc1(model.bbox_head.packed(rows.hi.device), rows)

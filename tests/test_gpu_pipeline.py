@@ -204,3 +204,45 @@ def test_intervideo_stage4_world1(world):
                                            proposals=[[p.to(dev) for p in auxs[0]['proposals']]])
     for a, b in zip(aux1[0]['cls'] + aux1[0]['reg'], auxs[0]['cls'] + auxs[0]['reg']):
         assert _rel(a.cpu(), b) < 1e-3
+
+
+def test_streaming_bit_identical(world):
+    """the streaming scheduler (per-frame caches of proposals and fc_new_1 rows)
+    returns the same detections, bit for bit, as the as-executed window path."""
+    import numpy as np
+    from hvrnet_b200.streaming import StreamingDetector
+    m, dev = world['model'], world['dev']
+    frames = world['frames'].to(dev)
+    m.enable_cuda_graphs(False)
+    order = [0, 1, 2, 0, 2]                                     # 3 successive windows of T=3
+    c4 = [m(img=frames[i:i + 1], img_meta=[world['metas'][0]], backbone_feat=True)[0] for i in order]
+    sd = StreamingDetector(m, window=3)
+    got = [sd.push(frames[i:i + 1], world['metas'][0]) for i in order]
+    assert got[0] is None and got[1] is None
+    for w in range(3):
+        ref = m(x=c4[w:w + 3], img=None, img_meta=world['metas'], forward_feat=True, return_loss=False, rescale=True)
+        for o in range(2):
+            for c in range(30):
+                assert np.array_equal(got[w + 2][o][c], ref[o][c])
+
+
+def test_stream_graph_runner_bit_identical(world):
+    """The CUDA-graph version of the streaming scheduler, two streams in lock-step."""
+    import numpy as np
+    from hvrnet_b200.runtime import StreamGraphRunner
+    m, dev = world['model'], world['dev']
+    frames = world['frames'].to(dev)
+    m.enable_cuda_graphs(False)
+    orders = ([0, 1, 2, 0], [2, 0, 1, 1])
+    c4 = [[m(img=frames[i:i + 1], img_meta=[world['metas'][0]], backbone_feat=True)[0] for i in o] for o in orders]
+    run = StreamGraphRunner(m, 2, window=3)
+    got = [run.push(torch.cat([frames[orders[0][t]][None], frames[orders[1][t]][None]]), world['metas'][0])
+           for t in range(4)]
+    assert got[0] is None and got[1] is None
+    for w in range(2):
+        for v in range(2):
+            ref = m(x=c4[v][w:w + 3], img=None, img_meta=world['metas'], forward_feat=True, return_loss=False,
+                    rescale=True)
+            for o in range(2):
+                for c in range(30):
+                    assert np.array_equal(got[w + 2][v][o][c], ref[o][c])

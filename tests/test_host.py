@@ -166,3 +166,29 @@ def test_igemm_struct_layout_matches_header():
         for part in decl.split(','):
             names.append(re.sub(r'\[.*\]', '', part.strip().split()[-1].lstrip('*')))
     assert names == [f[0] for f in _lib.HvrIGemm._fields_]
+
+
+def test_checkpoint_loader_mmdet_format(tmp_path):
+    """tools/hnl_test.py:746-752: mmdet-format checkpoint with the DataParallel prefix and meta."""
+    from hvrnet_b200 import checkpoint, configs, synth
+    from hvrnet_b200.builder import build_detector
+    cfg = configs.model_cfg('SelsaRCNN', 3, 1)
+    m = build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg)
+    sd = synth.make_state_dict('selsa', seed=3)
+    f = tmp_path / 'epoch_1.pth'
+    torch.save(dict(meta=dict(CLASSES=('a', 'b'), config='x'), state_dict={'module.' + k: v for k, v in sd.items()},
+                    optimizer={}), str(f))
+    ck = checkpoint.load_checkpoint(m, str(f), map_location='cpu')
+    assert ck['meta']['CLASSES'] == ('a', 'b')
+    got = m.state_dict()
+    for k, v in sd.items():
+        assert torch.equal(got[k], v), k
+    # tolerant like mmcv: extra / missing / mis-shaped keys are reported, strict raises
+    bad = dict(sd)
+    bad['bbox_head.fc_cls.weight'] = torch.zeros(3, 3)
+    bad['extra.weight'] = torch.zeros(1)
+    del bad['rpn_head.rpn_cls.bias']
+    missing, unexpected, mismatch = checkpoint.load_state_dict(m, bad)
+    assert 'rpn_head.rpn_cls.bias' in missing and unexpected == ['extra.weight'] and mismatch[0][0] == 'bbox_head.fc_cls.weight'
+    with pytest.raises(RuntimeError):
+        checkpoint.load_state_dict(m, bad, strict=True)

@@ -60,6 +60,8 @@ SIGNATURES = {
     'hvr_det_workspace_bytes': (c_sz, [c_int, c_int]),
     'hvr_det_postprocess': (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, ctypes.POINTER(c_f32), c_f32,
                                     c_f32, c_f32, c_int, c_f32, c_f32, c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'hvr_preprocess_u8': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_f32),
+                                  ctypes.POINTER(c_f32), c_vp, c_vp]),
     'hvr_softmax_rows_split': (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_i64, c_vp]),
 }
 

@@ -23,6 +23,7 @@ SOURCES = {
     'roi_align.cu': ['-fmad=false'],
     'nms.cu': ['-fmad=false'],
     'igemm_tc.cu': [],
+    'preprocess.cu': ['-fmad=false'],
 }
 
 

@@ -209,6 +209,17 @@ int hvr_det_postprocess(const float* rois, const float* cls, int64_t ld_cls, con
 int hvr_softmax_rows_split(const float* S, int rows, int cols, int64_t ld_s, hvr_bf16* p_hi,
                            hvr_bf16* p_lo, int64_t ld_p, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Test-time image pipeline (next row N2).  Replaces the CPU DataLoader path Resize(keep_ratio)
+ * -> Normalize -> Pad(16) -> ImageToTensor (mmdet/datasets/pipelines/transforms.py:111-125,
+ * 240-322; formating.py:48-56), i.e. mmcv.imrescale = cv2.resize(INTER_LINEAR) on uint8
+ * (OpenCV's fixed-point arithmetic, reproduced bit for bit), (x - mean) / std, zero padding.
+ *   img : uint8 HWC BGR [h, w, 3] (device);  out : fp32 CHW [3, pad_h, pad_w]
+ *   new_h/new_w : resized size (mmcv rescale_size rule, computed by the caller)
+ * ---------------------------------------------------------------------------------- */
+int hvr_preprocess_u8(const uint8_t* img, int h, int w, int new_h, int new_w, int pad_h, int pad_w,
+                      const float* mean3_host, const float* std3_host, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

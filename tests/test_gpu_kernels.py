@@ -433,3 +433,18 @@ def test_softmax_rows(cuda):
         got = ops.merge(P)[:, :cols].double().cpu()
         assert float((got - ref).abs().max() / ref.max()) < 1e-5
         assert float(ops.merge(P)[:, cols:].abs().sum()) == 0
+
+
+@pytest.mark.parametrize('h,w', [(720, 1280), (480, 640), (240, 320), (600, 1000), (333, 777)])
+def test_preprocess_bit_exact(cuda, h, w):
+    """Next row N2: fused resize + normalise + pad + CHW vs the numpy oracle (itself pinned to cv2)."""
+    import numpy as np
+    from hvrnet_b200 import preprocess as pp
+    from oracle import preprocess as P
+    rng = np.random.default_rng(h * 7 + w)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    ref, rmeta = P.preprocess(img)
+    out, meta = pp.preprocess(torch.from_numpy(img).to(cuda))
+    assert meta == rmeta
+    assert out.shape == (1,) + ref.shape
+    assert np.array_equal(out[0].cpu().numpy(), ref)

@@ -130,14 +130,15 @@ class GraphRunner:
                     rois_key = rois[o + s:o + s + P].clone()
                     rois_key[:, 0] = 0
                     # the head outputs are post-processed on parallel branches (tiny, latency-bound kernels)
-                    outs = []
+                    outs, used = [], []
                     for j, (c_, r_) in enumerate(zip(cls, reg)):
                         st = side[j % 2]
                         st.wait_stream(main)
+                        used.append(st)
                         with torch.cuda.stream(st):
                             outs.append(m.bbox_head.get_det_bboxes(rois_key, c_, r_, meta['img_shape'], sf,
                                                                    rescale=rescale, cfg=m.test_cfg.rcnn))
-                    for st in side:
+                    for st in used:                     # join only the branches that were forked
                         main.wait_stream(st)
                     keep += [cls, reg, rois_key, outs]
                     for d, l, k in outs:
@@ -230,15 +231,16 @@ class StreamGraphRunner:
                     outs = [o1, o2]
                 else:
                     outs = [engine.selsa_forward(packed, None, s, P, f1=f1w[v], f1T=f1Tw[v])]
-                dets = []
+                dets, used = [], []
                 for j, o in enumerate(outs):
                     cls, reg = head._split_out(o)
                     st = side[j % 2]
                     st.wait_stream(main)
+                    used.append(st)
                     with torch.cuda.stream(st):
                         dets.append(head.get_det_bboxes(rk[v], cls, reg, meta['img_shape'], sf, rescale=rescale,
                                                         cfg=m.test_cfg.rcnn))
-                for st in side:
+                for st in used:
                     main.wait_stream(st)
                 keep += [outs, dets]
                 for d, l, k in dets:

@@ -246,3 +246,23 @@ def test_stream_graph_runner_bit_identical(world):
             for o in range(2):
                 for c in range(30):
                     assert np.array_equal(got[w + 2][v][o][c], ref[o][c])
+
+
+def test_selsa_graph_runner(cuda):
+    """BASELINE.json configs[1] (SELSA, T=3) through the CUDA-graph runner == eager, bit for bit."""
+    import numpy as np
+    from hvrnet_b200 import configs, synth
+    m, sd, w = configs.build_workload('selsa', cuda)
+    frames = synth.make_frames(3, seed=2).to(cuda)
+    metas = [synth.make_img_meta() for _ in range(3)]
+    c4 = [m(img=frames[i:i + 1], img_meta=[metas[i]], backbone_feat=True)[0] for i in range(3)]
+    ref = m(x=c4, img=None, img_meta=metas, forward_feat=True, return_loss=False, rescale=True)
+    assert len(ref) == 1 and len(ref[0]) == 30
+    m.enable_cuda_graphs(True)
+    try:
+        c4g = [m(img=frames[i:i + 1], img_meta=[metas[i]], backbone_feat=True)[0] for i in range(3)]
+        got = m(x=c4g, img=None, img_meta=metas, forward_feat=True, return_loss=False, rescale=True)
+    finally:
+        m.enable_cuda_graphs(False)
+    for c in range(30):
+        assert np.array_equal(got[0][c], ref[0][c])

@@ -102,8 +102,13 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t 
   const int n_left = p.n - n_base;
   if (stage_out == nullptr && (!row_ok || n_left <= 0)) return;
   float v[32];
+  if (p.alpha == 1.0f) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * p.alpha;
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * p.alpha;
+  }
   const bool full = n_left >= 32;
   if (p.bias) {
     if (full) {
@@ -160,11 +165,14 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t 
     uint32_t hp[16], lp[16];  // packed pairs
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split2(v[j], h0, l0);
-      split2(v[j + 1], h1, l1);
-      hp[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-      lp[j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      // packed split: one cvt.rn.bf16x2 for the two hi parts, one for the two lo parts (same
+      // round-to-nearest-even as the scalar split2)
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j], v[j + 1]);
+      const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+      const __nv_bfloat162 l2 = __floats2bfloat162_rn(__fsub_rn(v[j], __uint_as_float(hb << 16)),
+                                                      __fsub_rn(v[j + 1], __uint_as_float(hb & 0xFFFF0000u)));
+      hp[j / 2] = hb;
+      lp[j / 2] = *reinterpret_cast<const uint32_t*>(&l2);
     }
     if (stage_out) {
       // 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
@@ -942,7 +950,7 @@ extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
   int bn = g_force_bn;
   // CTA pairs (256-row tiles, B split across the pair) once there is a full machine of pair tiles
   const long long pair_tiles = ((m_tiles + 1) / 2) * hvr_cdiv(g->n, 256);
-  if (g->passes >= 3 && g->n >= 128 && ((bn == 0 && pair_tiles >= 74) || bn == 512)) return launch2<256>(g, kp, st);
+  if (g->passes >= 3 && g->n >= 128 && ((bn == 0 && pair_tiles >= 64) || bn == 512)) return launch2<256>(g, kp, st);
   if (bn == 0) {
     if (g->n <= 64) bn = 64;
     else if (g->n % 256 == 0 && m_tiles * (g->n / 256) >= 2 * 148) bn = 256;

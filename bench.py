@@ -54,6 +54,14 @@ def workload_name(w, T):
             'faster_rcnn': 'Faster-RCNN R101-C5, single 600x1000 frame'}[w]
 
 
+def config_dict(workload, T, V, world, launch):
+    return {'workload': workload_name(workload, T), 'frames_per_window': T, 'proposals_per_frame': 300,
+            'videos_per_gpu': V, 'key_frames_per_step': V, 'input': '%dx3x608x1008 fp32 per step' % V,
+            'l2': 'working set (305 MB split weights + >1 GB activations per step) exceeds the 126 MB L2; '
+                  'no explicit flush',
+            'parallelism': 'replicas over videos, dp%d' % world, 'launch': launch}
+
+
 # ----------------------------------------------------------------------------------------
 # CPU reference leg (oracle): rank 0 only
 # ----------------------------------------------------------------------------------------
@@ -103,9 +111,12 @@ def run_reference(args):
         'impl': 'reference', 'metric': 'VID key frames/sec (1000x600, 300 proposals)', 'value': fps,
         'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps, 'steps_executed': done, 'warmup': args.warmup,
         'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic', 'config': {'workload': workload_name(args.workload, T), 'frames_per_window': T,
-                                        'note': 'reference package is not importable (SURVEY.md 8c): oracle port of '
-                                                'its PyTorch-CPU path, all host threads'},
+        'data': 'synthetic',
+        'config': dict(config_dict(args.workload, T, args.videos_per_gpu or (5 if args.workload == 'hrnmp_inter' else 7),
+                                   args.gpus, 'torch CPU, %d threads' % os.cpu_count()),
+                       note='reference package is not importable (SURVEY.md 8c): oracle port of its PyTorch-CPU '
+                            'path, all host threads; each step = ONE key frame (a bounded sample of the '
+                            'key_frames_per_step batch), value = key frames / s'),
         'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': 'port',
                          'sample': '%d key frame(s), trunk on 1 new frame + forward_feat over %d frames' % (done, T)},
         'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -370,18 +381,15 @@ def main():
         'steps': K, 'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'bf16x3 (split-bf16 operands, 3 tcgen05 products, fp32 accumulate)',
         'data': 'synthetic',
-        'config': {'workload': workload_name(args.workload, T), 'frames_per_window': T, 'proposals_per_frame': 300,
-                   'videos_per_gpu': V, 'key_frames_per_step': V,
-                   'input': '%dx3x608x1008 fp32 per step' % V, 'l2': 'working set (305 MB split weights + >1 GB '
-                   'activations per step) exceeds the 126 MB L2; no explicit flush',
-                   'parallelism': 'replicas over videos, dp%d' % world,
-                   'launch': 'eager' if (args.eager or args.workload == 'faster_rcnn') else 'cuda graphs (trunk + window)'},
+        'config': config_dict(args.workload, T, V, world, 'eager' if (args.eager or args.workload == 'faster_rcnn')
+                              else 'cuda graphs (trunk + window)'),
         'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': frame_bytes, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': ms_e2e / K},
         'gpu_launches': int(launches),
         'clocks': clk,
         'roofline': {'bound': 'tensor', 'kernel': 'igemm_tc_kernel (tcgen05 split-bf16 implicit GEMM)',
                      'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+                     'tensor_work_tflops': 3.0 * achieved, 'tensor_work_frac': 3.0 * achieved / peak,
                      'peak_source': peak_src, 'traffic': None,
                      'algorithmic_gflop_per_step': gemm_flops / K / 1e9, 'launches_per_step': len(prof) / K,
                      'kernel_ms_per_step': gemm_ms / K, 'share_of_step': gemm_ms / ms_prof,

@@ -123,6 +123,7 @@ class GraphRunner:
                 rows = m.bbox_roi_extractor.roi_layers[0].forward_nhwc_split(c5, rois)
                 flat = [counts.float()]
                 keep = [maps, props, counts, c5, rois, rows]
+                forked, per_video = set(), []
                 s = m.key_dim * P
                 for v in range(V):
                     o = v * T * P
@@ -138,9 +139,12 @@ class GraphRunner:
                         with torch.cuda.stream(st):
                             outs.append(m.bbox_head.get_det_bboxes(rois_key, c_, r_, meta['img_shape'], sf,
                                                                    rescale=rescale, cfg=m.test_cfg.rcnn))
-                    for st in used:                     # join only the branches that were forked
-                        main.wait_stream(st)
-                    keep += [cls, reg, rois_key, outs]
+                    forked.update(used)                 # joined once, after the last video: the next
+                    keep += [cls, reg, rois_key, outs]  # video's head overlaps this video's post-processing
+                    per_video.append(outs)
+                for st in forked:                       # join only the branches that were forked
+                    main.wait_stream(st)
+                for outs in per_video:
                     for d, l, k in outs:
                         flat += [k.float(), d.reshape(-1), l.float()]
                 return torch.cat(flat), keep
@@ -223,6 +227,7 @@ class StreamGraphRunner:
             main = torch.cuda.current_stream()
             packed = head.packed(dev)
             flat, keep = [counts.float()], []
+            forked, per_video = set(), []
             s = m.key_dim * P
             from . import engine
             for v in range(V):
@@ -240,9 +245,12 @@ class StreamGraphRunner:
                     with torch.cuda.stream(st):
                         dets.append(head.get_det_bboxes(rk[v], cls, reg, meta['img_shape'], sf, rescale=rescale,
                                                         cfg=m.test_cfg.rcnn))
-                for st in used:
-                    main.wait_stream(st)
+                forked.update(used)
                 keep += [outs, dets]
+                per_video.append(dets)
+            for st in forked:
+                main.wait_stream(st)
+            for dets in per_video:
                 for d, l, k in dets:
                     flat += [k.float(), d.reshape(-1), l.float()]
             return torch.cat(flat), keep

@@ -291,6 +291,69 @@ def relation(P, idx, X, XT, q_range=None, res=None, relu=True, extra=None, **kw)
     return out
 
 
+# ----------------------------------------------------------------------------------------
+# Batched-over-videos head: V windows of N rows each, laid out [V*Npad, D] (Npad = N rounded up to
+# 64; pad rows are finite garbage that never reaches a result).  Every row-wise GEMM (fc_new_k,
+# Q/K/out projections, cls|reg) runs ONCE over all videos (M = V*Npad fills the machine with
+# 256-row tile pairs); only QK^T, softmax and P.V stay per video.  Per-row arithmetic and the
+# per-video attention operands are those of the single-window functions above, so the results are
+# bit-identical to them.
+# ----------------------------------------------------------------------------------------
+def _key_rows(X, V, Npad, s, n):
+    D = X.shape[1]
+    return Split(X.hi.view(V, Npad, D)[:, s:s + n].reshape(V * n, D), X.lo.view(V, Npad, D)[:, s:s + n].reshape(V * n, D))
+
+
+def relation_batched(P, idx, X, XT, V, N, Npad, q_range=None, res=None, relu=True, **kw):
+    D = X.shape[1]
+    if q_range is None:
+        Xq, nq = X, Npad
+    else:
+        Xq, nq = _key_rows(X, V, Npad, q_range[0], q_range[1]), q_range[1]
+    Q, _, _ = lin(Xq, P['q%d' % idx], **kw)
+    K, _, _ = lin(X, P['k%d' % idx], **kw)
+    O = Split.empty((V * nq, D), X.hi.device)
+    for v in range(V):
+        Qv = Q[v * nq:(v + 1) * nq]
+        Kv = K[v * Npad:v * Npad + N]
+        _, S, _ = ops.linear(Qv, Kv, N, alpha=1.0 / math.sqrt(float(D)), want_split=False, want_f32=True, **kw)
+        Pm = ops.softmax_rows_split(S, N, ld_p=Npad)
+        XTv = Split(XT.hi[:, v * Npad:(v + 1) * Npad], XT.lo[:, v * Npad:(v + 1) * Npad])
+        ops.linear(Pm, XTv, D, out=O[v * nq:(v + 1) * nq], **kw)
+    out, _, _ = lin(O, P['o%d' % idx], relu=relu, res=res, **kw)
+    return out
+
+
+def hrnmp_forward_batched(P, rows, V, N, Npad, start, length, **kw):
+    """rows Split [V*Npad, 12544].  Returns fp32 (out1, out2) of shape [V*length, 64]."""
+    s, n = start, length
+    f1, _, f1T = lin(rows, P['fc1'], want_T=True, **kw)
+    a1 = relation_batched(P, 1, f1, f1T, V, N, Npad, res=f1, **kw)
+    f2, _, f2T = lin(a1, P['fc2'], want_T=True, **kw)
+    a2k = relation_batched(P, 2, f2, f2T, V, N, Npad, q_range=(s, n), res=_key_rows(f2, V, Npad, s, n), **kw)
+    _, out1, _ = lin(a2k, P['out1'], want_split=False, want_f32=True, **kw)
+    D = f1.shape[1]
+    x3 = Split(f1.hi.clone(), f1.lo.clone())
+    x3.hi.view(V, Npad, D)[:, s:s + n] = a2k.hi.view(V, n, D)
+    x3.lo.view(V, Npad, D)[:, s:s + n] = a2k.lo.view(V, n, D)
+    f3, _, f3T = lin(x3, P['fc3'], want_T=True, **kw)
+    a3 = relation_batched(P, 3, f3, f3T, V, N, Npad, res=f3, **kw)
+    f4, _, f4T = lin(a3, P['fc4'], want_T=True, **kw)
+    a4 = relation_batched(P, 4, f4, f4T, V, N, Npad, q_range=(s, n), res=_key_rows(f4, V, Npad, s, n), **kw)
+    _, out2, _ = lin(a4, P['out2'], want_split=False, want_f32=True, **kw)
+    return out1, out2
+
+
+def selsa_forward_batched(P, rows, V, N, Npad, start, length, **kw):
+    s, n = start, length
+    f1, _, f1T = lin(rows, P['fc1'], want_T=True, **kw)
+    a1 = relation_batched(P, 1, f1, f1T, V, N, Npad, res=f1, **kw)
+    f2, _, f2T = lin(a1, P['fc2'], want_T=True, **kw)
+    a2k = relation_batched(P, 2, f2, f2T, V, N, Npad, q_range=(s, n), res=_key_rows(f2, V, Npad, s, n), **kw)
+    _, out1, _ = lin(a2k, P['out1'], want_split=False, want_f32=True, **kw)
+    return out1
+
+
 def head_fc1(P, roi_feats, **kw):
     """fc_new_1 on RoI rows (hrnmp_bbox_head.py:827-828): per-row, so a frame's rows can be computed
     once and reused by every window the frame appears in.  Returns (f1 Split [n,D], f1^T Split [D,ld])."""

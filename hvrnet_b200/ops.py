@@ -204,13 +204,15 @@ def igemm_run(g, check_kernel=False):
 
 
 def linear(a, w, n, bias=None, relu=False, res=None, alpha=1.0, want_split=True, want_f32=False, want_T=False,
-           passes=3, check_kernel=False):
+           passes=3, check_kernel=False, out=None):
     """y = alpha * a @ w[:n].T + bias (+res) (relu).  a Split [M,K]; w Split [>=n, K].
-    Returns (Split or None, fp32 or None, Split^T or None)."""
+    Returns (Split or None, fp32 or None, Split^T or None).  `out`: caller-provided Split [M, >=n]
+    (e.g. a row slice of a batch buffer) instead of a fresh allocation."""
     M = a.shape[0]
     dev = a.hi.device
     ld = round_up(n, 8)
-    out = Split.empty((M, ld), dev) if want_split else None
+    if out is None:
+        out = Split.empty((M, ld), dev) if want_split else None
     of = torch.empty((M, round_up(n, 4)), dtype=torch.float32, device=dev) if want_f32 else None
     oT = Split.zeros((n, round_up(M, 64)), dev) if want_T else None
     g = igemm_desc(a, w, n, alpha=alpha, bias=bias, res=res, relu=relu, out=out, out_f32=of, outT=oT, passes=passes)

@@ -120,14 +120,35 @@ class GraphRunner:
                 main.wait_stream(side[0])
                 fidx = torch.arange(V * T, device=dev, dtype=torch.float32).view(V * T, 1, 1).expand(V * T, P, 1)
                 rois = torch.cat([fidx, props[..., :4]], -1).view(-1, 5).contiguous()
-                rows = m.bbox_roi_extractor.roi_layers[0].forward_nhwc_split(c5, rois)
                 flat = [counts.float()]
-                keep = [maps, props, counts, c5, rois, rows]
                 forked, per_video = set(), []
                 s = m.key_dim * P
+                N = T * P
+                head = m.bbox_head
+                if V > 1:
+                    # batched head: rows of video v live at [v*Npad, v*Npad + N) (Npad = N rounded up to 64);
+                    # the pad rows pool a dummy 1-pixel RoI and never reach a result
+                    from . import engine
+                    Npad = ops.round_up(N, 64)
+                    rois_p = torch.zeros((V, Npad, 5), device=dev)
+                    rois_p[:, :N] = rois.view(V, N, 5)
+                    rows = m.bbox_roi_extractor.roi_layers[0].forward_nhwc_split(c5, rois_p.view(-1, 5))
+                    packed = head.packed(dev)
+                    if head.kind == 'hrnmp':
+                        heads = list(engine.hrnmp_forward_batched(packed, rows, V, N, Npad, s, P))
+                    else:
+                        heads = [engine.selsa_forward_batched(packed, rows, V, N, Npad, s, P)]
+                    keep = [maps, props, counts, c5, rois, rois_p, rows, heads]
+                else:
+                    rows = m.bbox_roi_extractor.roi_layers[0].forward_nhwc_split(c5, rois)
+                    keep = [maps, props, counts, c5, rois, rows]
                 for v in range(V):
                     o = v * T * P
-                    cls, reg = m._head(rows[o:o + T * P], [dict(start=s, length=P)], None)
+                    if V > 1:
+                        cls = [head._split_out(h[v * P:(v + 1) * P])[0] for h in heads]
+                        reg = [head._split_out(h[v * P:(v + 1) * P])[1] for h in heads]
+                    else:
+                        cls, reg = m._head(rows[o:o + T * P], [dict(start=s, length=P)], None)
                     rois_key = rois[o + s:o + s + P].clone()
                     rois_key[:, 0] = 0
                     # the head outputs are post-processed on parallel branches (tiny, latency-bound kernels)

@@ -266,3 +266,26 @@ def test_selsa_graph_runner(cuda):
         m.enable_cuda_graphs(False)
     for c in range(30):
         assert np.array_equal(got[0][c], ref[0][c])
+
+
+def test_batched_windows_bit_identical(world):
+    """forward_feat_batch through the graph runner (batched-over-videos head: row-wise GEMMs once
+    over all videos, attention per video) == per-video eager forward_feat, bit for bit."""
+    import numpy as np
+    m, dev = world['model'], world['dev']
+    frames = world['frames'].to(dev)
+    m.enable_cuda_graphs(False)
+    orders = ([0, 1, 2], [2, 0, 1], [1, 1, 0])
+    c4 = [m(img=frames[i:i + 1], img_meta=[world['metas'][0]], backbone_feat=True)[0] for i in range(3)]
+    refs = [m(x=[c4[i] for i in o], img=None, img_meta=world['metas'], forward_feat=True, return_loss=False,
+              rescale=True) for o in orders]
+    m.enable_cuda_graphs(True)
+    try:
+        for _ in range(2):
+            got = m.forward_feat_batch([[c4[i] for i in o] for o in orders], world['metas'], rescale=True)
+            for v in range(3):
+                for o in range(2):
+                    for c in range(30):
+                        assert np.array_equal(got[v][o][c], refs[v][o][c])
+    finally:
+        m.enable_cuda_graphs(False)

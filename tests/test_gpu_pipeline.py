@@ -289,3 +289,48 @@ def test_batched_windows_bit_identical(world):
                         assert np.array_equal(got[v][o][c], refs[v][o][c])
     finally:
         m.enable_cuda_graphs(False)
+
+
+def test_ragged_proposal_counts(world):
+    """Frames that yield FEWER than max_num proposals (hnmb_rcnn.py:586-587: the key range comes
+    from the actual per-frame counts).  A low RPN NMS threshold leaves < 300 survivors per frame;
+    the graph runner's speculation must fail over to the eager path and the second stage must agree
+    with the oracle on the oracle's (ragged) proposals."""
+    import copy
+    import numpy as np
+    from oracle import cref, ref_torch as R
+    m, dev, sd = world['model'], world['dev'], world['sd']
+    old = m.test_cfg
+    cfg = copy.deepcopy(old)
+    cfg.rpn.nms_thr = 0.05
+    m.test_cfg = cfg
+    try:
+        rpn_cfg = dict(nms_pre=6000, nms_post=300, max_num=300, nms_thr=0.05)
+        with torch.no_grad():
+            ref, raux = R.hnmb_forward_feat(sd, [c for c in world['c4_ref'].split(1)], world['metas'], 1,
+                                            rpn_cfg=rpn_cfg, roi_align_fn=cref.roi_align, return_aux=True)
+        counts = [p.shape[0] for p in raux['proposals']]
+        assert all(c < 300 for c in counts) and len(set(counts)) > 1, counts
+        c4s = [m(img=world['frames'][i:i + 1].to(dev), img_meta=[world['metas'][i]], backbone_feat=True)[0]
+               for i in range(3)]
+        res, aux = m(x=c4s, img=None, img_meta=world['metas'], forward_feat=True, return_loss=False, rescale=True,
+                     return_aux=True)
+        assert all(abs(a - b) <= 3 for a, b in zip(aux['counts'], counts)), (aux['counts'], counts)
+        res2, aux2 = m(x=c4s, img=None, img_meta=world['metas'], forward_feat=True, return_loss=False, rescale=True,
+                       proposals=[p.to(dev) for p in raux['proposals']], return_aux=True)
+        assert aux2['start'] == counts[0] and aux2['length'] == counts[1]
+        for a, b in zip(aux2['cls'] + aux2['reg'], raux['cls'] + raux['reg']):
+            assert a.shape == b.shape and _rel(a.cpu(), b) < 1e-3
+        # graph runner: speculation (300 per frame) fails -> same result as the eager path
+        m.enable_cuda_graphs(True)
+        try:
+            c4g = [m(img=world['frames'][i:i + 1].to(dev), img_meta=[world['metas'][i]], backbone_feat=True)[0]
+                   for i in range(3)]
+            got = m(x=c4g, img=None, img_meta=world['metas'], forward_feat=True, return_loss=False, rescale=True)
+        finally:
+            m.enable_cuda_graphs(False)
+        for o in range(2):
+            for c in range(30):
+                assert np.array_equal(got[o][c], res[o][c])
+    finally:
+        m.test_cfg = old

@@ -334,3 +334,21 @@ def test_ragged_proposal_counts(world):
                 assert np.array_equal(got[o][c], res[o][c])
     finally:
         m.test_cfg = old
+
+
+def test_detect_video_window_loop(world):
+    """R15 on the device: the sliding-window driver emits one detection per frame, each equal to a
+    direct forward_feat call on the scheduled window."""
+    import numpy as np
+    from hvrnet_b200.video import detect_video, window_schedule
+    m, dev = world['model'], world['dev']
+    frames = [world['frames'][i % 3:i % 3 + 1].to(dev) for i in range(5)]
+    res = detect_video(m, frames, world['metas'][0], window=3, rng=np.random.RandomState(3))
+    assert sorted(res) == [0, 1, 2, 3, 4]
+    sched = [e for e in window_schedule(5, 3, np.random.RandomState(3)) if e[2] >= 0]
+    idxs, offs, key = sched[2]
+    c4 = [m(img=frames[i], img_meta=[world['metas'][0]], backbone_feat=True)[0] for i in idxs]
+    ref = m(x=c4, img=None, img_meta=world['metas'], forward_feat=True, return_loss=False, rescale=True)
+    for o in range(2):
+        for c in range(30):
+            assert np.array_equal(res[key][o][c], ref[o][c])

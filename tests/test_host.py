@@ -192,3 +192,21 @@ def test_checkpoint_loader_mmdet_format(tmp_path):
     assert 'rpn_head.rpn_cls.bias' in missing and unexpected == ['extra.weight'] and mismatch[0][0] == 'bbox_head.fc_cls.weight'
     with pytest.raises(RuntimeError):
         checkpoint.load_state_dict(m, bad, strict=True)
+
+
+@pytest.mark.parametrize('seg_len,window', [(40, 15), (15, 15), (9, 15), (100, 21), (3, 7), (30, 3)])
+def test_window_schedule_matches_reference_loop(seg_len, window):
+    """R15: the window schedule (which frames are in the deque, which offset the result is filed
+    under, how the random pre-padding consumes the numpy RNG) equals the oracle's trace of
+    tools/hnl_test.py:359-463."""
+    import numpy as np
+    from hvrnet_b200.video import window_schedule
+    from oracle.window_loop import trace
+    ref = trace(seg_len, window, np.random.RandomState(7))
+    got = list(window_schedule(seg_len, window, np.random.RandomState(7)))
+    assert len(got) == len(ref)
+    for (gi, go, gk), (ri, ro, rk) in zip(got, ref):
+        assert gi == ri and go == ro and gk == rk
+    keys = [k for _, _, k in got if k >= 0]
+    if seg_len >= window:
+        assert sorted(set(keys)) == list(range(seg_len))          # one detection per frame of the video

@@ -41,6 +41,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--videos-per-gpu', type=int, default=0, help='key frames (of different videos) batched per step (default 7: 133 of 148 SMs busy in the trunk)')
     ap.add_argument('--no-streaming', action='store_true', help='skip the extra (labelled) streaming-scheduler figure')
+    ap.add_argument('--no-other-workloads', action='store_true', help='skip the short side measurements of the other BASELINE.json configs')
     ap.add_argument('--eager', action='store_true', help='disable CUDA graphs (per-kernel Python launches)')
     ap.add_argument('--gemm-report', default=None, help='write a per-shape table of the igemm launches (csv)')
     return ap.parse_args()
@@ -398,6 +399,41 @@ def main():
                              'product (tensor-pipe work = 3x), so frac <= 1/3 by construction'},
     }
     line['roi_align'] = roi_rf
+    # the other single-GPU configurations of BASELINE.json, measured briefly through the same public
+    # call surface (one video per GPU, device-resident frames) so every config has a number on record
+    if world == 1 and args.workload == 'hrnmp' and not args.no_other_workloads and not args.eager:
+        others = {}
+        for wl in ('selsa', 'faster_rcnn'):
+            model = None
+            torch.cuda.empty_cache()
+            model, _, w2 = configs.build_workload(wl, dev)
+            T2 = w2['t_dim']
+            metas2 = [synth.make_img_meta() for _ in range(T2)]
+            model.enable_cuda_graphs(wl != 'faster_rcnn')
+            from collections import deque
+            dq = deque(maxlen=T2)
+
+            def one(i):
+                img = devf[i % len(devf)]
+                if wl == 'faster_rcnn':
+                    return model(img=[img], img_meta=[[metas2[0]]], return_loss=False, rescale=True)
+                dq.append(model(img=img, img_meta=[metas2[0]], backbone_feat=True)[0])
+                if len(dq) < T2:
+                    return None
+                return model(x=list(dq), img=None, img_meta=metas2, forward_feat=True, return_loss=False, rescale=True)
+            for i in range(T2 + 3):
+                one(i)
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for i in range(10):
+                one(T2 + 3 + i)
+            b_.record()
+            torch.cuda.synchronize()
+            others[wl] = {'value': 10 / (a_.elapsed_time(b_) / 1e3), 'unit': 'frames/s', 'videos_per_gpu': 1,
+                          'workload': workload_name(wl, T2)}
+        line['other_workloads'] = others
+        model = None
     if streaming is not None:
         line['streaming'] = streaming
     if rank == 0:

@@ -7,6 +7,7 @@ are loaded standalone with empty stand-ins for the modules they import but do no
   mmdet/core/bbox/transforms.py           delta2bbox, bbox2roi, bbox2result   (R6, R13)
   mmdet/core/post_processing/bbox_nms.py  multiclass_nms                      (R12)
   mmdet/ops/nms/src/nms_cpu.cpp           nms (compiled unmodified, oracle/_ref) (R7)
+  mmdet/core/evaluation/mean_ap.py        eval_map as tools/vid_eval.py calls it (next row N3)
 
 multiclass_nms runs on the reference's CPU NMS, i.e. the `>=` threshold semantic
 (nms_cpu.cpp:55); the oracle reproduces it with strict_gt=False.  Inputs are seeded; the
@@ -101,9 +102,54 @@ def main():
         d, l = bbox_nms.multiclass_nms(boxes, scores, 0.001, dict(type='nms', iou_thr=0.3), 300)
         out['mc_%s_scores' % tag], out['mc_%s_dets' % tag], out['mc_%s_labels' % tag] = scores, d, l
     out['mc_boxes'] = boxes
+    # ---- eval_map (next row N3): the reference's mean_ap.py as a package with stubbed printing deps
+    sys.modules.setdefault('terminaltables', types.ModuleType('terminaltables'))
+    sys.modules['terminaltables'].AsciiTable = object
+    ev_pkg = types.ModuleType('ref_eval')
+    ev_pkg.__path__ = [os.path.join(REF, 'core/evaluation')]
+    sys.modules['ref_eval'] = ev_pkg
+    for name in ('bbox_overlaps', 'class_names', 'mean_ap'):
+        spec = importlib.util.spec_from_file_location('ref_eval.' + name, os.path.join(REF, 'core/evaluation', name + '.py'))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules['ref_eval.' + name] = mod
+        try:
+            spec.loader.exec_module(mod)
+        except Exception:
+            if name != 'class_names':
+                raise
+    mean_ap = sys.modules['ref_eval.mean_ap']
+    rs = np.random.RandomState(99)
+    n_img, n_cls = 40, 6
+    gts, gls, igs, dets = [], [], [], []
+    for _ in range(n_img):
+        k = rs.randint(0, 4)
+        xy = rs.rand(k, 2) * 300
+        wh = rs.rand(k, 2) * 150 + 10
+        g = np.hstack([xy, xy + wh]).astype(np.float32)
+        gts.append(g)
+        gls.append(rs.randint(1, n_cls + 1, size=k))
+        igs.append(rs.rand(k) < 0.15)
+        per = []
+        for c in range(n_cls):
+            own = g[gls[-1] == c + 1]
+            jit = own + rs.randn(*own.shape).astype(np.float32) * 12 if own.shape[0] else np.zeros((0, 4), np.float32)
+            dup = jit[:1] + 3 if jit.shape[0] else np.zeros((0, 4), np.float32)
+            m = rs.randint(0, 3)
+            xy2 = rs.rand(m, 2) * 300
+            rnd = np.hstack([xy2, xy2 + rs.rand(m, 2) * 150 + 10]).astype(np.float32)
+            b = np.vstack([jit, dup, rnd]).astype(np.float32)
+            per.append(np.hstack([b, rs.rand(b.shape[0], 1).astype(np.float32)]))
+        dets.append(per)
+    m_ap, res = mean_ap.eval_map(dets, gts, gls, gt_ignore=igs, scale_ranges=None, iou_thr=0.5,
+                                 dataset=('a', 'b', 'c', 'd', 'e', 'f'), print_summary=False)
+    m_ap2, res2 = mean_ap.eval_map(dets, gts, gls, gt_ignore=None, scale_ranges=None, iou_thr=0.5,
+                                   dataset=('a', 'b', 'c', 'd', 'e', 'f'), print_summary=False)
+    out['ev_dets'], out['ev_gts'], out['ev_labels'], out['ev_ignore'] = dets, gts, gls, igs
+    out['ev_map'], out['ev_map_noignore'] = m_ap, m_ap2
+    out['ev_cls'] = [dict(num_gts=int(r['num_gts']), num_dets=int(r['num_dets']), ap=float(r['ap']),
+                          recall=np.asarray(r['recall']), precision=np.asarray(r['precision'])) for r in res]
     torch.save(out, os.path.join(HERE, 'ref_golden.pt'))
-    print('wrote', os.path.join(HERE, 'ref_golden.pt'), {k: (tuple(v.shape) if hasattr(v, 'shape') else len(v))
-                                                         for k, v in out.items()})
+    print('wrote', os.path.join(HERE, 'ref_golden.pt'), sorted(out.keys()))
 
 
 if __name__ == '__main__':

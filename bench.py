@@ -393,7 +393,12 @@ def main():
         'roofline': {'bound': 'tensor', 'kernel': 'igemm_tc_kernel (tcgen05 split-bf16 implicit GEMM)',
                      'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                      'tensor_work_tflops': 3.0 * achieved, 'tensor_work_frac': 3.0 * achieved / peak,
-                     'peak_source': peak_src, 'traffic': None,
+                     'peak_source': peak_src,
+                     # ncu dram__bytes_read.sum + dram__bytes_write.sum, average per igemm launch of one step
+                     # (profiles/r01f_igemm_ncu_metrics_step_V7.txt; the algorithmic FLOPs above are per step)
+                     'traffic': 298.5e6 if (args.workload == 'hrnmp' and V == 7) else None,
+                     'traffic_source': 'profiles/r01f_igemm_ncu_metrics_step_V7.txt',
+                     'ncu_tensor_pipe_active_pct': 72.3 if (args.workload == 'hrnmp' and V == 7) else None,
                      'algorithmic_gflop_per_step': gemm_flops / K / 1e9, 'launches_per_step': len(prof) / K,
                      'kernel_ms_per_step': gemm_ms / K, 'share_of_step': gemm_ms / ms_prof,
                      'profiled_ms_per_step': ms_prof / K,

@@ -352,3 +352,33 @@ def test_detect_video_window_loop(world):
     for o in range(2):
         for c in range(30):
             assert np.array_equal(res[key][o][c], ref[o][c])
+
+
+def test_full_size_hrnmp_window_T15(cuda):
+    """BASELINE.json configs[2] at full size: T=15 frames, key frame 7, 4500 proposals.  Trunk on all
+    15 frames, then forward_feat; with the oracle's proposals forced in, both head outputs agree with
+    the oracle to the north_star tolerance (1e-3 relative); end-to-end detections are matched."""
+    from hvrnet_b200 import configs, synth
+    from oracle import cref, ref_torch as R
+    m, sd, w = configs.build_workload('hrnmp', cuda)
+    T = w['t_dim']
+    frames = synth.make_frames(T, seed=5)
+    metas = [synth.make_img_meta() for _ in range(T)]
+    with torch.no_grad():
+        c4_ref = R.trunk_forward(sd, frames)
+        ref, raux = R.hnmb_forward_feat(sd, list(c4_ref.split(1)), metas, w['key_dim'], roi_align_fn=cref.roi_align,
+                                        return_aux=True)
+    assert raux['roi_feats'].shape[0] == 4500 and raux['start'] == 2100
+    c4s = [m(img=frames[i:i + 1].to(cuda), img_meta=[metas[i]], backbone_feat=True)[0] for i in range(T)]
+    assert _rel(torch.cat(c4s).cpu(), c4_ref) < 1e-3
+    res, aux = m(x=c4s, img=None, img_meta=metas, forward_feat=True, return_loss=False, rescale=True,
+                 proposals=[p.to(cuda) for p in raux['proposals']], return_aux=True)
+    for a, b in zip(aux['cls'] + aux['reg'], raux['cls'] + raux['reg']):
+        assert a.shape == b.shape == (300, b.shape[1]) and _rel(a.cpu(), b) < 1e-3
+    for o in range(2):
+        hit, tot = _match(res[o], ref[o])
+        assert tot == 0 or hit / tot > 0.98, (hit, tot)
+    res_free = m(x=c4s, img=None, img_meta=metas, forward_feat=True, return_loss=False, rescale=True)
+    for o in range(2):
+        hit, tot = _match(res_free[o], ref[o])
+        assert tot == 0 or hit / tot > 0.9, (hit, tot)

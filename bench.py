@@ -230,8 +230,8 @@ def main():
             if from_host and model._runner is None:
                 img = img.to(dev, non_blocking=True)
             c4 = model(img=img, img_meta=[metas[0]] * V, backbone_feat=True)[0]
-            if from_host and model._runner is not None:
-                model._runner.prefetch(hostV[T + (i + 1) % pool])    # next step's H2D overlaps this step's window graph
+            if model._runner is not None:   # next step's H2D + trunk overlap this step's window graph (side stream)
+                model._runner.prefetch((hostV if from_host else devV)[T + (i + 1) % pool])
             for v, t in enumerate(GraphRunner.per_frame(c4)):
                 dqs[v].append(t)
             if inter:   # configs 4-5: one all-gather of the post-fc_new_4 key rows, ring-order supports

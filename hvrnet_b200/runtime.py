@@ -31,31 +31,29 @@ class GraphRunner:
         self._window = {}
         self.replayed_launches = 0      # kernels launched through graph replays (bench.py gpu_launches)
         self._copy_stream = None
-        self._staged = None             # (id of the host tensor, device copy, ready event)
-        self._stage_bufs = {}
-        self._stage_flip = 0
+        self._staged = None             # (id of the prefetched tensor, trunk already run, ready event)
 
     # ------------------------------------------------------------------ input prefetch
-    def prefetch(self, img_host):
-        """Start the host->device copy of the NEXT step's frames on a copy stream so it overlaps the
-        current step's window graph; ``extract`` picks the staged copy up when it is handed the same
-        host tensor.  (The copy still happens once per step, inside whatever region the caller times.)"""
-        if img_host.is_cuda:
-            return
+    def prefetch(self, img, trunk=True):
+        """Software pipelining of the NEXT step: on a side stream, copy its frames host->device and
+        (trunk=True) replay the trunk graph on them, so both overlap the current step's window
+        graph; ``extract`` picks the result up when it is handed the same tensor.  All of the work
+        still happens once per step, inside whatever region the caller times."""
+        key = tuple(img.shape)
+        c = self._trunk.get(key)
+        if c is None:
+            return                                   # trunk graph not captured yet: first call goes through extract()
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream()
-        key = (tuple(img_host.shape), self._stage_flip)
-        self._stage_flip ^= 1
-        buf = self._stage_bufs.get(key)
-        if buf is None:
-            buf = torch.empty(img_host.shape, dtype=torch.float32, device='cuda:%d' % torch.cuda.current_device())
-            self._stage_bufs[key] = buf
-        self._copy_stream.wait_stream(torch.cuda.current_stream())   # the buffer's previous consumer has been enqueued
-        with torch.cuda.stream(self._copy_stream):
-            buf.copy_(img_host, non_blocking=True)
+        side = self._copy_stream
+        side.wait_stream(torch.cuda.current_stream())   # previous consumers of the static buffers are enqueued
+        with torch.cuda.stream(side):
+            c.inputs.copy_(img, non_blocking=True)
+            if trunk:
+                c.graph.replay()
             ev = torch.cuda.Event()
             ev.record()
-        self._staged = (id(img_host), buf, ev)
+        self._staged = (id(img), trunk, ev)
 
     # ------------------------------------------------------------------ capture helper
     def _capture(self, fn):
@@ -77,7 +75,7 @@ class GraphRunner:
 
     # ------------------------------------------------------------------ trunk
     def extract(self, img):
-        key = (tuple(img.shape), img.device.index)
+        key = tuple(img.shape)
         c = self._trunk.get(key)
         if c is None:
             buf = torch.zeros(img.shape, dtype=torch.float32, device='cuda:%d' % torch.cuda.current_device())
@@ -89,13 +87,14 @@ class GraphRunner:
             c.inputs = buf
             self._trunk[key] = c
         if self._staged is not None and self._staged[0] == id(img):
-            _, buf, ev = self._staged
+            _, trunk_done, ev = self._staged
             self._staged = None
-            torch.cuda.current_stream().wait_event(ev)
-            c.inputs.copy_(buf, non_blocking=True)      # staged by prefetch(): D2D into the static buffer
+            torch.cuda.current_stream().wait_event(ev)   # frames (and trunk) staged by prefetch()
+            if not trunk_done:
+                c.graph.replay()
         else:
             c.inputs.copy_(img, non_blocking=True)      # H2D (pinned host) or D2D into the static buffer
-        c.graph.replay()
+            c.graph.replay()
         self.replayed_launches += c.launches
         s, nchw = c.outputs
         out = nchw.clone()                              # the caller keeps C4 maps in its window deque

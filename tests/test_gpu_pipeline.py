@@ -382,3 +382,27 @@ def test_full_size_hrnmp_window_T15(cuda):
     for o in range(2):
         hit, tot = _match(res_free[o], ref[o])
         assert tot == 0 or hit / tot > 0.9, (hit, tot)
+
+
+def test_prefetch_pipelining_same_results(world):
+    """GraphRunner.prefetch (next step's H2D + trunk on a side stream, overlapping the current window
+    graph) hands extract() the same C4 bits as the in-line path, from pinned host or device frames."""
+    m, dev = world['model'], world['dev']
+    host = [world['frames'][i:i + 1].contiguous().pin_memory() for i in range(3)]
+    m.enable_cuda_graphs(True)
+    try:
+        ref = [m(img=host[i], img_meta=[world['metas'][0]], backbone_feat=True)[0] for i in range(3)]
+        run = m._runner
+        got = []
+        cur = m(img=host[0], img_meta=[world['metas'][0]], backbone_feat=True)[0]
+        for i in range(3):
+            got.append(cur)
+            nxt = host[(i + 1) % 3]
+            run.prefetch(nxt)
+            # work on the main stream while the side stream runs the next trunk
+            m(x=[cur, cur, cur], img=None, img_meta=world['metas'], forward_feat=True, return_loss=False, rescale=True)
+            cur = m(img=nxt, img_meta=[world['metas'][0]], backbone_feat=True)[0]
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b) and torch.equal(a._hvr_split.hi, b._hvr_split.hi)
+    finally:
+        m.enable_cuda_graphs(False)

@@ -198,66 +198,95 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 constexpr int SM_THREADS = 256;
-constexpr int SM_PER = 32;  // register-cached elements per thread
+constexpr int SM_VEC = 8;   // float4 per thread cached in registers: rows up to 8192 columns in one pass
+__device__ __forceinline__ float block_reduce(float v, bool is_max, float* red, float* bcast) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    float t = lane < SM_THREADS / 32 ? red[lane] : (is_max ? -INFINITY : 0.f);
+    t = is_max ? warp_max(t) : warp_sum(t);
+    if (lane == 0) *bcast = t;
+  }
+  __syncthreads();
+  return *bcast;
+}
+// One CTA per row.  Vector path (ld_s % 4 == 0, ld_p % 4 == 0, 16-byte aligned rows): LDG.128 of
+// the logits, row cached in registers, 8-byte packed bf16 stores of hi and lo.
 __global__ void __launch_bounds__(SM_THREADS) softmax_rows_kernel(const float* __restrict__ S, int cols, long long ld_s,
                                                                   __nv_bfloat16* __restrict__ phi,
-                                                                  __nv_bfloat16* __restrict__ plo, long long ld_p) {
+                                                                  __nv_bfloat16* __restrict__ plo, long long ld_p,
+                                                                  int vec_ok) {
   __shared__ float red[SM_THREADS / 32];
   __shared__ float bcast;
-  const int row = blockIdx.x;
+  const int row = blockIdx.x, tid = threadIdx.x;
   const float* s = S + (size_t)row * ld_s;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  float v[SM_PER];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < SM_PER; ++j) {
-    const int c = tid + j * SM_THREADS;
-    v[j] = c < cols ? __ldg(s + c) : -INFINITY;
-    mx = fmaxf(mx, v[j]);
-  }
-  for (int c = tid + SM_PER * SM_THREADS; c < cols; c += SM_THREADS) mx = fmaxf(mx, __ldg(s + c));
-  mx = warp_max(mx);
-  if (lane == 0) red[wid] = mx;
-  __syncthreads();
-  if (wid == 0) {
-    float t = lane < SM_THREADS / 32 ? red[lane] : -INFINITY;
-    t = warp_max(t);
-    if (lane == 0) bcast = t;
-  }
-  __syncthreads();
-  mx = bcast;
-  float sum = 0.f;
-#pragma unroll
-  for (int j = 0; j < SM_PER; ++j) {
-    const int c = tid + j * SM_THREADS;
-    v[j] = c < cols ? expf(v[j] - mx) : 0.f;
-    sum += v[j];
-  }
-  for (int c = tid + SM_PER * SM_THREADS; c < cols; c += SM_THREADS) sum += expf(__ldg(s + c) - mx);
-  sum = warp_sum(sum);
-  __syncthreads();
-  if (lane == 0) red[wid] = sum;
-  __syncthreads();
-  if (wid == 0) {
-    float t = lane < SM_THREADS / 32 ? red[lane] : 0.f;
-    t = warp_sum(t);
-    if (lane == 0) bcast = t;
-  }
-  __syncthreads();
-  const float inv = 1.0f / bcast;
   __nv_bfloat16* ph = phi + (size_t)row * ld_p;
   __nv_bfloat16* pl = plo + (size_t)row * ld_p;
+  if (vec_ok && cols <= SM_VEC * SM_THREADS * 4) {
+    const int nv = (cols + 3) >> 2;          // float4 groups that contain a valid column
+    float4 v[SM_VEC];
+    float mx = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < SM_PER; ++j) {
-    const int c = tid + j * SM_THREADS;
-    if (c < ld_p) {
-      __nv_bfloat16 h, l;
-      split2(c < cols ? v[j] * inv : 0.f, h, l);
-      ph[c] = h;
-      pl[c] = l;
+    for (int j = 0; j < SM_VEC; ++j) {
+      const int g = tid + j * SM_THREADS;
+      if (g < nv) {
+        v[j] = __ldg(reinterpret_cast<const float4*>(s) + g);
+        const int c = g << 2;                // tail group: columns >= cols do not take part
+        if (c + 1 >= cols) v[j].y = -INFINITY;
+        if (c + 2 >= cols) v[j].z = -INFINITY;
+        if (c + 3 >= cols) v[j].w = -INFINITY;
+        mx = fmaxf(mx, fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w)));
+      } else {
+        v[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
     }
+    mx = block_reduce(mx, true, red, &bcast);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < SM_VEC; ++j) {
+      // same per-element arithmetic and per-thread accumulation order as the scalar path would give
+      // for the elements this thread owns; the row sum is a tree over threads in both paths
+      v[j].x = expf(v[j].x - mx); v[j].y = expf(v[j].y - mx); v[j].z = expf(v[j].z - mx); v[j].w = expf(v[j].w - mx);
+      sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    sum = block_reduce(sum, false, red, &bcast);
+    const float inv = 1.0f / sum;
+    const int npv = (int)(ld_p >> 2);
+#pragma unroll
+    for (int j = 0; j < SM_VEC; ++j) {
+      const int g = tid + j * SM_THREADS;
+      if (g < npv) {
+        const float4 p = g < nv ? make_float4(v[j].x * inv, v[j].y * inv, v[j].z * inv, v[j].w * inv)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        __nv_bfloat16 h[4], l[4];
+        split2(p.x, h[0], l[0]); split2(p.y, h[1], l[1]); split2(p.z, h[2], l[2]); split2(p.w, h[3], l[3]);
+        uint2 hv, lv;
+        hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+        hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+        lv.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+        lv.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+        *reinterpret_cast<uint2*>(ph + (g << 2)) = hv;
+        *reinterpret_cast<uint2*>(pl + (g << 2)) = lv;
+      }
+    }
+    for (int g = tid + SM_VEC * SM_THREADS; g < npv; g += SM_THREADS) {      // zero padding beyond the cached span
+      *reinterpret_cast<uint2*>(ph + (g << 2)) = make_uint2(0, 0);
+      *reinterpret_cast<uint2*>(pl + (g << 2)) = make_uint2(0, 0);
+    }
+    return;
   }
-  for (int c = tid + SM_PER * SM_THREADS; c < ld_p; c += SM_THREADS) {
+  // scalar path: any alignment, any length (re-reads the row)
+  float mx = -INFINITY;
+  for (int c = tid; c < cols; c += SM_THREADS) mx = fmaxf(mx, __ldg(s + c));
+  mx = block_reduce(mx, true, red, &bcast);
+  float sum = 0.f;
+  for (int c = tid; c < cols; c += SM_THREADS) sum += expf(__ldg(s + c) - mx);
+  sum = block_reduce(sum, false, red, &bcast);
+  const float inv = 1.0f / sum;
+  for (int c = tid; c < ld_p; c += SM_THREADS) {
     __nv_bfloat16 h, l;
     split2(c < cols ? expf(__ldg(s + c) - mx) * inv : 0.f, h, l);
     ph[c] = h;
@@ -348,8 +377,10 @@ extern "C" int hvr_softmax_rows_split(const float* S, int rows, int cols, int64_
                                       hvr_bf16* p_lo, int64_t ld_p, void* stream) {
   if (!S || !p_hi || !p_lo || cols < 1 || cols > ld_s || cols > ld_p) return HVR_ERR_ARG;
   if (rows == 0) return HVR_OK;
+  const int vec_ok = (ld_s % 4 == 0) && (ld_p % 4 == 0) && ((reinterpret_cast<uintptr_t>(S) & 15u) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(p_hi) & 7u) == 0) && ((reinterpret_cast<uintptr_t>(p_lo) & 7u) == 0);
   softmax_rows_kernel<<<rows, SM_THREADS, 0, ST(stream)>>>(S, cols, ld_s, (__nv_bfloat16*)p_hi,
-                                                           (__nv_bfloat16*)p_lo, ld_p);
+                                                           (__nv_bfloat16*)p_lo, ld_p, vec_ok);
   HVR_LAUNCHED();
   return HVR_OK;
 }

@@ -324,8 +324,9 @@ def relation_batched(P, idx, X, XT, V, N, Npad, q_range=None, res=None, relu=Tru
     return out
 
 
-def hrnmp_forward_batched(P, rows, V, N, Npad, start, length, **kw):
-    """rows Split [V*Npad, 12544].  Returns fp32 (out1, out2) of shape [V*length, 64]."""
+def hrnmp_stage123_batched(P, rows, V, N, Npad, start, length, **kw):
+    """Stages 1-3 + fc_new_4 for V windows at once.  rows Split [V*Npad, 12544].  Returns
+    (out1 fp32 [V*length, 64], f4 Split [V*Npad, D], f4^T Split [D, V*Npad])."""
     s, n = start, length
     f1, _, f1T = lin(rows, P['fc1'], want_T=True, **kw)
     a1 = relation_batched(P, 1, f1, f1T, V, N, Npad, res=f1, **kw)
@@ -339,6 +340,13 @@ def hrnmp_forward_batched(P, rows, V, N, Npad, start, length, **kw):
     f3, _, f3T = lin(x3, P['fc3'], want_T=True, **kw)
     a3 = relation_batched(P, 3, f3, f3T, V, N, Npad, res=f3, **kw)
     f4, _, f4T = lin(a3, P['fc4'], want_T=True, **kw)
+    return out1, f4, f4T
+
+
+def hrnmp_forward_batched(P, rows, V, N, Npad, start, length, **kw):
+    """rows Split [V*Npad, 12544].  Returns fp32 (out1, out2) of shape [V*length, 64]."""
+    s, n = start, length
+    out1, f4, f4T = hrnmp_stage123_batched(P, rows, V, N, Npad, s, n, **kw)
     a4 = relation_batched(P, 4, f4, f4T, V, N, Npad, q_range=(s, n), res=_key_rows(f4, V, Npad, s, n), **kw)
     _, out2, _ = lin(a4, P['out2'], want_split=False, want_f32=True, **kw)
     return out1, out2

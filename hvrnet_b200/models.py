@@ -698,6 +698,31 @@ class HNMBRCNN(_WindowRCNN):
         P = self.test_cfg.rpn['max_num']
         head = self.bbox_head
         per_video, z = [], []
+        V, T = len(xs), len(xs[0])
+        if proposals is None and V > 1 and all(len(x) == T for x in xs):
+            # all V windows at once: C5 / RPN / proposals / RoIAlign over the V*T frames, stages 1-3 with
+            # the row-wise GEMMs batched over the videos (engine.hrnmp_stage123_batched)
+            c4 = self._window_split([t for x in xs for t in x])
+            c5 = self.shared_head.forward_nhwc(c4) if self.feat_from_shared_head else ops.merge(c4)
+            props, counts = self.rpn_head.get_proposals(c4, img_meta[0]['img_shape'], self.test_cfg.rpn)
+            cnt = counts.cpu().tolist()
+            if any(c != P for c in cnt):
+                raise ValueError('inter-video exchange needs %d proposals per frame, got %s' % (P, cnt))
+            dev = c4.hi.device
+            N, s = T * P, self.key_dim * P
+            Npad = ops.round_up(N, 64)
+            fidx = torch.arange(V * T, device=dev, dtype=torch.float32).view(V * T, 1, 1).expand(V * T, P, 1)
+            rois = torch.cat([fidx, props[..., :4]], -1).view(V, N, 5)
+            rois_p = torch.zeros((V, Npad, 5), device=dev)
+            rois_p[:, :N] = rois
+            rows = self.bbox_roi_extractor.roi_layers[0].forward_nhwc_split(c5, rois_p.view(-1, 5))
+            out1, f4, f4T = engine.hrnmp_stage123_batched(head.packed(dev), rows, V, N, Npad, s, P)
+            for v in range(V):
+                f4v = f4[v * Npad:v * Npad + N]
+                f4Tv = ops.Split(f4T.hi[:, v * Npad:(v + 1) * Npad], f4T.lo[:, v * Npad:(v + 1) * Npad])
+                per_video.append((rois[v, s:s + P].clone(), out1[v * P:(v + 1) * P], f4v, f4Tv, s))
+                z.append(f4v[s:s + P])
+            xs = []
         for vi, x in enumerate(xs):
             c4 = self._window_split(x)
             rois, cnt, rows, _ = self._rois_and_feats(c4, img_meta, None if proposals is None else proposals[vi])

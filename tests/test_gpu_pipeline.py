@@ -406,3 +406,30 @@ def test_prefetch_pipelining_same_results(world):
             assert torch.equal(a, b) and torch.equal(a._hvr_split.hi, b._hvr_split.hi)
     finally:
         m.enable_cuda_graphs(False)
+
+
+def test_intervideo_batched_equals_per_video(world):
+    """forward_feat_intervideo batches the V windows (C5 / RPN / RoIAlign over all frames, row-wise
+    head GEMMs over all videos); the detections equal the per-video evaluation bit for bit."""
+    import numpy as np
+    m, dev = world['model'], world['dev']
+    frames = world['frames'].to(dev)
+    m.enable_cuda_graphs(False)
+    c4 = [m(img=frames[i:i + 1], img_meta=[world['metas'][0]], backbone_feat=True)[0] for i in range(3)]
+    orders = ([0, 1, 2], [2, 0, 1], [1, 2, 0])
+    xs = [[c4[i] for i in o] for o in orders]
+    got, aux = m.forward_feat_intervideo(xs, world['metas'], n_support=4, rescale=True, return_aux=True)
+    # reference: the same call with the per-video code path (proposals given explicitly disables batching)
+    props = []
+    for x in xs:
+        _, a = m(x=x, img=None, img_meta=world['metas'], forward_feat=True, return_loss=False, rescale=True,
+                 return_aux=True)
+        props.append([a['proposals'][t, :a['counts'][t]] for t in range(3)])
+    ref, raux = m.forward_feat_intervideo(xs, world['metas'], n_support=4, rescale=True, return_aux=True,
+                                          proposals=props)
+    for v in range(3):
+        for a, b in zip(aux[v]['cls'] + aux[v]['reg'], raux[v]['cls'] + raux[v]['reg']):
+            assert torch.equal(a, b)
+        for o in range(2):
+            for c in range(30):
+                assert np.array_equal(got[v][o][c], ref[v][o][c])

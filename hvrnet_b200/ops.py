@@ -214,7 +214,13 @@ def linear(a, w, n, bias=None, relu=False, res=None, alpha=1.0, want_split=True,
     if out is None:
         out = Split.empty((M, ld), dev) if want_split else None
     of = torch.empty((M, round_up(n, 4)), dtype=torch.float32, device=dev) if want_f32 else None
-    oT = Split.zeros((n, round_up(M, 64)), dev) if want_T else None
+    oT = None
+    if want_T:                                 # only the pad columns need zeros (they meet P's zero padding in P.V;
+        ldT = round_up(M, 64)                  # uninitialised memory could hold NaN bit patterns)
+        oT = Split.empty((n, ldT), dev)
+        if ldT > M:
+            oT.hi[:, M:].zero_()
+            oT.lo[:, M:].zero_()
     g = igemm_desc(a, w, n, alpha=alpha, bias=bias, res=res, relu=relu, out=out, out_f32=of, outT=oT, passes=passes)
     igemm_run(g, check_kernel)
     return out, of, oT

@@ -108,6 +108,7 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, const void* src, 
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -167,8 +168,12 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 // shared::cluster address of the same smem offset in the even (leader) CTA of the pair
 __device__ __forceinline__ uint32_t leader_addr(const void* p) { return smem_u32(p) & 0xFEFFFFFFu; }
+// Remote arrive without a cluster-scope release: the only thing the waiter (the leader's MMA
+// thread) needs ordered is this warp's tcgen05.ld traffic, which tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync already order.  (.release.cluster compiles to MEMBAR.ALL.GPU +
+// ERRBAR, which stalled on the TMA stores in flight: 13 % of the epilogue warps' samples.)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(bar)) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(bar)) : "memory");
 }
 __device__ __forceinline__ void tma2_load_2d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1) {
   asm volatile(

@@ -439,31 +439,103 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
 // arms it with the bytes of both); empty[s] / tmem_full[b] are per CTA, signalled by multicast
 // tcgen05.commit; tmem_empty[b] lives in the leader and counts the 8 epilogue warps of the pair.
 // ------------------------------------------------------------------------------------
-template <int BN>
+// DEEP = deep-epilogue variant for layers whose epilogue (not the main loop) sets the pace (short
+// K, residual add, split output): 2 ring stages instead of 3; the shared memory that frees goes to
+// 3 in-place staging buffers per TMEM lane quarter (32 rows x 64 columns, hi|lo, 128-byte rows,
+// SWIZZLE_128B) and the CTA runs EIGHT epilogue warps: the two warps that may read a lane quarter
+// (w, w+4) each take 32 of the 64 columns of a chunk.  The residual tile of chunk g+2 is in flight
+// (TMA load) while chunk g is computed in place and chunk g-1 drains (TMA store), across tile
+// boundaries.
+constexpr int DEEP_NBUF = 3;
+constexpr int DEEP_TILE_BYTES = 32 * 128;            // 32 rows x 64 bf16
+constexpr int DEEP_BUF_BYTES = 2 * DEEP_TILE_BYTES;  // hi | lo
+template <int BN, bool DEEP = false>
 struct Cfg2 {
   static constexpr int BH_BYTES = (BN / 2) * BK * 2;              // this CTA's half of one B tile
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;  // A hi/lo + B-half hi/lo
-  static constexpr int STAGES = (BN == 256) ? 3 : 4;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_SMEM + 1024 + 256;
+  static constexpr int STAGES = DEEP ? 2 : ((BN == 256) ? 3 : 4);
+  static constexpr int EPI_WARP = DEEP ? DEEP_NBUF * DEEP_BUF_BYTES : EPI_WARP_BYTES;   // per lane quarter
+  static constexpr int EPI_BYTES = 4 * EPI_WARP;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int THREADS = DEEP ? 320 : 192;                // 2 + 8 or 2 + 4 warps
 };
 
-template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Deep epilogue: 32 columns (half `half` of a 64-column chunk) of one row, in place in the lane
+// quarter's staging tile.  row_hi / row_lo: this lane's 128-byte rows; 16-byte chunk j of row r sits
+// at chunk j ^ (r & 7).  b4: the 32 bias values, loaded by the caller ahead of the barrier waits.
+__device__ __forceinline__ void deep_half(const KParams& p, const uint32_t (&acc)[32], const float4 (&b4)[8],
+                                          uint8_t* row_hi, uint8_t* row_lo, int sw, int half, bool has_res) {
+  float v[32];
+  if (p.alpha == 1.0f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * p.alpha;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[4 * j] += b4[j].x; v[4 * j + 1] += b4[j].y; v[4 * j + 2] += b4[j].z; v[4 * j + 3] += b4[j].w;
+  }
+  if (has_res) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const int ch = ((half * 4 + j / 8) ^ sw) << 4;
+      const uint4 h = *reinterpret_cast<const uint4*>(row_hi + ch);
+      const uint4 l = *reinterpret_cast<const uint4*>(row_lo + ch);
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+      const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[j + 2 * q] += __fadd_rn(bf16bits_to_f32(hw[q] & 0xFFFFu), bf16bits_to_f32(lw[q] & 0xFFFFu));
+        v[j + 2 * q + 1] += __fadd_rn(bf16bits_to_f32(hw[q] >> 16), bf16bits_to_f32(lw[q] >> 16));
+      }
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
+  uint32_t hp[16], lp[16];
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j], v[j + 1]);
+    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(__fsub_rn(v[j], __uint_as_float(hb << 16)),
+                                                    __fsub_rn(v[j + 1], __uint_as_float(hb & 0xFFFF0000u)));
+    hp[j / 2] = hb;
+    lp[j / 2] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ch = ((half * 4 + j) ^ sw) << 4;
+    *reinterpret_cast<uint4*>(row_hi + ch) = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
+    *reinterpret_cast<uint4*>(row_lo + ch) = make_uint4(lp[4 * j], lp[4 * j + 1], lp[4 * j + 2], lp[4 * j + 3]);
+  }
+}
+
+template <int BN, bool DEEP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DEEP ? 320 : 192, 1)
     igemm_tc2_kernel(const __grid_constant__ KParams p) {
-  using C_ = Cfg2<BN>;
+  using C_ = Cfg2<BN, DEEP>;
   constexpr int STAGES = C_::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* tiles = smem_raw + pad;
   uint8_t* epi_smem = tiles + STAGES * C_::STAGE_BYTES;          // 4 warps x [res_hi|res_lo|out_hi|out_lo]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + EPI_SMEM);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + C_::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
-  uint64_t* res_bar = tmem_empty_bar + 2;            // [4] one per epilogue warp (residual TMA loads)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 4);
+  constexpr int NRES = DEEP ? 4 * DEEP_NBUF : 4;     // residual TMA barriers: per lane quarter (x staging buffer)
+  uint64_t* res_bar = tmem_empty_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + NRES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -488,9 +560,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 8);   // 4 epilogue warps x 2 CTAs (used in the leader only)
+      mbar_init(&tmem_empty_bar[b], DEEP ? 16 : 8);   // epilogue warps x 2 CTAs (used in the leader only)
     }
-    for (int w = 0; w < 4; ++w) mbar_init(&res_bar[w], 1);
+    for (int w = 0; w < NRES; ++w) mbar_init(&res_bar[w], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -572,85 +644,189 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
       }
     }
   } else {
-    // ================= epilogue (both CTAs, own 128 rows) =================
-    const int q = warp & 3;
-    const int m = q * 32 + lane;
-    uint32_t res_phase = 0;
-    int lt = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
-      const int nt = tile % n_tiles;
-      const int m_tile = 2 * (tile / n_tiles) + (int)rank;
-      const int tx = m_tile % p.tiles_x;
-      const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-      const int bimg = m_tile / (p.tiles_x * p.tiles_y);
-      const int px = tx * p.tile_w + m % p.tile_w;
-      const int py = ty * p.tile_h + m / p.tile_w;
-      const bool row_ok = (px < p.out_w) && (py < p.out_h) && (bimg < p.batch);
-      const long long row = ((long long)bimg * p.out_h + py) * p.out_w + px;
-      const int ab = lt & 1;
-      const uint32_t aph = (uint32_t)((lt >> 1) & 1);
-      // TMA epilogue: this warp's 32 rows are the pixel box (bw x bh) at (ox, oy) of image bimg
-      const int ox = tx * p.tile_w + (q * 32) % p.tile_w;
-      const int oy = ty * p.tile_h + (q * 32) / p.tile_w;
-      const bool t_out = (p.tma_epi & 1) != 0, t_res = (p.tma_epi & 2) != 0;
-      uint8_t* ebuf = epi_smem + (warp - 2) * EPI_WARP_BYTES;
-      uint64_t* rbar = &res_bar[warp - 2];
-      if (t_res && lane == 0) {                          // residual of chunk 0: in flight during the main loop
-        mbar_expect_tx(rbar, 2 * EPI_TILE_BYTES);
-        tma_load_4d(ebuf, &p.tmR_hi, rbar, nt * BN, ox, oy, bimg);
-        tma_load_4d(ebuf + EPI_TILE_BYTES, &p.tmR_lo, rbar, nt * BN, ox, oy, bimg);
+    if constexpr (DEEP) {
+      // ================= deep epilogue (both CTAs, own 128 rows, 8 warps) =================
+      // Chunks of 64 columns, numbered g = 0, 1, ... over all tiles of this CTA; chunk g lives in
+      // staging buffer g % 3 of its lane quarter.  Steady state for chunk g: its residual tile landed
+      // two chunks ago; accumulator + residual -> split output written in place by the quarter's two
+      // warps (32 columns each) -> TMA store(g); then, once store(g-1) has been read out of buffer
+      // (g+2) % 3, the residual of chunk g+2 is loaded into it.
+      const int q = warp & 3;                     // TMEM lane quarter
+      const int half = (warp - 2) >> 2;           // which 32 of a chunk's 64 columns
+      const bool issuer = half == 0 && lane == 0; // the quarter's TMA thread
+      const bool t_res = (p.tma_epi & 2) != 0;
+      uint8_t* wbuf = epi_smem + q * C_::EPI_WARP;
+      uint64_t* rbar = res_bar + q * DEEP_NBUF;
+      const int sw = lane & 7;
+      const int qx = (q * 32) % p.tile_w, qy = (q * 32) / p.tile_w;
+      // load cursor (issuer only): runs two chunks ahead of the consumer, across tile boundaries
+      int l_tile = cluster_id, l_c = 0, l_g = 0, l_n0 = 0, l_x = 0, l_y = 0, l_b = 0;
+      auto load_tile = [&]() {
+        const int nt = l_tile % n_tiles;
+        const int m_tile = 2 * (l_tile / n_tiles) + (int)rank;
+        const int tx = m_tile % p.tiles_x;
+        const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+        l_n0 = nt * BN;
+        l_x = tx * p.tile_w + qx;
+        l_y = ty * p.tile_h + qy;
+        l_b = m_tile / (p.tiles_x * p.tiles_y);
+      };
+      auto issue_load = [&]() {
+        if (l_tile < num_tiles) {
+          uint8_t* dst = wbuf + (l_g % DEEP_NBUF) * DEEP_BUF_BYTES;
+          uint64_t* bar = &rbar[l_g % DEEP_NBUF];
+          mbar_expect_tx(bar, DEEP_BUF_BYTES);
+          tma_load_4d(dst, &p.tmR_hi, bar, l_n0 + l_c, l_x, l_y, l_b);
+          tma_load_4d(dst + DEEP_TILE_BYTES, &p.tmR_lo, bar, l_n0 + l_c, l_x, l_y, l_b);
+          ++l_g;
+          l_c += 64;
+          if (l_c >= BN || l_n0 + l_c >= p.n) {
+            l_c = 0;
+            l_tile += num_clusters;
+            if (l_tile < num_tiles) load_tile();
+          }
+        }
+      };
+      if (t_res && issuer) {
+        if (l_tile < num_tiles) load_tile();
+        issue_load();
+        issue_load();
       }
-      mbar_wait(&tmem_full_bar[ab], aph);
-      tc_fence_after();
+      int g = 0, lt = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
+        const int nt = tile % n_tiles;
+        const int m_tile = 2 * (tile / n_tiles) + (int)rank;
+        const int tx = m_tile % p.tiles_x;
+        const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+        const int bimg = m_tile / (p.tiles_x * p.tiles_y);
+        const int ox = tx * p.tile_w + qx;
+        const int oy = ty * p.tile_h + qy;
+        const int ab = lt & 1;
+        const uint32_t aph = (uint32_t)((lt >> 1) & 1);
+        mbar_wait(&tmem_full_bar[ab], aph);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        const int nb = nt * BN + c0;
-        uint32_t acc[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0), acc);
-        ResRegs rr;
-        rr.valid = false;
-        if (t_res) {
-          mbar_wait(rbar, res_phase);
-          res_phase ^= 1u;
-          const uint8_t* mh = ebuf + lane * 64;
-          const int sw = (lane >> 1) & 3;
+        for (int c0 = 0; c0 < BN && nt * BN + c0 < p.n; c0 += 64, ++g) {
+          const int nb = nt * BN + c0;            // first column of the chunk
+          const int nh = nb + half * 32;          // first column of this warp's half
+          uint8_t* buf = wbuf + (g % DEEP_NBUF) * DEEP_BUF_BYTES;
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0 + half * 32), acc);
+          // bias of the 32 columns: requested before the waits so its latency hides behind them
+          float4 b4[8];
+          if (p.bias && p.n - nh >= 32) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            rr.h[j] = *reinterpret_cast<const uint4*>(mh + ((j ^ sw) << 4));
-            rr.l[j] = *reinterpret_cast<const uint4*>(mh + EPI_TILE_BYTES + ((j ^ sw) << 4));
+            for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + nh) + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = nh + 4 * j;
+              b4[j].x = (p.bias && c < p.n) ? __ldg(p.bias + c) : 0.f;
+              b4[j].y = (p.bias && c + 1 < p.n) ? __ldg(p.bias + c + 1) : 0.f;
+              b4[j].z = (p.bias && c + 2 < p.n) ? __ldg(p.bias + c + 2) : 0.f;
+              b4[j].w = (p.bias && c + 3 < p.n) ? __ldg(p.bias + c + 3) : 0.f;
+            }
           }
-          rr.valid = true;
-          __syncwarp();
-          if (c0 + 32 < BN && lane == 0) {               // next chunk's residual lands while this one is processed
-            fence_proxy_async();
-            mbar_expect_tx(rbar, 2 * EPI_TILE_BYTES);
-            tma_load_4d(ebuf, &p.tmR_hi, rbar, nb + 32, ox, oy, bimg);
-            tma_load_4d(ebuf + EPI_TILE_BYTES, &p.tmR_lo, rbar, nb + 32, ox, oy, bimg);
-          }
-        } else {
-          prefetch_res(p, row, nb, row_ok, rr);
-        }
-        tmem_ld_wait();
-        if (t_out) {
-          if (lane == 0) bulk_wait_read0();              // the previous chunk's store has drained the tile
-          __syncwarp();
-        }
-        epilogue_chunk(p, acc, row, nb, row_ok, rr, t_out ? ebuf + 2 * EPI_TILE_BYTES : nullptr, lane);
-        if (t_out) {
+          if (t_res) mbar_wait(&rbar[g % DEEP_NBUF], (uint32_t)((g / DEEP_NBUF) & 1));
+          tmem_ld_wait();
+          uint8_t* row_hi = buf + lane * 128;
+          deep_half(p, acc, b4, row_hi, row_hi + DEEP_TILE_BYTES, sw, half, t_res);
           fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_4d(&p.tmO_hi, ebuf + 2 * EPI_TILE_BYTES, nb, ox, oy, bimg);
-            tma_store_4d(&p.tmO_lo, ebuf + 3 * EPI_TILE_BYTES, nb, ox, oy, bimg);
+          named_bar_sync(1 + q, 64);              // both halves of the chunk are in the staging tile
+          if (issuer) {
+            tma_store_4d(&p.tmO_hi, buf, nb, ox, oy, bimg);
+            tma_store_4d(&p.tmO_lo, buf + DEEP_TILE_BYTES, nb, ox, oy, bimg);
             bulk_commit();
+            bulk_wait_read1();                     // store(g-1) has left buffer (g+2) % 3
+            if (t_res) issue_load();               // residual of chunk g+2
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[ab]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[ab]);
-    }
-    if ((p.tma_epi & 1) && lane == 0) bulk_wait0();
+      if (issuer) bulk_wait0();
+    } else {
+      // ================= epilogue (both CTAs, own 128 rows) =================
+      const int q = warp & 3;
+      const int m = q * 32 + lane;
+      uint32_t res_phase = 0;
+      int lt = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
+        const int nt = tile % n_tiles;
+        const int m_tile = 2 * (tile / n_tiles) + (int)rank;
+        const int tx = m_tile % p.tiles_x;
+        const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+        const int bimg = m_tile / (p.tiles_x * p.tiles_y);
+        const int px = tx * p.tile_w + m % p.tile_w;
+        const int py = ty * p.tile_h + m / p.tile_w;
+        const bool row_ok = (px < p.out_w) && (py < p.out_h) && (bimg < p.batch);
+        const long long row = ((long long)bimg * p.out_h + py) * p.out_w + px;
+        const int ab = lt & 1;
+        const uint32_t aph = (uint32_t)((lt >> 1) & 1);
+        // TMA epilogue: this warp's 32 rows are the pixel box (bw x bh) at (ox, oy) of image bimg
+        const int ox = tx * p.tile_w + (q * 32) % p.tile_w;
+        const int oy = ty * p.tile_h + (q * 32) / p.tile_w;
+        const bool t_out = (p.tma_epi & 1) != 0, t_res = (p.tma_epi & 2) != 0;
+        uint8_t* ebuf = epi_smem + (warp - 2) * EPI_WARP_BYTES;
+        uint64_t* rbar = &res_bar[warp - 2];
+        if (t_res && lane == 0) {                          // residual of chunk 0: in flight during the main loop
+          mbar_expect_tx(rbar, 2 * EPI_TILE_BYTES);
+          tma_load_4d(ebuf, &p.tmR_hi, rbar, nt * BN, ox, oy, bimg);
+          tma_load_4d(ebuf + EPI_TILE_BYTES, &p.tmR_lo, rbar, nt * BN, ox, oy, bimg);
+        }
+        mbar_wait(&tmem_full_bar[ab], aph);
+        tc_fence_after();
+  #pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          const int nb = nt * BN + c0;
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0), acc);
+          ResRegs rr;
+          rr.valid = false;
+          if (t_res) {
+            mbar_wait(rbar, res_phase);
+            res_phase ^= 1u;
+            const uint8_t* mh = ebuf + lane * 64;
+            const int sw = (lane >> 1) & 3;
+  #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              rr.h[j] = *reinterpret_cast<const uint4*>(mh + ((j ^ sw) << 4));
+              rr.l[j] = *reinterpret_cast<const uint4*>(mh + EPI_TILE_BYTES + ((j ^ sw) << 4));
+            }
+            rr.valid = true;
+            __syncwarp();
+            if (c0 + 32 < BN && lane == 0) {               // next chunk's residual lands while this one is processed
+              fence_proxy_async();
+              mbar_expect_tx(rbar, 2 * EPI_TILE_BYTES);
+              tma_load_4d(ebuf, &p.tmR_hi, rbar, nb + 32, ox, oy, bimg);
+              tma_load_4d(ebuf + EPI_TILE_BYTES, &p.tmR_lo, rbar, nb + 32, ox, oy, bimg);
+            }
+          } else {
+            prefetch_res(p, row, nb, row_ok, rr);
+          }
+          tmem_ld_wait();
+          if (t_out) {
+            if (lane == 0) bulk_wait_read0();              // the previous chunk's store has drained the tile
+            __syncwarp();
+          }
+          epilogue_chunk(p, acc, row, nb, row_ok, rr, t_out ? ebuf + 2 * EPI_TILE_BYTES : nullptr, lane);
+          if (t_out) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&p.tmO_hi, ebuf + 2 * EPI_TILE_BYTES, nb, ox, oy, bimg);
+              tma_store_4d(&p.tmO_lo, ebuf + 3 * EPI_TILE_BYTES, nb, ox, oy, bimg);
+              bulk_commit();
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[ab]);
+      }
+      if ((p.tma_epi & 1) && lane == 0) bulk_wait0();
+      }
   }
   tc_fence_before();
   __syncthreads();
@@ -787,6 +963,7 @@ int validate(const HvrIGemm* g) {
 }
 
 int g_force_bn = 0;   // test hook (hvr_debug_force_bn): 0 = heuristic
+int g_deep_mode = 0;  // test hook: 0 = heuristic, 1 = deep epilogue wherever it applies, 2 = never
 bool g_tma_epilogue = true;   // test hook: bit 10 of hvr_debug_force_bn's argument selects the per-row epilogue
 
 template <int BN>
@@ -829,11 +1006,12 @@ int launch(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
   return HVR_OK;
 }
 
-template <int BN>
+template <int BN, bool DEEP>
 int launch2(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    HVR_CUDA(cudaFuncSetAttribute(igemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::SMEM));
+    HVR_CUDA(cudaFuncSetAttribute(igemm_tc2_kernel<BN, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg2<BN, DEEP>::SMEM));
     attr_set = true;
   }
   const uint64_t ktot = (uint64_t)g->ntaps * g->a_c;
@@ -856,15 +1034,15 @@ int launch2(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
   const long long clusters = pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(2 * clusters));
-  cfg.blockDim = dim3(192);
-  cfg.dynamicSmemBytes = Cfg2<BN>::SMEM;
+  cfg.blockDim = dim3(Cfg2<BN, DEEP>::THREADS);
+  cfg.dynamicSmemBytes = Cfg2<BN, DEEP>::SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  HVR_CUDA(cudaLaunchKernelEx(&cfg, igemm_tc2_kernel<BN>, kp));
+  HVR_CUDA(cudaLaunchKernelEx(&cfg, igemm_tc2_kernel<BN, DEEP>, kp));
   HVR_LAUNCHED();
   return HVR_OK;
 }
@@ -915,42 +1093,71 @@ extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
   kp.outT_hi = reinterpret_cast<__nv_bfloat16*>(g->outT_hi);
   kp.outT_lo = reinterpret_cast<__nv_bfloat16*>(g->outT_lo);
   kp.ld_outT = g->ld_outT;
-  // TMA epilogue maps: the [rows, ld] output / residual seen as (C = n, W, H, B) pixel tensors; one
-  // box = one epilogue warp's 32 rows x 32 columns (64-byte rows, SWIZZLE_64B); out-of-range
-  // columns / pixels are clipped (store) or zero-filled (load) by the TMA unit.
-  kp.tma_epi = 0;
-  if (g_tma_epilogue) {
-    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-    const uint32_t bw = g->tile_w < 32 ? (uint32_t)g->tile_w : 32u;
-    const uint32_t ebox[4] = {32, bw, 32 / bw, 1};
-    const uint64_t edims[4] = {(uint64_t)g->n, (uint64_t)g->out_w, (uint64_t)g->out_h, (uint64_t)g->batch};
-    if (g->out_hi && g->ld_out % 8 == 0 && al16(g->out_hi) && al16(g->out_lo)) {
-      const uint64_t es[3] = {(uint64_t)g->ld_out * 2, (uint64_t)g->out_w * g->ld_out * 2,
-                              (uint64_t)g->out_h * g->out_w * g->ld_out * 2};
-      rc = make_map(&kp.tmO_hi, g->out_hi, 4, edims, es, ebox, 64);
-      if (rc) return rc;
-      rc = make_map(&kp.tmO_lo, g->out_lo, 4, edims, es, ebox, 64);
-      if (rc) return rc;
-      kp.tma_epi |= 1;
-    }
-    if (g->res_hi && g->ld_res % 8 == 0 && al16(g->res_hi) && al16(g->res_lo)) {
-      const uint64_t es[3] = {(uint64_t)g->ld_res * 2, (uint64_t)g->out_w * g->ld_res * 2,
-                              (uint64_t)g->out_h * g->out_w * g->ld_res * 2};
-      rc = make_map(&kp.tmR_hi, g->res_hi, 4, edims, es, ebox, 64);
-      if (rc) return rc;
-      rc = make_map(&kp.tmR_lo, g->res_lo, 4, edims, es, ebox, 64);
-      if (rc) return rc;
-      kp.tma_epi |= 2;
-    }
-  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // Tile width: 256 when the problem still fills the machine (halves the A traffic per FLOP),
-  // 64 for narrow outputs or when 128-wide tiles would leave most SMs idle.
   const long long m_tiles = (long long)kp.tiles_x * kp.tiles_y * kp.batch;
   int bn = g_force_bn;
   // CTA pairs (256-row tiles, B split across the pair) once there is a full machine of pair tiles
   const long long pair_tiles = ((m_tiles + 1) / 2) * hvr_cdiv(g->n, 256);
-  if (g->passes >= 3 && g->n >= 128 && ((bn == 0 && pair_tiles >= 64) || bn == 512)) return launch2<256>(g, kp, st);
+  const bool pair = g->passes >= 3 && g->n >= 128 && ((bn == 0 && pair_tiles >= 64) || bn == 512 || bn == 640);
+  // 128-wide pair tiles when the output is only 128 columns wide (half of a 256-wide tile would be
+  // MMA work on zero-filled weight rows)
+  const bool pair128 = pair && (bn == 640 || (bn == 0 && g->n <= 128));
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  const bool out_tma = g_tma_epilogue && g->out_hi && g->ld_out % 8 == 0 && al16(g->out_hi) && al16(g->out_lo);
+  const bool res_tma = g_tma_epilogue && g->res_hi && g->ld_res % 8 == 0 && al16(g->res_hi) && al16(g->res_lo);
+  // Deep epilogue (pair kernel, 2 ring stages): split output only, everything through TMA.  Chosen
+  // where the epilogue sets the pace: residual layers, and short-K layers (the main loop of a tile
+  // is shorter than a 3-stage pipeline needs anyway).
+  const bool deep_ok = pair && !pair128 && out_tma && !g->out_f32 && !g->outT_hi && (!g->res_hi || res_tma);
+  const int total_k = g->ntaps * kp.cblocks;
+  // Measured (scripts/epilogue_bench.py, profiles/r01h_epilogue_bench.csv): the deep variant wins for
+  // K <= 512 (trunk / C5 conv3: 1.1-1.55x) and for single-wave problems, whose epilogue cannot hide
+  // behind a next tile (trunk layer3 conv1 / conv2 at 7 frames); with K >= 1024 and several tiles per
+  // CTA pair the third ring stage is worth more than the faster epilogue.
+  int sms = 0;
+  {
+    int dev = 0;
+    static int cached = 0;
+    if (!cached) {
+      HVR_CUDA(cudaGetDevice(&dev));
+      HVR_CUDA(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev));
+    }
+    sms = cached;
+  }
+  const bool deep = deep_ok && (g_deep_mode == 1 || (g_deep_mode == 0 && (total_k <= 8 || pair_tiles <= sms / 2)));
+  // TMA epilogue maps: the [rows, ld] output / residual seen as (C = n, W, H, B) pixel tensors; one
+  // box = one epilogue warp's 32 rows x 32 columns (64-byte rows, SWIZZLE_64B) or, for the deep
+  // epilogue, 32 rows x 64 columns (128-byte rows, SWIZZLE_128B); out-of-range columns / pixels are
+  // clipped (store) or zero-filled (load) by the TMA unit.
+  kp.tma_epi = 0;
+  {
+    const uint32_t bw = g->tile_w < 32 ? (uint32_t)g->tile_w : 32u;
+    const uint32_t ebox[4] = {deep ? 64u : 32u, bw, 32 / bw, 1};
+    const int esw = deep ? 128 : 64;
+    const uint64_t edims[4] = {(uint64_t)g->n, (uint64_t)g->out_w, (uint64_t)g->out_h, (uint64_t)g->batch};
+    if (out_tma) {
+      const uint64_t es[3] = {(uint64_t)g->ld_out * 2, (uint64_t)g->out_w * g->ld_out * 2,
+                              (uint64_t)g->out_h * g->out_w * g->ld_out * 2};
+      rc = make_map(&kp.tmO_hi, g->out_hi, 4, edims, es, ebox, esw);
+      if (rc) return rc;
+      rc = make_map(&kp.tmO_lo, g->out_lo, 4, edims, es, ebox, esw);
+      if (rc) return rc;
+      kp.tma_epi |= 1;
+    }
+    if (res_tma) {
+      const uint64_t es[3] = {(uint64_t)g->ld_res * 2, (uint64_t)g->out_w * g->ld_res * 2,
+                              (uint64_t)g->out_h * g->out_w * g->ld_res * 2};
+      rc = make_map(&kp.tmR_hi, g->res_hi, 4, edims, es, ebox, esw);
+      if (rc) return rc;
+      rc = make_map(&kp.tmR_lo, g->res_lo, 4, edims, es, ebox, esw);
+      if (rc) return rc;
+      kp.tma_epi |= 2;
+    }
+  }
+  if (pair128) return launch2<128, false>(g, kp, st);
+  if (pair) return deep ? launch2<256, true>(g, kp, st) : launch2<256, false>(g, kp, st);
+  // Tile width: 256 when the problem still fills the machine (halves the A traffic per FLOP),
+  // 64 for narrow outputs or when 128-wide tiles would leave most SMs idle.
   if (bn == 0) {
     if (g->n <= 64) bn = 64;
     else if (g->n % 256 == 0 && m_tiles * (g->n / 256) >= 2 * 148) bn = 256;
@@ -964,8 +1171,10 @@ extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
 
 extern "C" int hvr_debug_force_bn(int bn) {
   g_tma_epilogue = (bn & 1024) == 0;
-  bn &= ~1024;
-  if (bn != 0 && bn != 64 && bn != 128 && bn != 256 && bn != 512) return HVR_ERR_ARG;   // 512 = CTA-pair kernel
+  g_deep_mode = (bn & 2048) ? 1 : ((bn & 4096) ? 2 : 0);   // bit 11: deep epilogue wherever it applies, bit 12: never
+  bn &= ~(1024 | 2048 | 4096);
+  // 512 = CTA-pair kernel (256-wide tiles), 640 = CTA-pair kernel with 128-wide tiles
+  if (bn != 0 && bn != 64 && bn != 128 && bn != 256 && bn != 512 && bn != 640) return HVR_ERR_ARG;
   g_force_bn = bn;
   return HVR_OK;
 }

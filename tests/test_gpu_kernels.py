@@ -83,9 +83,10 @@ def test_igemm_linear(cuda, M, K, N, relu, use_res, use_bias):
     assert _rel(of2[:, :N].double().cpu(), ref) < 1e-5
 
 
-@pytest.mark.parametrize('bn', [64, 128, 256, 512])
+@pytest.mark.parametrize('bn', [64, 128, 256, 512, 640])
 def test_igemm_tile_widths(cuda, bn):
-    """Every N-tile instantiation of the persistent kernel (512 = the cta_group::2 pair kernel) on a
+    """Every N-tile instantiation of the persistent kernel (512 / 640 = the cta_group::2 pair kernel with
+    256- / 128-wide tiles) on a
     multi-tile, multi-wave problem (more tiles than SMs, so each CTA walks several tiles through
     both TMEM buffers)."""
     from hvrnet_b200 import _lib, ops
@@ -147,7 +148,7 @@ def test_igemm_cta_pair_conv(cuda):
     assert _rel(ops.nhwc_split_to_nchw(out).double().cpu(), ref) < 3e-5
 
 
-@pytest.mark.parametrize('force', [0, 64, 128, 256, 512])
+@pytest.mark.parametrize('force', [0, 64, 128, 256, 512, 640])
 def test_igemm_tma_epilogue_matches_per_row_epilogue(cuda, force):
     """The TMA epilogue (residual tiles loaded / split output tiles stored by TMA through swizzled
     shared memory) writes the same bits as the per-row register epilogue (flag 1024)."""
@@ -172,6 +173,73 @@ def test_igemm_tma_epilogue_matches_per_row_epilogue(cuda, force):
         assert torch.equal(x, y)
     ref = _ref_linear(a, w, N, bias, res, True, 1.0)
     assert _rel(outs[0][2].double().cpu(), ref) < 3e-5
+
+
+@pytest.mark.parametrize('M,K,N,use_res', [
+    (128 * 9 + 50, 256, 600, True),          # ragged M and N (600 = 9*64 + 24: clipped last chunk)
+    (128 * 9 + 50, 256, 600, False),         # store-only staging
+    (128 * 150 + 3, 128, 1024, True),        # more pair tiles than clusters: prefetch crosses tile boundaries
+    (128 * 5, 1024, 320, True),              # odd number of 128-row tiles, N tail inside a 256 tile
+])
+def test_igemm_deep_epilogue_bit_identical(cuda, M, K, N, use_res):
+    """The deep-epilogue pair kernel (2 ring stages, 3 in-place 64-column staging buffers per
+    epilogue warp, residual prefetched two chunks ahead across tiles; flag 2048) writes the same
+    bits as the 3-stage pair kernel (flag 4096) and as the per-row register epilogue (flag 1024)."""
+    from hvrnet_b200 import _lib, ops
+    g = torch.Generator().manual_seed(M + N + int(use_res))
+    a = ops.split(torch.randn(M, K, generator=g).to(cuda))
+    w = ops.split((torch.randn(ops.round_up(N, 64), K, generator=g) / math.sqrt(K)).to(cuda))
+    bias = torch.randn(ops.round_up(N, 64), generator=g).to(cuda)
+    res = ops.split(torch.randn(M, ops.round_up(N, 8), generator=g).to(cuda)) if use_res else None
+    outs = []
+    for flag in (512 | 2048, 512 | 4096, 512 | 4096 | 1024):
+        _lib.lib().hvr_debug_force_bn(flag)
+        try:
+            o, _, _ = ops.linear(a, w, N, bias=bias, relu=True, res=res, want_split=True)
+            torch.cuda.synchronize()
+        finally:
+            _lib.lib().hvr_debug_force_bn(0)
+        outs.append((o.hi[:, :N].clone(), o.lo[:, :N].clone()))
+    for other in outs[1:]:
+        assert torch.equal(outs[0][0], other[0]) and torch.equal(outs[0][1], other[1])
+    ref = _ref_linear(a, w, N, bias, res, True, 1.0)
+    from hvrnet_b200.ops import Split
+    assert _rel(ops.merge(Split(outs[0][0].contiguous(), outs[0][1].contiguous())).double().cpu(), ref) < 3e-5
+
+
+@pytest.mark.parametrize('tile', [(16, 8), (8, 16), (32, 4), (64, 2), (128, 1)])
+def test_igemm_deep_epilogue_conv_tile_shapes(cuda, tile):
+    """Deep epilogue on every pixel-box shape of the M tile: 1x1 conv + residual + ReLU on a map
+    whose width / height are not multiples of the tile (clipped boxes)."""
+    import torch.nn.functional as F
+    from hvrnet_b200 import _lib, engine, ops
+    from hvrnet_b200.ops import Split
+    g = torch.Generator().manual_seed(100 + tile[0])
+    B, H, W, C, N = 3, 38, 63, 64, 320
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(N, C, 1, 1, generator=g) / math.sqrt(C)
+    r = torch.randn(B, N, H, W, generator=g)
+    xs, rs = ops.nchw_to_nhwc_split(x.to(cuda)), ops.nchw_to_nhwc_split(r.to(cuda))
+    wp = engine.pack_conv(w, None, cuda)
+    rows = B * H * W
+    outs = []
+    for flag in (512 | 2048, 512 | 4096):
+        out = Split.zeros((B, H, W, N), cuda)
+        gd = ops.igemm_desc(xs, wp, N, taps=engine._taps(1, 1), out_whb=(W, H, B), tile=tile, relu=True,
+                            res=Split(rs.hi.view(rows, N), rs.lo.view(rows, N)),
+                            out=Split(out.hi.view(rows, N), out.lo.view(rows, N)))
+        _lib.lib().hvr_debug_force_bn(flag)
+        try:
+            ops.igemm_run(gd)
+            torch.cuda.synchronize()
+        finally:
+            _lib.lib().hvr_debug_force_bn(0)
+        outs.append(out)
+    assert torch.equal(outs[0].hi, outs[1].hi) and torch.equal(outs[0].lo, outs[1].lo)
+    xm = ops.nhwc_split_to_nchw(xs).double().cpu()
+    wm = ops.merge(wp).double().cpu()[:N].view(N, 1, 1, C).permute(0, 3, 1, 2)
+    ref = (F.conv2d(xm, wm) + ops.nhwc_split_to_nchw(rs).double().cpu()).clamp_min(0)
+    assert _rel(ops.nhwc_split_to_nchw(outs[0]).double().cpu(), ref) < 3e-5
 
 
 @pytest.mark.parametrize('tile', [(16, 8), (8, 16), (32, 4), (64, 2), (128, 1)])

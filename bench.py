@@ -230,7 +230,9 @@ def main():
             if from_host and model._runner is None:
                 img = img.to(dev, non_blocking=True)
             c4 = model(img=img, img_meta=[metas[0]] * V, backbone_feat=True)[0]
-            if model._runner is not None:   # next step's H2D + trunk overlap this step's window graph (side stream)
+            # next step's H2D + trunk overlap this step's window graph (side stream); not in the roofline leg,
+            # whose per-launch event timings must not see a second stream's kernels
+            if model._runner is not None and model._runner.capture:
                 model._runner.prefetch((hostV if from_host else devV)[T + (i + 1) % pool])
             for v, t in enumerate(GraphRunner.per_frame(c4)):
                 dqs[v].append(t)
@@ -249,7 +251,9 @@ def main():
 
     def timed(from_host, K, W, profile=False):
         # the roofline leg brackets individual launches with events, which needs the eager path
-        model.enable_cuda_graphs(not (profile or args.eager) and args.workload != 'faster_rcnn')   # inter: trunk graph only
+        # (the runner's launch sequence - batched head, forked branches - re-issued eagerly: capture=False)
+        graphs_ok = not args.eager and args.workload != 'faster_rcnn'                                # inter: trunk graph only
+        model.enable_cuda_graphs(graphs_ok, capture=not profile)
         dq = prefill()
         for i in range(W):
             res = step(dq, i, from_host)

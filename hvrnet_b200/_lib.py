@@ -29,6 +29,7 @@ class HvrIGemm(ctypes.Structure):
         ('out_f32', c_vp), ('ld_f32', c_i64),
         ('outT_hi', c_vp), ('outT_lo', c_vp), ('ld_outT', c_i64),
         ('passes', c_int),
+        ('b_stride_batch', c_i64),
     ]
 
 
@@ -60,6 +61,10 @@ SIGNATURES = {
     'hvr_det_workspace_bytes': (c_sz, [c_int, c_int]),
     'hvr_det_postprocess': (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, ctypes.POINTER(c_f32), c_f32,
                                     c_f32, c_f32, c_int, c_f32, c_f32, c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'hvr_det_batched_workspace_bytes': (c_sz, [c_int, c_int, c_int]),
+    'hvr_det_postprocess_batched': (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int,
+                                            ctypes.POINTER(c_f32), c_f32, c_f32, c_f32, c_int, c_f32, c_f32, c_int,
+                                            c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'hvr_preprocess_u8': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_f32),
                                   ctypes.POINTER(c_f32), c_vp, c_vp]),
     'hvr_softmax_rows_split': (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_i64, c_vp]),

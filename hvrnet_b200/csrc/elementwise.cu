@@ -18,7 +18,7 @@ extern "C" const char* hvr_strerror(int code) {
   }
 }
 extern "C" int hvr_last_cuda_error(void) { return g_hvr_last_cuda_error; }
-extern "C" int hvr_abi_version(void) { return 1; }
+extern "C" int hvr_abi_version(void) { return 2; }
 extern "C" uint64_t hvr_launch_count(void) { return g_hvr_launches.load(); }
 
 namespace {

@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -48,7 +49,9 @@ struct alignas(64) KParams {
   int tile_w, tile_h, tiles_x, tiles_y;
   int out_w, out_h, batch;
   int n, n_tiles;
+  int b_batched;                                 // B operand has its own matrix per image (3rd TMA coordinate)
   int passes;
+  int pf;                                        // L2 prefetch distance of the A operand in K steps (0 = off)
   int relu;
   float alpha;
   const float* bias;
@@ -277,6 +280,34 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
     // ================= TMA producer =================
     if (lane == 0) {
       const uint32_t stage_tx = three ? (uint32_t)C_::STAGE_BYTES : (uint32_t)(A_BYTES + C_::B_BYTES);
+      // L2 prefetch cursor: walks the same (tile, tap, channel block) sequence p.pf K steps ahead of
+      // the loads, across tile boundaries, so activations streamed from HBM are already in L2 when
+      // the ring has room for them (the ring alone holds too few bytes in flight for HBM latency)
+      int q_tile = blockIdx.x, q_tap = 0, q_cb = 0, q_x0 = 0, q_y0 = 0, q_b = 0;
+      auto q_decode = [&]() {
+        const int m_tile = q_tile / n_tiles;
+        q_x0 = (m_tile % p.tiles_x) * p.tile_w;
+        q_y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.tile_h;
+        q_b = m_tile / (p.tiles_x * p.tiles_y);
+      };
+      auto q_step = [&]() {
+        if (q_tile >= num_tiles) return;
+        const int ax = q_x0 + p.tap_dx[q_tap], ay = q_y0 + p.tap_dy[q_tap];
+        tma_prefetch_4d(&p.tmA_hi, q_cb * BK, ax, ay, q_b);
+        if (three) tma_prefetch_4d(&p.tmA_lo, q_cb * BK, ax, ay, q_b);
+        if (++q_cb == p.cblocks) {
+          q_cb = 0;
+          if (++q_tap == p.ntaps) {
+            q_tap = 0;
+            q_tile += gridDim.x;
+            if (q_tile < num_tiles) q_decode();
+          }
+        }
+      };
+      if (p.pf > 0) {
+        if (q_tile < num_tiles) q_decode();
+        for (int i = 0; i < p.pf; ++i) q_step();
+      }
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int nt = tile % n_tiles;
@@ -291,15 +322,17 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
           for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+            if (p.pf > 0) q_step();
             mbar_wait(&empty_bar[s], ph ^ 1u);
             uint8_t* st = tiles + s * C_::STAGE_BYTES;
             mbar_expect_tx(&full_bar[s], stage_tx);
             const int kc = cb * BK;
             tma_load_4d(st, &p.tmA_hi, &full_bar[s], kc, ax, ay, bimg);
-            tma_load_2d(st + 2 * A_BYTES, &p.tmB_hi, &full_bar[s], tap * p.C + kc, n0);
+            tma_load_3d(st + 2 * A_BYTES, &p.tmB_hi, &full_bar[s], tap * p.C + kc, n0, p.b_batched ? bimg : 0);
             if (three) {
               tma_load_4d(st + A_BYTES, &p.tmA_lo, &full_bar[s], kc, ax, ay, bimg);
-              tma_load_2d(st + 2 * A_BYTES + C_::B_BYTES, &p.tmB_lo, &full_bar[s], tap * p.C + kc, n0);
+              tma_load_3d(st + 2 * A_BYTES + C_::B_BYTES, &p.tmB_lo, &full_bar[s], tap * p.C + kc, n0,
+                          p.b_batched ? bimg : 0);
             }
           }
         }
@@ -439,6 +472,34 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
 // arms it with the bytes of both); empty[s] / tmem_full[b] are per CTA, signalled by multicast
 // tcgen05.commit; tmem_empty[b] lives in the leader and counts the 8 epilogue warps of the pair.
 // ------------------------------------------------------------------------------------
+// M tile (128 output rows) of CTA `rank` in pair `pair_idx`.  Shared B: pairs run over the global
+// list of M tiles (the odd tail pairs a real tile with an image index >= batch).  Batched B: the two
+// CTAs of a pair share the B tile, so pairs never straddle images; the idle half of an image's odd
+// last pair gets ty = tiles_y.  Either way the idle CTA's loads are zero-filled and its stores clipped.
+struct MTile { int tx, ty, bimg; };
+__device__ __forceinline__ MTile pair_m_tile(const KParams& p, int pair_idx, int rank) {
+  MTile r;
+  const int tpi = p.tiles_x * p.tiles_y;
+  int m_in;
+  if (p.b_batched) {
+    const int ppi = (tpi + 1) >> 1;
+    r.bimg = pair_idx / ppi;
+    m_in = 2 * (pair_idx % ppi) + rank;
+  } else {
+    const int m_tile = 2 * pair_idx + rank;
+    r.bimg = m_tile / tpi;
+    m_in = m_tile % tpi;
+  }
+  if (m_in >= tpi) {
+    r.tx = 0;
+    r.ty = p.tiles_y;
+  } else {
+    r.tx = m_in % p.tiles_x;
+    r.ty = m_in / p.tiles_x;
+  }
+  return r;
+}
+
 // DEEP = deep-epilogue variant for layers whose epilogue (not the main loop) sets the pace (short
 // K, residual add, split output): 2 ring stages instead of 3; the shared memory that frees goes to
 // 3 in-place staging buffers per TMEM lane quarter (32 rows x 64 columns, hi|lo, 128-byte rows,
@@ -543,8 +604,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DEEP ? 320 : 192, 1)
   const bool leader = rank == 0;
   const int total_k = p.ntaps * p.cblocks;
   const int n_tiles = p.n_tiles;
-  const int m_tiles = p.tiles_x * p.tiles_y * p.batch;
-  const int m_pairs = (m_tiles + 1) >> 1;
+  const int m_pairs = p.b_batched ? ((p.tiles_x * p.tiles_y + 1) >> 1) * p.batch
+                                  : (p.tiles_x * p.tiles_y * p.batch + 1) >> 1;
   const int num_tiles = m_pairs * n_tiles;           // pair tiles
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
@@ -580,14 +641,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DEEP ? 320 : 192, 1)
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================
     if (lane == 0) {
+      // L2 prefetch cursor of this CTA's A rows, p.pf K steps ahead of the loads (see igemm_tc_kernel)
+      int q_tile = cluster_id, q_tap = 0, q_cb = 0, q_x0 = 0, q_y0 = 0, q_b = 0;
+      auto q_decode = [&]() {
+        const MTile mt = pair_m_tile(p, q_tile / n_tiles, (int)rank);
+        q_x0 = mt.tx * p.tile_w;
+        q_y0 = mt.ty * p.tile_h;
+        q_b = mt.bimg;
+      };
+      auto q_step = [&]() {
+        if (q_tile >= num_tiles) return;
+        const int ax = q_x0 + p.tap_dx[q_tap], ay = q_y0 + p.tap_dy[q_tap];
+        tma_prefetch_4d(&p.tmA_hi, q_cb * BK, ax, ay, q_b);
+        tma_prefetch_4d(&p.tmA_lo, q_cb * BK, ax, ay, q_b);
+        if (++q_cb == p.cblocks) {
+          q_cb = 0;
+          if (++q_tap == p.ntaps) {
+            q_tap = 0;
+            q_tile += num_clusters;
+            if (q_tile < num_tiles) q_decode();
+          }
+        }
+      };
+      if (p.pf > 0) {
+        if (q_tile < num_tiles) q_decode();
+        for (int i = 0; i < p.pf; ++i) q_step();
+      }
       int it = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int nt = tile % n_tiles;
-        const int m_tile = 2 * (tile / n_tiles) + (int)rank;
-        const int tx = m_tile % p.tiles_x;
-        const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-        const int bimg = m_tile / (p.tiles_x * p.tiles_y);   // >= batch for the odd tail: TMA zero-fills
-        const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
+        const MTile mt = pair_m_tile(p, tile / n_tiles, (int)rank);
+        const int bimg = mt.bimg;                             // idle half of an odd pair: TMA zero-fills
+        const int bb = p.b_batched ? bimg : 0;
+        const int x0 = mt.tx * p.tile_w, y0 = mt.ty * p.tile_h;
         const int n0 = nt * BN + (int)rank * (BN / 2);
         for (int tap = 0; tap < p.ntaps; ++tap) {
           const int ax = x0 + p.tap_dx[tap];
@@ -595,14 +681,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DEEP ? 320 : 192, 1)
           for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+            if (p.pf > 0) q_step();
             mbar_wait(&empty_bar[s], ph ^ 1u);
             uint8_t* st = tiles + s * C_::STAGE_BYTES;
             if (leader) mbar_expect_tx(&full_bar[s], 2u * (uint32_t)C_::STAGE_BYTES);
             const int kc = cb * BK;
             tma2_load_4d(st, &p.tmA_hi, &full_bar[s], kc, ax, ay, bimg);
-            tma2_load_2d(st + 2 * A_BYTES, &p.tmB_hi, &full_bar[s], tap * p.C + kc, n0);
+            tma2_load_3d(st + 2 * A_BYTES, &p.tmB_hi, &full_bar[s], tap * p.C + kc, n0, bb);
             tma2_load_4d(st + A_BYTES, &p.tmA_lo, &full_bar[s], kc, ax, ay, bimg);
-            tma2_load_2d(st + 2 * A_BYTES + C_::BH_BYTES, &p.tmB_lo, &full_bar[s], tap * p.C + kc, n0);
+            tma2_load_3d(st + 2 * A_BYTES + C_::BH_BYTES, &p.tmB_lo, &full_bar[s], tap * p.C + kc, n0, bb);
           }
         }
       }
@@ -663,13 +750,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DEEP ? 320 : 192, 1)
       int l_tile = cluster_id, l_c = 0, l_g = 0, l_n0 = 0, l_x = 0, l_y = 0, l_b = 0;
       auto load_tile = [&]() {
         const int nt = l_tile % n_tiles;
-        const int m_tile = 2 * (l_tile / n_tiles) + (int)rank;
-        const int tx = m_tile % p.tiles_x;
-        const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+        const MTile mt = pair_m_tile(p, l_tile / n_tiles, (int)rank);
         l_n0 = nt * BN;
-        l_x = tx * p.tile_w + qx;
-        l_y = ty * p.tile_h + qy;
-        l_b = m_tile / (p.tiles_x * p.tiles_y);
+        l_x = mt.tx * p.tile_w + qx;
+        l_y = mt.ty * p.tile_h + qy;
+        l_b = mt.bimg;
       };
       auto issue_load = [&]() {
         if (l_tile < num_tiles) {
@@ -695,10 +780,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DEEP ? 320 : 192, 1)
       int g = 0, lt = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
         const int nt = tile % n_tiles;
-        const int m_tile = 2 * (tile / n_tiles) + (int)rank;
-        const int tx = m_tile % p.tiles_x;
-        const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-        const int bimg = m_tile / (p.tiles_x * p.tiles_y);
+        const MTile mt = pair_m_tile(p, tile / n_tiles, (int)rank);
+        const int tx = mt.tx, ty = mt.ty, bimg = mt.bimg;
         const int ox = tx * p.tile_w + qx;
         const int oy = ty * p.tile_h + qy;
         const int ab = lt & 1;
@@ -754,10 +837,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DEEP ? 320 : 192, 1)
       int lt = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
         const int nt = tile % n_tiles;
-        const int m_tile = 2 * (tile / n_tiles) + (int)rank;
-        const int tx = m_tile % p.tiles_x;
-        const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-        const int bimg = m_tile / (p.tiles_x * p.tiles_y);
+        const MTile mt = pair_m_tile(p, tile / n_tiles, (int)rank);
+        const int tx = mt.tx, ty = mt.ty, bimg = mt.bimg;
         const int px = tx * p.tile_w + m % p.tile_w;
         const int py = ty * p.tile_h + m / p.tile_w;
         const bool row_ok = (px < p.out_w) && (py < p.out_h) && (bimg < p.batch);
@@ -854,7 +935,7 @@ __global__ void igemm_check_kernel(HvrIGemm g, long long rows) {
     const int ax = x + g.tap_dx[t], ay = y + g.tap_dy[t];
     if (ax < 0 || ax >= g.a_w || ay < 0 || ay >= g.a_h) continue;
     const long long ao = b * g.a_stride_b + ay * g.a_stride_h + ax * g.a_stride_w;
-    const long long bo = (long long)n * g.ldb + (long long)t * g.a_c;
+    const long long bo = (long long)b * g.b_stride_batch + (long long)n * g.ldb + (long long)t * g.a_c;
     for (int c = 0; c < g.a_c; ++c) {
       float a = __bfloat162float(ah[ao + c]);
       float w = __bfloat162float(bh[bo + c]);
@@ -959,11 +1040,14 @@ int validate(const HvrIGemm* g) {
   if ((g->outT_hi == nullptr) != (g->outT_lo == nullptr)) return HVR_ERR_ARG;
   if ((g->res_hi == nullptr) != (g->res_lo == nullptr)) return HVR_ERR_ARG;
   if (!g->out_hi && !g->out_f32 && !g->outT_hi) return HVR_ERR_ARG;
+  if (g->b_stride_batch < 0 || (g->b_stride_batch % 8) != 0) return HVR_ERR_ARG;
+  if (g->b_stride_batch && (g->bias || g->outT_hi)) return HVR_ERR_ARG;   // per-image B: plain products only
   return HVR_OK;
 }
 
 int g_force_bn = 0;   // test hook (hvr_debug_force_bn): 0 = heuristic
 int g_deep_mode = 0;  // test hook: 0 = heuristic, 1 = deep epilogue wherever it applies, 2 = never
+int g_pf_mode = 0;    // test hook: 0 = heuristic, 1..14 = L2 prefetch distance in K steps, 15 = off
 bool g_tma_epilogue = true;   // test hook: bit 10 of hvr_debug_force_bn's argument selects the per-row epilogue
 
 template <int BN>
@@ -973,14 +1057,15 @@ int launch(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
     HVR_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
     attr_set = true;
   }
+  // B as a 3-D tensor (k, n, image): one shared matrix (third extent 1) or one per image
   const uint64_t ktot = (uint64_t)g->ntaps * g->a_c;
-  const uint64_t bdims[2] = {ktot, (uint64_t)g->n};
-  const uint64_t bstr[1] = {(uint64_t)g->ldb * 2};
-  const uint32_t bbox[2] = {BK, BN};
-  int rc = make_map(&kp.tmB_hi, g->b_hi, 2, bdims, bstr, bbox);
+  const uint64_t bdims[3] = {ktot, (uint64_t)g->n, (uint64_t)(g->b_stride_batch ? g->batch : 1)};
+  const uint64_t bstr[2] = {(uint64_t)g->ldb * 2, (uint64_t)(g->b_stride_batch ? g->b_stride_batch : g->ldb) * 2};
+  const uint32_t bbox[3] = {BK, BN, 1};
+  int rc = make_map(&kp.tmB_hi, g->b_hi, 3, bdims, bstr, bbox);
   if (rc) return rc;
   if (g->passes >= 3) {
-    rc = make_map(&kp.tmB_lo, g->b_lo, 2, bdims, bstr, bbox);
+    rc = make_map(&kp.tmB_lo, g->b_lo, 3, bdims, bstr, bbox);
     if (rc) return rc;
   }
   kp.n_tiles = hvr_cdiv(g->n, BN);
@@ -1015,16 +1100,17 @@ int launch2(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
     attr_set = true;
   }
   const uint64_t ktot = (uint64_t)g->ntaps * g->a_c;
-  const uint64_t bdims[2] = {ktot, (uint64_t)g->n};
-  const uint64_t bstr[1] = {(uint64_t)g->ldb * 2};
-  const uint32_t bbox[2] = {BK, BN / 2};
-  int rc = make_map(&kp.tmB_hi, g->b_hi, 2, bdims, bstr, bbox);
+  const uint64_t bdims[3] = {ktot, (uint64_t)g->n, (uint64_t)(g->b_stride_batch ? g->batch : 1)};
+  const uint64_t bstr[2] = {(uint64_t)g->ldb * 2, (uint64_t)(g->b_stride_batch ? g->b_stride_batch : g->ldb) * 2};
+  const uint32_t bbox[3] = {BK, BN / 2, 1};
+  int rc = make_map(&kp.tmB_hi, g->b_hi, 3, bdims, bstr, bbox);
   if (rc) return rc;
-  rc = make_map(&kp.tmB_lo, g->b_lo, 2, bdims, bstr, bbox);
+  rc = make_map(&kp.tmB_lo, g->b_lo, 3, bdims, bstr, bbox);
   if (rc) return rc;
   kp.n_tiles = hvr_cdiv(g->n, BN);
-  const long long m_tiles = (long long)kp.tiles_x * kp.tiles_y * kp.batch;
-  const long long pair_tiles = ((m_tiles + 1) / 2) * kp.n_tiles;
+  const long long tpi = (long long)kp.tiles_x * kp.tiles_y;
+  const long long m_pairs = kp.b_batched ? ((tpi + 1) / 2) * kp.batch : (tpi * kp.batch + 1) / 2;
+  const long long pair_tiles = m_pairs * kp.n_tiles;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
@@ -1049,9 +1135,15 @@ int launch2(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
 
 }  // namespace
 
+extern "C" int hvr_debug_force_bn(int bn);
+
 extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
   int rc = validate(g);
   if (rc) return rc;
+  static std::once_flag env_once;      // HVR_DEBUG_FLAGS=<int>: hvr_debug_force_bn() at first use (experiments)
+  std::call_once(env_once, [] {
+    if (const char* e = getenv("HVR_DEBUG_FLAGS")) hvr_debug_force_bn(atoi(e));
+  });
   KParams kp;
   memset(&kp, 0, sizeof(kp));
   const uint64_t adims[4] = {(uint64_t)g->a_c, (uint64_t)g->a_w, (uint64_t)g->a_h, (uint64_t)g->a_b};
@@ -1078,7 +1170,11 @@ extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
   kp.out_h = g->out_h;
   kp.batch = g->batch;
   kp.n = g->n;
+  kp.b_batched = g->b_stride_batch != 0;
   kp.passes = g->passes >= 3 ? 3 : 1;
+  // L2 prefetch of the A operand: 1x1 layers stream their activations once (from HBM when the tensor
+  // exceeds L2); multi-tap layers re-read 8 of 9 taps from L2 anyway
+  kp.pf = (g_pf_mode > 0 && g_pf_mode < 15) ? g_pf_mode : 0;   // measured in the pipeline: no gain -> off unless forced
   kp.relu = g->relu;
   kp.alpha = g->alpha;
   kp.bias = g->bias;
@@ -1097,7 +1193,8 @@ extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
   const long long m_tiles = (long long)kp.tiles_x * kp.tiles_y * kp.batch;
   int bn = g_force_bn;
   // CTA pairs (256-row tiles, B split across the pair) once there is a full machine of pair tiles
-  const long long pair_tiles = ((m_tiles + 1) / 2) * hvr_cdiv(g->n, 256);
+  const long long tpi = (long long)kp.tiles_x * kp.tiles_y;
+  const long long pair_tiles = (kp.b_batched ? ((tpi + 1) / 2) * kp.batch : (m_tiles + 1) / 2) * hvr_cdiv(g->n, 256);
   const bool pair = g->passes >= 3 && g->n >= 128 && ((bn == 0 && pair_tiles >= 64) || bn == 512 || bn == 640);
   // 128-wide pair tiles when the output is only 128 columns wide (half of a 256-wide tile would be
   // MMA work on zero-filled weight rows)
@@ -1110,10 +1207,10 @@ extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
   // is shorter than a 3-stage pipeline needs anyway).
   const bool deep_ok = pair && !pair128 && out_tma && !g->out_f32 && !g->outT_hi && (!g->res_hi || res_tma);
   const int total_k = g->ntaps * kp.cblocks;
-  // Measured (scripts/epilogue_bench.py, profiles/r01h_epilogue_bench.csv): the deep variant wins for
-  // K <= 512 (trunk / C5 conv3: 1.1-1.55x) and for single-wave problems, whose epilogue cannot hide
-  // behind a next tile (trunk layer3 conv1 / conv2 at 7 frames); with K >= 1024 and several tiles per
-  // CTA pair the third ring stage is worth more than the faster epilogue.
+  // Measured (scripts/epilogue_bench.py, profiles/r01h_epilogue_bench.csv, and in the pipeline with
+  // cold operands): the deep variant wins for K <= 512 (trunk / C5 conv3: 1.1-1.55x) and for
+  // single-wave problems, whose epilogue cannot hide behind a next tile (trunk layer3 conv1 / conv2 at
+  // 7 frames: 4-6 %); with K >= 1024 and several tiles per CTA pair the third ring stage is worth more.
   int sms = 0;
   {
     int dev = 0;
@@ -1172,7 +1269,8 @@ extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
 extern "C" int hvr_debug_force_bn(int bn) {
   g_tma_epilogue = (bn & 1024) == 0;
   g_deep_mode = (bn & 2048) ? 1 : ((bn & 4096) ? 2 : 0);   // bit 11: deep epilogue wherever it applies, bit 12: never
-  bn &= ~(1024 | 2048 | 4096);
+  g_pf_mode = (bn >> 13) & 15;                             // bits 13-16: L2 prefetch distance (15 = off, 0 = heuristic)
+  bn &= ~(1024 | 2048 | 4096 | (15 << 13));
   // 512 = CTA-pair kernel (256-wide tiles), 640 = CTA-pair kernel with 128-wide tiles
   if (bn != 0 && bn != 64 && bn != 128 && bn != 256 && bn != 512 && bn != 640) return HVR_ERR_ARG;
   g_force_bn = bn;

@@ -528,6 +528,10 @@ __global__ void __launch_bounds__(256) det_class_nms_kernel(const float* __restr
   unsigned long long* skey = sm + (size_t)n * nw;              // [npow]
   unsigned long long* removed = skey + npow;                   // [nw]
   const int c = blockIdx.x + 1;
+  // blockIdx.y = problem of a batched call: its own scores / mask / flags
+  scores += (size_t)blockIdx.y * n * n_cls;
+  mask += (size_t)blockIdx.y * n * nw;
+  flags += (size_t)blockIdx.y * (n_cls - 1) * n;
   for (int i = threadIdx.x; i < n * nw; i += blockDim.x) smask[i] = mask[i];
   // composite key: high 32 = ordered score bits, low 32 = ~index  -> descending sort gives
   // score desc, index asc.  Entries with score <= thr get key 0 (sort last, ignored).
@@ -613,6 +617,65 @@ __global__ void __launch_bounds__(256) det_emit_kernel(const int* __restrict__ f
   if (blockIdx.x == 0 && threadIdx.x == 0) *n_dets = min(count, max_per_img);
 }
 
+// Batched variants (G problems of n rois each, e.g. the key frames of G videos): one launch per
+// stage for all problems.  Candidate keys are 64-bit (problem << 32 | ~score bits): ONE ascending
+// stable radix sort orders every problem by (score desc, position asc), the same total order as the
+// per-problem descending float sort.
+__global__ void det_candidates_batched_kernel(const int* __restrict__ flags, const float* __restrict__ scores, int n,
+                                              int n_cls, int G, unsigned long long* __restrict__ keys,
+                                              int* __restrict__ pos) {
+  const int total = (n_cls - 1) * n;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= G * total) return;
+  const int g = p / total, q = p % total;
+  const int c = q / n + 1, i = q % n;
+  const unsigned lo = flags[p] ? ~__float_as_uint(scores[((size_t)g * n + i) * n_cls + c]) : 0xFFFFFFFFu;
+  keys[p] = ((unsigned long long)g << 32) | lo;
+  pos[p] = q;
+}
+
+__global__ void __launch_bounds__(256) det_emit_batched_kernel(const int* __restrict__ flags,
+                                                               const int* __restrict__ fscan,
+                                                               const int* __restrict__ pos_sorted,
+                                                               const float* __restrict__ scores,
+                                                               const float4* __restrict__ boxes, int n, int n_cls,
+                                                               int max_per_img, float* __restrict__ dets,
+                                                               long long* __restrict__ labels,
+                                                               int* __restrict__ n_dets) {
+  const int total = (n_cls - 1) * n;
+  const int g = blockIdx.y;
+  flags += (size_t)g * total;
+  fscan += (size_t)g * total;          // exclusive scan over ALL problems: subtract this problem's base
+  pos_sorted += (size_t)g * total;
+  scores += (size_t)g * n * n_cls;
+  boxes += (size_t)g * n;
+  dets += (size_t)g * max_per_img * 5;
+  labels += (size_t)g * max_per_img;
+  const int base = fscan[0];
+  const int count = fscan[total - 1] + flags[total - 1] - base;
+  if (count <= max_per_img) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+      if (!flags[p]) continue;
+      const int o = fscan[p] - base;
+      const int c = p / n + 1, i = p % n;
+      const float4 b = boxes[i];
+      dets[o * 5 + 0] = b.x; dets[o * 5 + 1] = b.y; dets[o * 5 + 2] = b.z; dets[o * 5 + 3] = b.w;
+      dets[o * 5 + 4] = scores[(size_t)i * n_cls + c];
+      labels[o] = c - 1;
+    }
+  } else {
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < max_per_img; o += gridDim.x * blockDim.x) {
+      const int p = pos_sorted[o];
+      const int c = p / n + 1, i = p % n;
+      const float4 b = boxes[i];
+      dets[o * 5 + 0] = b.x; dets[o * 5 + 1] = b.y; dets[o * 5 + 2] = b.z; dets[o * 5 + 3] = b.w;
+      dets[o * 5 + 4] = scores[(size_t)i * n_cls + c];
+      labels[o] = c - 1;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) n_dets[g] = min(count, max_per_img);
+}
+
 size_t scan_temp_bytes(int n) {
   size_t b = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, b, (const int*)nullptr, (int*)nullptr, n);
@@ -690,6 +753,84 @@ extern "C" int hvr_det_postprocess(const float* rois, const float* cls, int64_t 
   g_hvr_launches.fetch_add(1);
   det_emit_kernel<<<hvr_cdiv(total, 256), 256, 0, st>>>(flags, fscan, keys_out, pos_out, scores, boxes, n, n_cls,
                                                         max_per_img, dets, (long long*)labels, n_dets);
+  HVR_LAUNCHED();
+  return HVR_OK;
+}
+
+extern "C" size_t hvr_det_batched_workspace_bytes(int G, int n, int n_cls) {
+  if (n < 1) n = 1;
+  if (G < 1) G = 1;
+  const size_t nw = (n + 63) / 64;
+  const size_t total = (size_t)G * (n_cls - 1) * n;
+  size_t b = 0;
+  b += align_up((size_t)G * n * n_cls * 4);   // scores
+  b += align_up((size_t)G * n * 16);          // boxes
+  b += align_up((size_t)G * n * nw * 8);      // masks
+  b += 2 * align_up(total * 4);               // flags, scan
+  b += 2 * align_up(total * 8);               // keys in/out
+  b += 2 * align_up(total * 4);               // pos in/out
+  b += align_up(sort64_temp_bytes((int)total));
+  b += align_up(scan_temp_bytes((int)total));
+  return b + 256;
+}
+
+// G problems (consecutive blocks of n rows of rois / cls / reg) through one launch per stage.
+// Per problem bit-identical to hvr_det_postprocess.  dets [G, max_per_img, 5], labels
+// [G, max_per_img], n_dets [G].
+extern "C" int hvr_det_postprocess_batched(const float* rois, const float* cls, int64_t ld_cls, const float* reg,
+                                           int64_t ld_reg, int G, int n, int n_cls, const float* stds4_host,
+                                           float img_h, float img_w, float scale_factor, int rescale,
+                                           float score_thr, float iou_thr, int max_per_img, float* dets,
+                                           int64_t* labels, int* n_dets, void* ws, size_t ws_bytes, void* stream) {
+  if (G < 1 || n < 1 || n_cls < 2 || !dets || !labels || !n_dets || max_per_img < 1 || !stds4_host) return HVR_ERR_ARG;
+  if (!rois || !cls || !reg) return HVR_ERR_ARG;
+  if (n > 2048 || G > 4096) return HVR_ERR_UNSUPPORTED;
+  if (!ws || ws_bytes < hvr_det_batched_workspace_bytes(G, n, n_cls)) return HVR_ERR_WORKSPACE;
+  cudaStream_t st = ST(stream);
+  const int nw = (n + 63) / 64;
+  const int per = (n_cls - 1) * n;
+  const int total = G * per;
+  Carver cv(ws);
+  float* scores = cv.take<float>((size_t)G * n * n_cls);
+  float4* boxes = cv.take<float4>((size_t)G * n);
+  unsigned long long* mask = cv.take<unsigned long long>((size_t)G * n * nw);
+  int* flags = cv.take<int>(total);
+  int* fscan = cv.take<int>(total);
+  unsigned long long* keys_in = cv.take<unsigned long long>(total);
+  unsigned long long* keys_out = cv.take<unsigned long long>(total);
+  int* pos_in = cv.take<int>(total);
+  int* pos_out = cv.take<int>(total);
+  size_t tb = sort64_temp_bytes(total), sb = scan_temp_bytes(total);
+  void* temp = cv.take<uint8_t>(tb);
+  void* stemp = cv.take<uint8_t>(sb);
+  const float max_ratio = fabsf(logf(16.0f / 1000.0f));
+  det_decode_kernel<<<hvr_cdiv((int64_t)G * n, 128), 128, 0, st>>>(rois, cls, ld_cls, reg, ld_reg, G * n, n_cls,
+                                                                  stds4_host[0], stds4_host[1], stds4_host[2],
+                                                                  stds4_host[3], img_h, img_w, scale_factor, rescale,
+                                                                  max_ratio, scores, boxes);
+  HVR_LAUNCHED();
+  nms_mask_kernel<<<dim3(nw, nw, G), 64, 0, st>>>(boxes, nullptr, n, nw, iou_thr, 1, 0, mask);
+  HVR_LAUNCHED();
+  const int npow = 1 << (32 - __builtin_clz(n - 1 > 1 ? n - 1 : 1));
+  const size_t smem = ((size_t)n * nw + npow + nw) * 8;
+  static bool attr = false;
+  if (!attr) {
+    HVR_CUDA(cudaFuncSetAttribute(det_class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr = true;
+  }
+  if (smem > 220 * 1024) return HVR_ERR_UNSUPPORTED;
+  det_class_nms_kernel<<<dim3(n_cls - 1, G), 256, smem, st>>>(scores, n, n_cls, nw, mask, score_thr, flags);
+  HVR_LAUNCHED();
+  det_candidates_batched_kernel<<<hvr_cdiv(total, 256), 256, 0, st>>>(flags, scores, n, n_cls, G, keys_in, pos_in);
+  HVR_LAUNCHED();
+  HVR_CUDA(cub::DeviceScan::ExclusiveSum(stemp, sb, flags, fscan, total, st));
+  g_hvr_launches.fetch_add(1);
+  int gbits = 0;
+  while ((1 << gbits) < G) ++gbits;
+  HVR_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, keys_in, keys_out, pos_in, pos_out, total, 0, 32 + gbits, st));
+  g_hvr_launches.fetch_add(1);
+  det_emit_batched_kernel<<<dim3(hvr_cdiv(per, 256), G), 256, 0, st>>>(flags, fscan, pos_out, scores, boxes, n, n_cls,
+                                                                      max_per_img, dets, (long long*)labels, n_dets);
   HVR_LAUNCHED();
   return HVR_OK;
 }

@@ -295,9 +295,9 @@ def relation(P, idx, X, XT, q_range=None, res=None, relu=True, extra=None, **kw)
 # Batched-over-videos head: V windows of N rows each, laid out [V*Npad, D] (Npad = N rounded up to
 # 64; pad rows are finite garbage that never reaches a result).  Every row-wise GEMM (fc_new_k,
 # Q/K/out projections, cls|reg) runs ONCE over all videos (M = V*Npad fills the machine with
-# 256-row tile pairs); only QK^T, softmax and P.V stay per video.  Per-row arithmetic and the
-# per-video attention operands are those of the single-window functions above, so the results are
-# bit-identical to them.
+# 256-row tile pairs); QK^T and P.V are one batched launch each (ops.bmm: a per-video B matrix), the
+# softmax one launch over all V*Nq rows.  Per-row arithmetic and the per-video attention operands are
+# those of the single-window functions above, so the results are bit-identical to them.
 # ----------------------------------------------------------------------------------------
 def _key_rows(X, V, Npad, s, n):
     D = X.shape[1]
@@ -312,14 +312,12 @@ def relation_batched(P, idx, X, XT, V, N, Npad, q_range=None, res=None, relu=Tru
         Xq, nq = _key_rows(X, V, Npad, q_range[0], q_range[1]), q_range[1]
     Q, _, _ = lin(Xq, P['q%d' % idx], **kw)
     K, _, _ = lin(X, P['k%d' % idx], **kw)
-    O = Split.empty((V * nq, D), X.hi.device)
-    for v in range(V):
-        Qv = Q[v * nq:(v + 1) * nq]
-        Kv = K[v * Npad:v * Npad + N]
-        _, S, _ = ops.linear(Qv, Kv, N, alpha=1.0 / math.sqrt(float(D)), want_split=False, want_f32=True, **kw)
-        Pm = ops.softmax_rows_split(S, N, ld_p=Npad)
-        XTv = Split(XT.hi[:, v * Npad:(v + 1) * Npad], XT.lo[:, v * Npad:(v + 1) * Npad])
-        ops.linear(Pm, XTv, D, out=O[v * nq:(v + 1) * nq], **kw)
+    # the V per-video products Q_v K_v^T and P_v X_v as ONE launch each (hvr_igemm with a per-image B
+    # matrix): S [V*nq, N], softmax over all V*nq rows at once, O [V*nq, D]
+    _, S = ops.bmm(Q, K, V, N, Npad * K.hi.stride(0), alpha=1.0 / math.sqrt(float(D)), want_split=False,
+                   want_f32=True)
+    Pm = ops.softmax_rows_split(S, N, ld_p=Npad)
+    O, _ = ops.bmm(Pm, XT, V, D, Npad)
     out, _, _ = lin(O, P['o%d' % idx], relu=relu, res=res, **kw)
     return out
 

@@ -356,6 +356,18 @@ class BBoxHead(_Packed):
                                             n_cls=self.num_classes))
         return outs[0] if single else outs
 
+    def get_det_bboxes_batched(self, rois, cls_score, bbox_pred, G, img_shape, scale_factor, rescale=False, cfg=None):
+        """get_det_bboxes for the key frames of G videos at once (rows of video g = [g*n, (g+1)*n)):
+        one launch per post-processing stage; per video the same bits as get_det_bboxes.
+        Returns (dets [G,max,5], labels [G,max], n [G])."""
+        if isinstance(scale_factor, (np.ndarray, list, tuple)):
+            scale_factor = float(np.asarray(scale_factor).reshape(-1)[0])
+        nms_cfg = dict(cfg['nms'])
+        assert nms_cfg.pop('type', 'nms') == 'nms'
+        return ops.det_postprocess_batched(rois, cls_score, bbox_pred, G, img_shape[:2], scale_factor, rescale,
+                                           self.target_stds, cfg['score_thr'], nms_cfg['iou_thr'],
+                                           cfg['max_per_img'], n_cls=self.num_classes)
+
 
 @HEADS.register_module
 class SharedFCBBoxHead(BBoxHead):
@@ -512,11 +524,12 @@ class TwoStageDetector(nn.Module):
 
     _runner = None
 
-    def enable_cuda_graphs(self, flag=True):
+    def enable_cuda_graphs(self, flag=True, capture=True):
         """Run the trunk and the window stage through captured CUDA graphs (runtime.GraphRunner):
-        same kernels and results, two graph launches and one device->host read per key frame."""
+        same kernels and results, two graph launches and one device->host read per key frame.
+        capture=False keeps the runner's batched launch sequence but issues it eagerly."""
         from .runtime import GraphRunner
-        self._runner = GraphRunner(self) if flag else None
+        self._runner = GraphRunner(self, capture=capture) if flag else None
         return self
 
     def extract_feat(self, img):

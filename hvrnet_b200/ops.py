@@ -134,7 +134,7 @@ def pick_tile(out_w, out_h):
 
 
 def igemm_desc(a, b, n, *, taps=((0, 0),), a_view=None, out_whb=None, tile=None, alpha=1.0, bias=None, res=None,
-               relu=False, out=None, out_f32=None, outT=None, passes=3):
+               relu=False, out=None, out_f32=None, outT=None, passes=3, b_batch_stride=0):
     """Fill an HvrIGemm.
 
     a      Split; either 2-D [M, K] (plain GEMM) or NHWC 4-D [B, H, W, C]
@@ -178,6 +178,7 @@ def igemm_desc(a, b, n, *, taps=((0, 0),), a_view=None, out_whb=None, tile=None,
     if outT is not None:
         g.outT_hi, g.outT_lo, g.ld_outT = outT.hi.data_ptr(), outT.lo.data_ptr(), outT.hi.stride(0)
     g.passes = passes
+    g.b_stride_batch = b_batch_stride       # elements between the per-image B matrices (0 = one shared B)
     return g
 
 
@@ -224,6 +225,25 @@ def linear(a, w, n, bias=None, relu=False, res=None, alpha=1.0, want_split=True,
     g = igemm_desc(a, w, n, alpha=alpha, bias=bias, res=res, relu=relu, out=out, out_f32=of, outT=oT, passes=passes)
     igemm_run(g, check_kernel)
     return out, of, oT
+
+
+def bmm(a, b, V, n, b_batch_stride, alpha=1.0, want_split=True, want_f32=False, out=None, check_kernel=False):
+    """torch.bmm over V problems in ONE launch: a Split [V*m, K] (problem v = rows [v*m, (v+1)*m)),
+    b Split whose matrix of problem v starts b_batch_stride elements after that of v-1 ([n, K]
+    K-major, row stride b.hi.stride(0)).  y_v = alpha * a_v @ b_v[:n].T.  Returns (Split [V*m, ld]
+    or None, fp32 [V*m, ld4] or None).  Per problem the same arithmetic as linear()."""
+    M, K = a.shape
+    assert M % V == 0
+    m = M // V
+    dev = a.hi.device
+    lda = a.hi.stride(0)
+    if out is None and want_split:
+        out = Split.empty((M, round_up(n, 8)), dev)
+    of = torch.empty((M, round_up(n, 4)), dtype=torch.float32, device=dev) if want_f32 else None
+    g = igemm_desc(a, b, n, a_view=(K, m, 1, V, lda, lda * m, lda * m), out_whb=(m, 1, V), alpha=alpha,
+                   out=out if want_split else None, out_f32=of, b_batch_stride=b_batch_stride)
+    igemm_run(g, check_kernel)
+    return (out if want_split else None), of
 
 
 # ----------------------------------------------------------------------------------------
@@ -319,6 +339,32 @@ def det_postprocess(rois, cls, reg, img_shape, scale_factor=1.0, rescale=False, 
                                 float(img_shape[0]), float(img_shape[1]), float(scale_factor), int(rescale),
                                 float(score_thr), float(iou_thr), int(max_per_img), _p(dets), _p(labels), _p(nd),
                                 _p(ws), wsb, _stream()), 'hvr_det_postprocess')
+    return dets, labels, nd
+
+
+def det_postprocess_batched(rois, cls, reg, G, img_shape, scale_factor=1.0, rescale=False, stds=(0.1, 0.1, 0.2, 0.2),
+                            score_thr=0.001, iou_thr=0.3, max_per_img=300, n_cls=None):
+    """G problems of n rois each in one launch per stage: rois [G*n,5], cls [G*n,>=n_cls], reg [G*n,>=4]
+    (row-strided views allowed; problem g = rows [g*n, (g+1)*n)).  Returns dets [G,max_per_img,5],
+    labels [G,max_per_img] int64, n_dets [G] int32; per problem bit-identical to det_postprocess."""
+    _need_cuda(rois, cls, reg)
+    L = _lib.lib()
+    dev = rois.device
+    assert rois.shape[0] % G == 0
+    n = rois.shape[0] // G
+    n_cls = n_cls or cls.shape[1]
+    rois = rois.contiguous().float()
+    assert cls.stride(1) == 1 and reg.stride(1) == 1
+    wsb = L.hvr_det_batched_workspace_bytes(G, n, n_cls)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    dets = torch.zeros((G, max_per_img, 5), dtype=torch.float32, device=dev)
+    labels = torch.zeros((G, max_per_img), dtype=torch.long, device=dev)
+    nd = torch.zeros(G, dtype=torch.int32, device=dev)
+    stds_c = (ctypes.c_float * 4)(*stds)
+    check(L.hvr_det_postprocess_batched(_p(rois), _p(cls), cls.stride(0), _p(reg), reg.stride(0), G, n, n_cls, stds_c,
+                                        float(img_shape[0]), float(img_shape[1]), float(scale_factor), int(rescale),
+                                        float(score_thr), float(iou_thr), int(max_per_img), _p(dets), _p(labels),
+                                        _p(nd), _p(ws), wsb, _stream()), 'hvr_det_postprocess_batched')
     return dets, labels, nd
 
 

@@ -20,13 +20,17 @@ from . import _lib, ops
 
 
 class _Captured:
-    __slots__ = ('graph', 'inputs', 'outputs', 'launches')
+    __slots__ = ('graph', 'fn', 'inputs', 'outputs', 'launches')
 
 
 class GraphRunner:
 
-    def __init__(self, model):
+    def __init__(self, model, capture=True):
+        """capture=False: the same two closures (static buffers, forked branches, batched head) are
+        re-issued eagerly every step instead of being replayed as graphs - identical launches, so
+        bench.py's roofline leg can bracket each one with CUDA events."""
         self.m = model
+        self.capture = capture
         self._trunk = {}
         self._window = {}
         self.replayed_launches = 0      # kernels launched through graph replays (bench.py gpu_launches)
@@ -50,7 +54,7 @@ class GraphRunner:
         with torch.cuda.stream(side):
             c.inputs.copy_(img, non_blocking=True)
             if trunk:
-                c.graph.replay()
+                self._replay(c)
             ev = torch.cuda.Event()
             ev.record()
         self._staged = (id(img), trunk, ev)
@@ -66,12 +70,23 @@ class GraphRunner:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         c = _Captured()
+        c.fn = fn
+        if not getattr(self, 'capture', True):
+            c.graph, c.outputs, c.launches = None, None, 0
+            return c
         c.graph = torch.cuda.CUDAGraph()
         l0 = _lib.launch_count()
         with torch.cuda.graph(c.graph):
             c.outputs = fn()
         c.launches = _lib.launch_count() - l0
         return c
+
+    @staticmethod
+    def _replay(c):
+        if c.graph is None:
+            c.outputs = c.fn()          # eager re-issue (capture=False): counted by _lib.launch_count()
+        else:
+            c.graph.replay()
 
     # ------------------------------------------------------------------ trunk
     def extract(self, img):
@@ -91,10 +106,10 @@ class GraphRunner:
             self._staged = None
             torch.cuda.current_stream().wait_event(ev)   # frames (and trunk) staged by prefetch()
             if not trunk_done:
-                c.graph.replay()
+                self._replay(c)
         else:
             c.inputs.copy_(img, non_blocking=True)      # H2D (pinned host) or D2D into the static buffer
-            c.graph.replay()
+            self._replay(c)
         self.replayed_launches += c.launches
         s, nchw = c.outputs
         out = nchw.clone()                              # the caller keeps C4 maps in its window deque
@@ -165,34 +180,51 @@ class GraphRunner:
                     rois_p[:, :N] = rois.view(V, N, 5)
                     rows = m.bbox_roi_extractor.roi_layers[0].forward_nhwc_split(c5, rois_p.view(-1, 5))
                     packed = head.packed(dev)
+                    # key-frame rois of every video, batch index 0 as bbox2roi([props_key]) gives them
+                    rois_key = rois.view(V, N, 5)[:, s:s + P].reshape(V * P, 5).clone()
+                    rois_key[:, 0] = 0
+
+                    def post(j, h):
+                        """decode + multiclass NMS of head output j for all V key frames: one launch per
+                        stage (hvr_det_postprocess_batched), on a forked branch"""
+                        st = side[j % 2]
+                        st.wait_stream(main)
+                        forked.add(st)
+                        cls_, reg_ = head._split_out(h)
+                        with torch.cuda.stream(st):
+                            return head.get_det_bboxes_batched(rois_key, cls_, reg_, V, meta['img_shape'], sf,
+                                                               rescale=rescale, cfg=m.test_cfg.rcnn)
                     if head.kind == 'hrnmp':
-                        heads = list(engine.hrnmp_forward_batched(packed, rows, V, N, Npad, s, P))
+                        # the branch output is post-processed under stages 3-4
+                        out1, f4, f4T = engine.hrnmp_stage123_batched(packed, rows, V, N, Npad, s, P)
+                        b1 = post(0, out1)
+                        a4 = engine.relation_batched(packed, 4, f4, f4T, V, N, Npad, q_range=(s, P),
+                                                     res=engine._key_rows(f4, V, Npad, s, P))
+                        _, out2, _ = engine.lin(a4, packed['out2'], want_split=False, want_f32=True)
+                        batched = [b1, post(1, out2)]
+                        keep = [maps, props, counts, c5, rois, rois_p, rows, out1, f4, f4T, a4, out2, rois_key, batched]
                     else:
-                        heads = [engine.selsa_forward_batched(packed, rows, V, N, Npad, s, P)]
-                    keep = [maps, props, counts, c5, rois, rois_p, rows, heads]
+                        out1 = engine.selsa_forward_batched(packed, rows, V, N, Npad, s, P)
+                        batched = [post(0, out1)]
+                        keep = [maps, props, counts, c5, rois, rois_p, rows, out1, rois_key, batched]
+                    for v in range(V):
+                        per_video.append([(d[v], l[v], k[v:v + 1]) for d, l, k in batched])
                 else:
                     rows = m.bbox_roi_extractor.roi_layers[0].forward_nhwc_split(c5, rois)
                     keep = [maps, props, counts, c5, rois, rows]
-                for v in range(V):
-                    o = v * T * P
-                    if V > 1:
-                        cls = [head._split_out(h[v * P:(v + 1) * P])[0] for h in heads]
-                        reg = [head._split_out(h[v * P:(v + 1) * P])[1] for h in heads]
-                    else:
-                        cls, reg = m._head(rows[o:o + T * P], [dict(start=s, length=P)], None)
-                    rois_key = rois[o + s:o + s + P].clone()
+                    cls, reg = m._head(rows[0:T * P], [dict(start=s, length=P)], None)
+                    rois_key = rois[s:s + P].clone()
                     rois_key[:, 0] = 0
                     # the head outputs are post-processed on parallel branches (tiny, latency-bound kernels)
-                    outs, used = [], []
+                    outs = []
                     for j, (c_, r_) in enumerate(zip(cls, reg)):
                         st = side[j % 2]
                         st.wait_stream(main)
-                        used.append(st)
+                        forked.add(st)
                         with torch.cuda.stream(st):
                             outs.append(m.bbox_head.get_det_bboxes(rois_key, c_, r_, meta['img_shape'], sf,
                                                                    rescale=rescale, cfg=m.test_cfg.rcnn))
-                    forked.update(used)                 # joined once, after the last video: the next
-                    keep += [cls, reg, rois_key, outs]  # video's head overlaps this video's post-processing
+                    keep += [cls, reg, rois_key, outs]
                     per_video.append(outs)
                 for st in forked:                       # join only the branches that were forked
                     main.wait_stream(st)
@@ -205,7 +237,7 @@ class GraphRunner:
             c.inputs = win
             self._window[key] = c
         fill(c.inputs)
-        c.graph.replay()
+        self._replay(c)
         self.replayed_launches += c.launches
         host = c.outputs[0].cpu()                       # the one device->host read of the step
         n_out = (host.numel() - V * T) // (V * (1 + 6 * M))

@@ -113,6 +113,10 @@ typedef struct HvrIGemm {
   hvr_bf16* outT_lo;
   int64_t ld_outT;
   int passes;                             /* 3 = hi*hi+hi*lo+lo*hi (default), 1 = hi*hi */
+  /* Batched product (torch.bmm over videos, hrnmp_bbox_head.py:293,342): image b of the A view
+   * multiplies its own matrix Wt + b * b_stride_batch (elements, multiple of 8); 0 = one shared
+   * matrix.  No bias / transposed output in this mode. */
+  int64_t b_stride_batch;
 } HvrIGemm;
 
 /* tcgen05 / TMEM / TMA kernel.  rows = batch*out_h*out_w. */
@@ -200,6 +204,15 @@ int hvr_det_postprocess(const float* rois, const float* cls, int64_t ld_cls, con
                         float img_w, float scale_factor, int rescale, float score_thr,
                         float iou_thr, int max_per_img, float* dets, int64_t* labels, int* n_dets,
                         void* ws, size_t ws_bytes, void* stream);
+/* G problems of n rois each (the key frames of G videos; problem g = rows [g*n, (g+1)*n) of rois /
+ * cls / reg) through ONE launch per stage; per problem bit-identical to hvr_det_postprocess.
+ *   dets [G, max_per_img, 5], labels [G, max_per_img], n_dets [G] */
+size_t hvr_det_batched_workspace_bytes(int G, int n, int n_cls);
+int hvr_det_postprocess_batched(const float* rois, const float* cls, int64_t ld_cls, const float* reg,
+                                int64_t ld_reg, int G, int n, int n_cls, const float* stds4_host,
+                                float img_h, float img_w, float scale_factor, int rescale,
+                                float score_thr, float iou_thr, int max_per_img, float* dets,
+                                int64_t* labels, int* n_dets, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Relation-head row softmax (hrnmp_bbox_head.py:332): P = softmax(S, dim=keys), written

@@ -242,6 +242,51 @@ def test_igemm_deep_epilogue_conv_tile_shapes(cuda, tile):
     assert _rel(ops.nhwc_split_to_nchw(outs[0]).double().cpu(), ref) < 3e-5
 
 
+@pytest.mark.parametrize('V,m,K,n,kind', [
+    (7, 300, 1024, 4500, 'qk'),        # key-row queries: 3 M tiles per video (odd: idle half pair), ragged n
+    (3, 448, 256, 600, 'qk'),          # even tiles per video
+    (5, 300, 4544, 1024, 'pv'),        # P.V: B is a column block of X^T (batch stride = Npad columns)
+    (2, 100, 192, 96, 'qk'),           # small: 1-CTA kernels
+])
+@pytest.mark.parametrize('force', [0, 64, 512])
+def test_igemm_batched_b_matches_per_problem(cuda, V, m, K, n, kind, force):
+    """ops.bmm (one launch, per-image B matrix through the third TMA coordinate; CTA pairs never
+    straddle two images) == V separate ops.linear calls, bit for bit, and both match fp64."""
+    from hvrnet_b200 import _lib, ops
+    from hvrnet_b200.ops import Split
+    g = torch.Generator().manual_seed(V * 100 + m + force)
+    a = ops.split(torch.randn(V * m, K, generator=g).to(cuda))
+    if kind == 'qk':                   # B_v = rows [v*npad, v*npad + n) of a [V*npad, K] matrix
+        npad = ops.round_up(n, 64)
+        b = ops.split((torch.randn(V * npad, K, generator=g) / math.sqrt(K)).to(cuda))
+        stride = npad * b.hi.stride(0)
+        bv = lambda v: Split(b.hi[v * npad:(v + 1) * npad], b.lo[v * npad:(v + 1) * npad])
+    else:                              # B_v = columns [v*K, (v+1)*K) of a [n, V*K] matrix
+        b = ops.split((torch.randn(n, V * K, generator=g) / math.sqrt(K)).to(cuda))
+        stride = K
+        bv = lambda v: Split(b.hi[:, v * K:(v + 1) * K], b.lo[:, v * K:(v + 1) * K])
+    _lib.lib().hvr_debug_force_bn(force)
+    try:
+        o, of = ops.bmm(a, b, V, n, stride, alpha=0.25, want_split=True, want_f32=True)
+        torch.cuda.synchronize()
+        for v in range(V):
+            av = a[v * m:(v + 1) * m]
+            o1, f1, _ = ops.linear(av, bv(v), n, alpha=0.25, want_split=True, want_f32=True)
+            torch.cuda.synchronize()
+            assert torch.equal(of[v * m:(v + 1) * m, :n], f1[:, :n])
+            assert torch.equal(o.hi[v * m:(v + 1) * m, :n], o1.hi[:, :n])
+            assert torch.equal(o.lo[v * m:(v + 1) * m, :n], o1.lo[:, :n])
+            ref = 0.25 * (ops.merge(Split(av.hi.contiguous(), av.lo.contiguous())).double().cpu()
+                          @ ops.merge(Split(bv(v).hi.contiguous(), bv(v).lo.contiguous())).double().cpu()[:n].t())
+            assert _rel(f1[:, :n].double().cpu(), ref) < 3e-5
+        # the SIMT cross-check kernel evaluates the batched descriptor too
+        _, of2 = ops.bmm(a, b, V, n, stride, alpha=0.25, want_split=False, want_f32=True, check_kernel=True)
+        # (fp32 sequential accumulation over K up to 4544: looser than the tensor-core path itself)
+        assert _rel(of2[:, :n].double().cpu(), of[:, :n].double().cpu()) < 1e-4
+    finally:
+        _lib.lib().hvr_debug_force_bn(0)
+
+
 @pytest.mark.parametrize('tile', [(16, 8), (8, 16), (32, 4), (64, 2), (128, 1)])
 def test_igemm_conv_tile_shapes(cuda, tile):
     """Every pixel-box shape of the M tile (and of the TMA epilogue box) on a 3x3 conv with residual."""
@@ -489,6 +534,35 @@ def test_det_postprocess(cuda, n, scale, rescale, boost):
     assert torch.equal(labels[:k].cpu(), labels_ref[0])
     assert float((dets[:k, :4].cpu() - dets_ref[0][:, :4]).abs().max()) < 1e-3
     assert float((dets[:k, 4].cpu() - dets_ref[0][:, 4]).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize('G,n,rescale', [(7, 300, True), (3, 37, False), (1, 300, True)])
+def test_det_postprocess_batched_bit_identical(cuda, G, n, rescale):
+    """G problems through one launch per stage (64-bit composite sort keys, one scan over all
+    problems) == G calls of the per-problem path, bit for bit; problems alternate between the
+    concatenation branch (<= 300 candidates) and the top-k branch (> 300), and the inputs are
+    strided views of one [G*n, 64] head output as the runtime passes them."""
+    from hvrnet_b200 import ops
+    g = torch.Generator().manual_seed(G * 1000 + n)
+    d = _dets(g, G * n, spread=500.)
+    rois = torch.cat([torch.zeros(G * n, 1), d[:, :4]], 1).to(cuda)
+    out = torch.randn(G * n, 64, generator=g) * 2
+    for p_ in range(G):
+        out[p_ * n:(p_ + 1) * n, 1:31] += 3.0 if p_ % 2 else -14.0    # odd: > 300 candidates, even: a few dozen
+    out[:, 31:35] *= 0.25
+    out = out.to(cuda)
+    cls, reg = out[:, :31], out[:, 31:35]
+    D, L, K = ops.det_postprocess_batched(rois, cls, reg, G, (600, 1000), 1.6, rescale, n_cls=31)
+    branches = set()
+    for p_ in range(G):
+        sl = slice(p_ * n, (p_ + 1) * n)
+        d1, l1, k1 = ops.det_postprocess(rois[sl], cls[sl], reg[sl], (600, 1000), 1.6, rescale, n_cls=31)
+        k = int(k1)
+        assert int(K[p_]) == k
+        assert torch.equal(D[p_, :k], d1[:k]) and torch.equal(L[p_, :k], l1[:k])
+        branches.add(k == 300)       # 300 = max_per_img reached (top-k branch)
+    if G > 1 and n == 300:
+        assert branches == {True, False}
 
 
 def test_softmax_rows(cuda):

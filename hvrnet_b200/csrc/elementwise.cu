@@ -99,17 +99,31 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ xf, const __nv_bfl
 }
 
 // Stem im2col: out[(b,oy,ox), k] with k = (r*7+s)*3 + c for the 7x7/2 pad-3 conv, 192 columns
-// (147 real + zero padding).  One thread per (pixel, 8-column group): 16-byte stores.
-__global__ void im2col_stem_kernel(const float* __restrict__ img, int B, int H, int W, int OH, int OW,
-                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-  const size_t total = (size_t)B * OH * OW * 24;  // 192 / 8 groups
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int g = (int)(i % 24);
-    const size_t pix = i / 24;
-    const int ox = (int)(pix % OW);
-    const int oy = (int)((pix / OW) % OH);
-    const int b = (int)(pix / ((size_t)OW * OH));
+// (147 real + zero padding).  One CTA per 32 x 4 tile of output pixels: the 3 x 13 x 69 input patch
+// is staged in shared memory with coalesced loads (zeros outside the image = conv padding), then
+// each thread emits 8-column groups with 16-byte stores (consecutive threads -> consecutive 16 bytes).
+constexpr int IM_TW = 32, IM_TH = 4;
+constexpr int IM_PH = 2 * IM_TH + 5, IM_PW = 2 * IM_TW + 5, IM_PS = IM_PW + 3;   // patch rows / cols / row pitch
+__global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restrict__ img, int B, int H, int W, int OH,
+                                                          int OW, __nv_bfloat16* __restrict__ hi,
+                                                          __nv_bfloat16* __restrict__ lo) {
+  __shared__ float patch[3 * IM_PH * IM_PS];
+  const int ox0 = blockIdx.x * IM_TW, oy0 = blockIdx.y * IM_TH, b = blockIdx.z;
+  const int ix0 = ox0 * 2 - 3, iy0 = oy0 * 2 - 3;
+  for (int i = threadIdx.x; i < 3 * IM_PH * IM_PW; i += blockDim.x) {
+    const int px = i % IM_PW, py = (i / IM_PW) % IM_PH, c = i / (IM_PW * IM_PH);
+    const int iy = iy0 + py, ix = ix0 + px;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + (((size_t)b * 3 + c) * H + iy) * W + ix);
+    patch[(c * IM_PH + py) * IM_PS + px] = v;
+  }
+  __syncthreads();
+  for (int item = threadIdx.x; item < IM_TW * IM_TH * 24; item += blockDim.x) {
+    const int g = item % 24, pl = item / 24;
+    const int px = pl % IM_TW, py = pl / IM_TW;
+    const int ox = ox0 + px, oy = oy0 + py;
+    if (ox >= OW || oy >= OH) continue;
+    const int base = (2 * py) * IM_PS + 2 * px;
     uint32_t hp[4], lp[4];
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
@@ -120,9 +134,8 @@ __global__ void im2col_stem_kernel(const float* __restrict__ img, int B, int H, 
         float v = 0.f;
         if (k < 147) {
           const int c = k % 3, rs = k / 3;
-          const int s = rs % 7, r = rs / 7;
-          const int iy = oy * 2 - 3 + r, ix = ox * 2 - 3 + s;
-          if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + (((size_t)b * 3 + c) * H + iy) * W + ix);
+          const int sx = rs % 7, r = rs / 7;
+          v = patch[(c * IM_PH + r) * IM_PS + sx + base];
         }
         __nv_bfloat16 h, l;
         split2(v, h, l);
@@ -132,7 +145,7 @@ __global__ void im2col_stem_kernel(const float* __restrict__ img, int B, int H, 
       hp[j / 2] = (uint32_t)hs[0] | ((uint32_t)hs[1] << 16);
       lp[j / 2] = (uint32_t)ls[0] | ((uint32_t)ls[1] << 16);
     }
-    const size_t o = pix * 192 + (size_t)g * 8;
+    const size_t o = (((size_t)b * OH + oy) * OW + ox) * 192 + (size_t)g * 8;
     *reinterpret_cast<uint4*>(hi + o) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
     *reinterpret_cast<uint4*>(lo + o) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
   }
@@ -358,7 +371,8 @@ extern "C" int hvr_im2col_stem(const float* img, int B, int H, int W, hvr_bf16* 
                                int out_w, void* stream) {
   if (!img || !hi || !lo) return HVR_ERR_ARG;
   if (out_h != (H + 6 - 7) / 2 + 1 || out_w != (W + 6 - 7) / 2 + 1) return HVR_ERR_ARG;
-  im2col_stem_kernel<<<ew_grid((size_t)B * out_h * out_w * 24), EW_THREADS, 0, ST(stream)>>>(
+  if (B < 1 || B > 65535) return HVR_ERR_ARG;
+  im2col_stem_kernel<<<dim3(hvr_cdiv(out_w, IM_TW), hvr_cdiv(out_h, IM_TH), B), 256, 0, ST(stream)>>>(
       img, B, H, W, out_h, out_w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
   HVR_LAUNCHED();
   return HVR_OK;

@@ -510,12 +510,19 @@ __device__ __forceinline__ MTile pair_m_tile(const KParams& p, int pair_idx, int
 constexpr int DEEP_NBUF = 3;
 constexpr int DEEP_TILE_BYTES = 32 * 128;            // 32 rows x 64 bf16
 constexpr int DEEP_BUF_BYTES = 2 * DEEP_TILE_BYTES;  // hi | lo
-template <int BN, bool DEEP = false>
+// MODE 0: 3-4 ring stages, per-warp residual + output staging.  MODE 1: deep epilogue (above).
+// MODE 2 (lean): as 0 without the residual staging tiles, for layers that have no residual: 16 KB
+// less shared memory, which leaves room for a small co-resident CTA of another stream (the RPN
+// greedy-NMS branch runs UNDER the C5 convolutions instead of taking their SMs away).
+template <int BN, int MODE = 0>
 struct Cfg2 {
+  static constexpr bool DEEP = MODE == 1;
+  static constexpr bool LEAN = MODE == 2;
   static constexpr int BH_BYTES = (BN / 2) * BK * 2;              // this CTA's half of one B tile
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;  // A hi/lo + B-half hi/lo
   static constexpr int STAGES = DEEP ? 2 : ((BN == 256) ? 3 : 4);
-  static constexpr int EPI_WARP = DEEP ? DEEP_NBUF * DEEP_BUF_BYTES : EPI_WARP_BYTES;   // per lane quarter
+  static constexpr int EPI_WARP = DEEP ? DEEP_NBUF * DEEP_BUF_BYTES
+                                       : (LEAN ? 2 * EPI_TILE_BYTES : EPI_WARP_BYTES);   // per lane quarter
   static constexpr int EPI_BYTES = 4 * EPI_WARP;
   static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = 2 * BN;
@@ -580,10 +587,12 @@ __device__ __forceinline__ void deep_half(const KParams& p, const uint32_t (&acc
   }
 }
 
-template <int BN, bool DEEP>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DEEP ? 320 : 192, 1)
+template <int BN, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 1 ? 320 : 192, 1)
     igemm_tc2_kernel(const __grid_constant__ KParams p) {
-  using C_ = Cfg2<BN, DEEP>;
+  using C_ = Cfg2<BN, MODE>;
+  constexpr bool DEEP = C_::DEEP;
+  constexpr bool LEAN = C_::LEAN;
   constexpr int STAGES = C_::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -848,8 +857,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DEEP ? 320 : 192, 1)
         // TMA epilogue: this warp's 32 rows are the pixel box (bw x bh) at (ox, oy) of image bimg
         const int ox = tx * p.tile_w + (q * 32) % p.tile_w;
         const int oy = ty * p.tile_h + (q * 32) / p.tile_w;
-        const bool t_out = (p.tma_epi & 1) != 0, t_res = (p.tma_epi & 2) != 0;
-        uint8_t* ebuf = epi_smem + (warp - 2) * EPI_WARP_BYTES;
+        const bool t_out = (p.tma_epi & 1) != 0, t_res = !LEAN && (p.tma_epi & 2) != 0;
+        constexpr int OUT_OFF = LEAN ? 0 : 2 * EPI_TILE_BYTES;   // output staging tiles inside the warp's buffer
+        uint8_t* ebuf = epi_smem + (warp - 2) * C_::EPI_WARP;
         uint64_t* rbar = &res_bar[warp - 2];
         if (t_res && lane == 0) {                          // residual of chunk 0: in flight during the main loop
           mbar_expect_tx(rbar, 2 * EPI_TILE_BYTES);
@@ -891,13 +901,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DEEP ? 320 : 192, 1)
             if (lane == 0) bulk_wait_read0();              // the previous chunk's store has drained the tile
             __syncwarp();
           }
-          epilogue_chunk(p, acc, row, nb, row_ok, rr, t_out ? ebuf + 2 * EPI_TILE_BYTES : nullptr, lane);
+          epilogue_chunk(p, acc, row, nb, row_ok, rr, t_out ? ebuf + OUT_OFF : nullptr, lane);
           if (t_out) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              tma_store_4d(&p.tmO_hi, ebuf + 2 * EPI_TILE_BYTES, nb, ox, oy, bimg);
-              tma_store_4d(&p.tmO_lo, ebuf + 3 * EPI_TILE_BYTES, nb, ox, oy, bimg);
+              tma_store_4d(&p.tmO_hi, ebuf + OUT_OFF, nb, ox, oy, bimg);
+              tma_store_4d(&p.tmO_lo, ebuf + OUT_OFF + EPI_TILE_BYTES, nb, ox, oy, bimg);
               bulk_commit();
             }
           }
@@ -1047,6 +1057,7 @@ int validate(const HvrIGemm* g) {
 
 int g_force_bn = 0;   // test hook (hvr_debug_force_bn): 0 = heuristic
 int g_deep_mode = 0;  // test hook: 0 = heuristic, 1 = deep epilogue wherever it applies, 2 = never
+bool g_lean = true;   // test hook (bit 17 of hvr_debug_force_bn's argument): false = never the lean variant
 int g_pf_mode = 0;    // test hook: 0 = heuristic, 1..14 = L2 prefetch distance in K steps, 15 = off
 bool g_tma_epilogue = true;   // test hook: bit 10 of hvr_debug_force_bn's argument selects the per-row epilogue
 
@@ -1091,12 +1102,12 @@ int launch(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
   return HVR_OK;
 }
 
-template <int BN, bool DEEP>
+template <int BN, int MODE>
 int launch2(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    HVR_CUDA(cudaFuncSetAttribute(igemm_tc2_kernel<BN, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg2<BN, DEEP>::SMEM));
+    HVR_CUDA(cudaFuncSetAttribute(igemm_tc2_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg2<BN, MODE>::SMEM));
     attr_set = true;
   }
   const uint64_t ktot = (uint64_t)g->ntaps * g->a_c;
@@ -1120,15 +1131,15 @@ int launch2(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
   const long long clusters = pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(2 * clusters));
-  cfg.blockDim = dim3(Cfg2<BN, DEEP>::THREADS);
-  cfg.dynamicSmemBytes = Cfg2<BN, DEEP>::SMEM;
+  cfg.blockDim = dim3(Cfg2<BN, MODE>::THREADS);
+  cfg.dynamicSmemBytes = Cfg2<BN, MODE>::SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  HVR_CUDA(cudaLaunchKernelEx(&cfg, igemm_tc2_kernel<BN, DEEP>, kp));
+  HVR_CUDA(cudaLaunchKernelEx(&cfg, igemm_tc2_kernel<BN, MODE>, kp));
   HVR_LAUNCHED();
   return HVR_OK;
 }
@@ -1251,8 +1262,9 @@ extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
       kp.tma_epi |= 2;
     }
   }
-  if (pair128) return launch2<128, false>(g, kp, st);
-  if (pair) return deep ? launch2<256, true>(g, kp, st) : launch2<256, false>(g, kp, st);
+  const bool lean = g->res_hi == nullptr && g_lean;       // no residual: the 16 KB leaner variant
+  if (pair128) return lean ? launch2<128, 2>(g, kp, st) : launch2<128, 0>(g, kp, st);
+  if (pair) return deep ? launch2<256, 1>(g, kp, st) : (lean ? launch2<256, 2>(g, kp, st) : launch2<256, 0>(g, kp, st));
   // Tile width: 256 when the problem still fills the machine (halves the A traffic per FLOP),
   // 64 for narrow outputs or when 128-wide tiles would leave most SMs idle.
   if (bn == 0) {
@@ -1270,7 +1282,8 @@ extern "C" int hvr_debug_force_bn(int bn) {
   g_tma_epilogue = (bn & 1024) == 0;
   g_deep_mode = (bn & 2048) ? 1 : ((bn & 4096) ? 2 : 0);   // bit 11: deep epilogue wherever it applies, bit 12: never
   g_pf_mode = (bn >> 13) & 15;                             // bits 13-16: L2 prefetch distance (15 = off, 0 = heuristic)
-  bn &= ~(1024 | 2048 | 4096 | (15 << 13));
+  g_lean = (bn & (1 << 17)) == 0;
+  bn &= ~(1024 | 2048 | 4096 | (15 << 13) | (1 << 17));
   // 512 = CTA-pair kernel (256-wide tiles), 640 = CTA-pair kernel with 128-wide tiles
   if (bn != 0 && bn != 64 && bn != 128 && bn != 256 && bn != 512 && bn != 640) return HVR_ERR_ARG;
   g_force_bn = bn;

@@ -42,6 +42,7 @@ SIGNATURES = {
     'hvr_split_f32': (c_int, [c_vp, c_sz, c_vp, c_vp, c_vp]),
     'hvr_merge_f32': (c_int, [c_vp, c_vp, c_sz, c_vp, c_vp]),
     'hvr_split_f32_2d': (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
+    'hvr_transpose_split': (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_i64, c_vp]),
     'hvr_nchw_to_nhwc_split': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     'hvr_nhwc_split_to_nchw': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     'hvr_nchw_to_nhwc_f32': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),

@@ -151,6 +151,47 @@ __global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restric
   }
 }
 
+// Transpose of a split matrix: in [rows, ld_in] (cols valid) -> out [cols, ld_out] with columns
+// [rows, ld_out) zero-filled.  64 x 64 tiles through shared memory as packed (hi | lo << 16) words,
+// 16-byte loads and stores on both sides.  (X^T operands of the relation head's P.V products.)
+__global__ void __launch_bounds__(256) transpose_split_kernel(const __nv_bfloat16* __restrict__ hi,
+                                                              const __nv_bfloat16* __restrict__ lo, int rows,
+                                                              int cols, long long ld_in,
+                                                              __nv_bfloat16* __restrict__ ohi,
+                                                              __nv_bfloat16* __restrict__ olo, long long ld_out) {
+  __shared__ uint32_t tile[64][65];
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  for (int i = threadIdx.x; i < 512; i += 256) {
+    const int r = i >> 3, cv = i & 7;
+    uint4 h = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
+    if (r0 + r < rows && c0 + cv * 8 < cols) {
+      h = *reinterpret_cast<const uint4*>(hi + (size_t)(r0 + r) * ld_in + c0 + cv * 8);
+      l = *reinterpret_cast<const uint4*>(lo + (size_t)(r0 + r) * ld_in + c0 + cv * 8);
+    }
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      tile[cv * 8 + 2 * j][r] = (hw[j] & 0xFFFFu) | (lw[j] << 16);
+      tile[cv * 8 + 2 * j + 1][r] = (hw[j] >> 16) | (lw[j] & 0xFFFF0000u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512; i += 256) {
+    const int c = i >> 3, rv = i & 7;
+    if (c0 + c >= cols || r0 + rv * 8 >= ld_out) continue;
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = tile[c][rv * 8 + j];
+    uint4 h, l;
+    h.x = (w[0] & 0xFFFFu) | (w[1] << 16); l.x = (w[0] >> 16) | (w[1] & 0xFFFF0000u);
+    h.y = (w[2] & 0xFFFFu) | (w[3] << 16); l.y = (w[2] >> 16) | (w[3] & 0xFFFF0000u);
+    h.z = (w[4] & 0xFFFFu) | (w[5] << 16); l.z = (w[4] >> 16) | (w[5] & 0xFFFF0000u);
+    h.w = (w[6] & 0xFFFFu) | (w[7] << 16); l.w = (w[6] >> 16) | (w[7] & 0xFFFF0000u);
+    *reinterpret_cast<uint4*>(ohi + (size_t)(c0 + c) * ld_out + r0 + rv * 8) = h;
+    *reinterpret_cast<uint4*>(olo + (size_t)(c0 + c) * ld_out + r0 + rv * 8) = l;
+  }
+}
+
 // 3x3 stride-2 pad-1 max-pool on split NHWC, 8 channels per thread.
 __global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int B,
                                int H, int W, int C, __nv_bfloat16* __restrict__ ohi, __nv_bfloat16* __restrict__ olo,
@@ -332,6 +373,19 @@ extern "C" int hvr_split_f32_2d(const float* x, int rows, int cols, int ld_in, h
   if (rows == 0) return HVR_OK;
   split2d_kernel<<<ew_grid((size_t)rows * ld_out, 4), EW_THREADS, 0, ST(stream)>>>(
       x, rows, cols, ld_in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld_out);
+  HVR_LAUNCHED();
+  return HVR_OK;
+}
+extern "C" int hvr_transpose_split(const hvr_bf16* hi, const hvr_bf16* lo, int rows, int cols, int64_t ld_in,
+                                   hvr_bf16* out_hi, hvr_bf16* out_lo, int64_t ld_out, void* stream) {
+  if (!hi || !lo || !out_hi || !out_lo || rows < 1 || cols < 1) return HVR_ERR_ARG;
+  if (cols % 8 != 0 || ld_in % 8 != 0 || ld_out % 8 != 0 || ld_in < cols || ld_out < rows) return HVR_ERR_ARG;
+  if (((uintptr_t)hi | (uintptr_t)lo | (uintptr_t)out_hi | (uintptr_t)out_lo) & 15u) return HVR_ERR_ARG;
+  // the grid covers the pad columns [rows, ld_out) too: they are written as zeros
+  dim3 grid(hvr_cdiv(ld_out, 64), hvr_cdiv(cols, 64));
+  if (grid.y > 65535) return HVR_ERR_UNSUPPORTED;
+  transpose_split_kernel<<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo, rows, cols,
+                                                        ld_in, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_out);
   HVR_LAUNCHED();
   return HVR_OK;
 }

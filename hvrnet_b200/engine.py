@@ -262,8 +262,14 @@ def rpn_forward(P, c4, **kw):
 
 
 def lin(a, lp, relu=False, res=None, want_split=True, want_f32=False, want_T=False, **kw):
-    return ops.linear(a, lp.w, lp.w.shape[0], bias=lp.bias, relu=relu, res=res, want_split=want_split, want_f32=want_f32,
-                      want_T=want_T, **kw)
+    """Linear layer.  want_T: also X^T (Split [n, round_up(M, 64)]) - produced by a separate transpose
+    of the split output (two 16-byte-vectorised passes over 4 B/element) rather than by the GEMM's
+    transposed-store epilogue, which made the fc_new_k launches 2x slower (2-byte scattered stores)."""
+    n = lp.w.shape[0]
+    out, of, _ = ops.linear(a, lp.w, n, bias=lp.bias, relu=relu, res=res, want_split=want_split or want_T,
+                            want_f32=want_f32, **kw)
+    oT = ops.transpose_split(out, n) if want_T else None
+    return (out if want_split else None), of, oT
 
 
 def relation(P, idx, X, XT, q_range=None, res=None, relu=True, extra=None, **kw):

@@ -227,6 +227,16 @@ def linear(a, w, n, bias=None, relu=False, res=None, alpha=1.0, want_split=True,
     return out, of, oT
 
 
+def transpose_split(s, cols=None):
+    """Split [M, ld] (first `cols` columns) -> Split [cols, round_up(M, 64)], pad columns zero."""
+    M = s.shape[0]
+    cols = cols or s.shape[1]
+    out = Split.empty((cols, round_up(M, 64)), s.hi.device)
+    check(_lib.lib().hvr_transpose_split(_p(s.hi), _p(s.lo), M, cols, s.hi.stride(0), _p(out.hi), _p(out.lo),
+                                         out.hi.stride(0), _stream()), 'hvr_transpose_split')
+    return out
+
+
 def bmm(a, b, V, n, b_batch_stride, alpha=1.0, want_split=True, want_f32=False, out=None, check_kernel=False):
     """torch.bmm over V problems in ONE launch: a Split [V*m, K] (problem v = rows [v*m, (v+1)*m)),
     b Split whose matrix of problem v starts b_batch_stride elements after that of v-1 ([n, K]

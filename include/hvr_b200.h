@@ -58,6 +58,11 @@ int hvr_merge_f32(const hvr_bf16* hi, const hvr_bf16* lo, size_t n, float* out, 
  * columns [cols, ld_out) are zero-filled. */
 int hvr_split_f32_2d(const float* x, int rows, int cols, int ld_in, hvr_bf16* hi, hvr_bf16* lo,
                      int ld_out, void* stream);
+/* Transposed copy of a split matrix: in [rows, ld_in] (cols valid, multiple of 8) -> out
+ * [cols, ld_out], columns [rows, ld_out) zero-filled.  The X^T operand of the relation head's
+ * P.V product (hrnmp_bbox_head.py:340-342, V = un-projected rows). */
+int hvr_transpose_split(const hvr_bf16* hi, const hvr_bf16* lo, int rows, int cols, int64_t ld_in,
+                        hvr_bf16* out_hi, hvr_bf16* out_lo, int64_t ld_out, void* stream);
 /* NCHW fp32 (the reference's layout) -> NHWC split, and back. */
 int hvr_nchw_to_nhwc_split(const float* x, int B, int C, int H, int W, hvr_bf16* hi, hvr_bf16* lo,
                            void* stream);

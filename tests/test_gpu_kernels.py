@@ -565,6 +565,23 @@ def test_det_postprocess_batched_bit_identical(cuda, G, n, rescale):
         assert branches == {True, False}
 
 
+@pytest.mark.parametrize('M,D', [(4544, 1024), (300, 1024), (129, 72), (64, 8)])
+def test_transpose_split(cuda, M, D):
+    """X^T operand of the P.V products: exact transposed copy, pad columns [M, round_up(M,64)) zero."""
+    from hvrnet_b200 import ops
+    g = torch.Generator().manual_seed(M + D)
+    s = ops.split(torch.randn(M, D, generator=g).to(cuda))
+    t = ops.transpose_split(s)
+    ld = ops.round_up(M, 64)
+    assert t.shape == (D, ld)
+    assert torch.equal(t.hi[:, :M], s.hi.t()) and torch.equal(t.lo[:, :M], s.lo.t())
+    assert int(t.hi[:, M:].view(torch.int16).abs().sum()) == 0 and int(t.lo[:, M:].view(torch.int16).abs().sum()) == 0
+    # a row-strided input view (the first n columns of a wider matrix)
+    w = ops.split(torch.randn(M, D + 64, generator=g).to(cuda))
+    t2 = ops.transpose_split(w, D)
+    assert torch.equal(t2.hi[:, :M], w.hi[:, :D].t()) and torch.equal(t2.lo[:, :M], w.lo[:, :D].t())
+
+
 def test_softmax_rows(cuda):
     from hvrnet_b200 import ops
     g = torch.Generator().manual_seed(9)

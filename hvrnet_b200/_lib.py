@@ -30,6 +30,9 @@ class HvrIGemm(ctypes.Structure):
         ('outT_hi', c_vp), ('outT_lo', c_vp), ('ld_outT', c_i64),
         ('passes', c_int),
         ('b_stride_batch', c_i64),
+        ('a2_hi', c_vp), ('a2_lo', c_vp),
+        ('a2_c', c_int), ('a2_w', c_int), ('a2_h', c_int), ('a2_b', c_int),
+        ('a2_stride_w', c_i64), ('a2_stride_h', c_i64), ('a2_stride_b', c_i64),
     ]
 
 

@@ -41,11 +41,13 @@ constexpr int EPI_SMEM = 4 * EPI_WARP_BYTES;
 
 struct alignas(64) KParams {
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+  CUtensorMap tmA2_hi, tmA2_lo;                  // second A operand (K segment after the taps), cblocks2 > 0
   CUtensorMap tmO_hi, tmO_lo, tmR_hi, tmR_lo;   // epilogue: split output (TMA store) / residual (TMA load)
   int tma_epi;                                   // bit 0: output through TMA, bit 1: residual through TMA
   int ntaps;
   int tap_dx[9], tap_dy[9];
   int C, cblocks;
+  int cblocks2;                                  // 64-wide K steps of the second A operand (0 = none)
   int tile_w, tile_h, tiles_x, tiles_y;
   int out_w, out_h, batch;
   int n, n_tiles;
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_k = p.ntaps * p.cblocks;
+  const int total_k = p.ntaps * p.cblocks + p.cblocks2;
   const bool three = p.passes >= 3;
   const int n_tiles = p.n_tiles;
   const int num_tiles = p.tiles_x * p.tiles_y * p.batch * n_tiles;
@@ -334,6 +336,22 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
               tma_load_3d(st + 2 * A_BYTES + C_::B_BYTES, &p.tmB_lo, &full_bar[s], tap * p.C + kc, n0,
                           p.b_batched ? bimg : 0);
             }
+          }
+        }
+        // second A operand: one more K segment at the tile's own pixels (1x1), weights columns
+        // [ntaps*C, ntaps*C + C2)
+        for (int cb = 0; cb < p.cblocks2; ++cb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* st = tiles + s * C_::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], stage_tx);
+          const int kc = cb * BK, kb = p.ntaps * p.C + kc;
+          tma_load_4d(st, &p.tmA2_hi, &full_bar[s], kc, x0, y0, bimg);
+          tma_load_3d(st + 2 * A_BYTES, &p.tmB_hi, &full_bar[s], kb, n0, p.b_batched ? bimg : 0);
+          if (three) {
+            tma_load_4d(st + A_BYTES, &p.tmA2_lo, &full_bar[s], kc, x0, y0, bimg);
+            tma_load_3d(st + 2 * A_BYTES + C_::B_BYTES, &p.tmB_lo, &full_bar[s], kb, n0, p.b_batched ? bimg : 0);
           }
         }
       }
@@ -611,7 +629,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 1 ? 320 : 19
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int total_k = p.ntaps * p.cblocks;
+  const int total_k = p.ntaps * p.cblocks + p.cblocks2;
   const int n_tiles = p.n_tiles;
   const int m_pairs = p.b_batched ? ((p.tiles_x * p.tiles_y + 1) >> 1) * p.batch
                                   : (p.tiles_x * p.tiles_y * p.batch + 1) >> 1;
@@ -700,6 +718,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 1 ? 320 : 19
             tma2_load_4d(st + A_BYTES, &p.tmA_lo, &full_bar[s], kc, ax, ay, bimg);
             tma2_load_3d(st + 2 * A_BYTES + C_::BH_BYTES, &p.tmB_lo, &full_bar[s], tap * p.C + kc, n0, bb);
           }
+        }
+        for (int cb = 0; cb < p.cblocks2; ++cb, ++it) {        // second A operand (see igemm_tc_kernel)
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* st = tiles + s * C_::STAGE_BYTES;
+          if (leader) mbar_expect_tx(&full_bar[s], 2u * (uint32_t)C_::STAGE_BYTES);
+          const int kc = cb * BK, kb = p.ntaps * p.C + kc;
+          tma2_load_4d(st, &p.tmA2_hi, &full_bar[s], kc, x0, y0, bimg);
+          tma2_load_3d(st + 2 * A_BYTES, &p.tmB_hi, &full_bar[s], kb, n0, bb);
+          tma2_load_4d(st + A_BYTES, &p.tmA2_lo, &full_bar[s], kc, x0, y0, bimg);
+          tma2_load_3d(st + 2 * A_BYTES + C_::BH_BYTES, &p.tmB_lo, &full_bar[s], kb, n0, bb);
         }
       }
     }
@@ -956,6 +986,21 @@ __global__ void igemm_check_kernel(HvrIGemm g, long long rows) {
       acc = fmaf(a, w, acc);
     }
   }
+  if (g.a2_hi) {
+    const __nv_bfloat16* ah2 = reinterpret_cast<const __nv_bfloat16*>(g.a2_hi);
+    const __nv_bfloat16* al2 = reinterpret_cast<const __nv_bfloat16*>(g.a2_lo);
+    const long long ao = b * g.a2_stride_b + y * g.a2_stride_h + x * g.a2_stride_w;
+    const long long bo = (long long)b * g.b_stride_batch + (long long)n * g.ldb + (long long)g.ntaps * g.a_c;
+    for (int c = 0; c < g.a2_c; ++c) {
+      float a = __bfloat162float(ah2[ao + c]);
+      float w = __bfloat162float(bh[bo + c]);
+      if (g.passes >= 3) {
+        a = __fadd_rn(a, __bfloat162float(al2[ao + c]));
+        w = __fadd_rn(w, __bfloat162float(bl[bo + c]));
+      }
+      acc = fmaf(a, w, acc);
+    }
+  }
   float v = acc * g.alpha;
   if (g.bias) v += g.bias[n];
   if (g.res_hi)
@@ -1050,6 +1095,8 @@ int validate(const HvrIGemm* g) {
   if ((g->outT_hi == nullptr) != (g->outT_lo == nullptr)) return HVR_ERR_ARG;
   if ((g->res_hi == nullptr) != (g->res_lo == nullptr)) return HVR_ERR_ARG;
   if (!g->out_hi && !g->out_f32 && !g->outT_hi) return HVR_ERR_ARG;
+  if ((g->a2_hi == nullptr) != (g->a2_lo == nullptr)) return HVR_ERR_ARG;
+  if (g->a2_hi && (g->a2_c < 8 || g->a2_c % 8 != 0 || g->a_c % 64 != 0 || g->passes < 3)) return HVR_ERR_ARG;
   if (g->b_stride_batch < 0 || (g->b_stride_batch % 8) != 0) return HVR_ERR_ARG;
   if (g->b_stride_batch && (g->bias || g->outT_hi)) return HVR_ERR_ARG;   // per-image B: plain products only
   return HVR_OK;
@@ -1069,7 +1116,7 @@ int launch(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
     attr_set = true;
   }
   // B as a 3-D tensor (k, n, image): one shared matrix (third extent 1) or one per image
-  const uint64_t ktot = (uint64_t)g->ntaps * g->a_c;
+  const uint64_t ktot = (uint64_t)g->ntaps * g->a_c + (uint64_t)(g->a2_hi ? g->a2_c : 0);
   const uint64_t bdims[3] = {ktot, (uint64_t)g->n, (uint64_t)(g->b_stride_batch ? g->batch : 1)};
   const uint64_t bstr[2] = {(uint64_t)g->ldb * 2, (uint64_t)(g->b_stride_batch ? g->b_stride_batch : g->ldb) * 2};
   const uint32_t bbox[3] = {BK, BN, 1};
@@ -1110,7 +1157,7 @@ int launch2(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
                                   Cfg2<BN, MODE>::SMEM));
     attr_set = true;
   }
-  const uint64_t ktot = (uint64_t)g->ntaps * g->a_c;
+  const uint64_t ktot = (uint64_t)g->ntaps * g->a_c + (uint64_t)(g->a2_hi ? g->a2_c : 0);
   const uint64_t bdims[3] = {ktot, (uint64_t)g->n, (uint64_t)(g->b_stride_batch ? g->batch : 1)};
   const uint64_t bstr[2] = {(uint64_t)g->ldb * 2, (uint64_t)(g->b_stride_batch ? g->b_stride_batch : g->ldb) * 2};
   const uint32_t bbox[3] = {BK, BN / 2, 1};
@@ -1166,6 +1213,17 @@ extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
     rc = make_map(&kp.tmA_lo, g->a_lo, 4, adims, astr, abox);
     if (rc) return rc;
   }
+  kp.cblocks2 = 0;
+  if (g->a2_hi) {   // second A operand: the same output pixel grid seen through its own strided view
+    const uint64_t a2dims[4] = {(uint64_t)g->a2_c, (uint64_t)g->a2_w, (uint64_t)g->a2_h, (uint64_t)g->a2_b};
+    const uint64_t a2str[3] = {(uint64_t)g->a2_stride_w * 2, (uint64_t)g->a2_stride_h * 2,
+                               (uint64_t)g->a2_stride_b * 2};
+    rc = make_map(&kp.tmA2_hi, g->a2_hi, 4, a2dims, a2str, abox);
+    if (rc) return rc;
+    rc = make_map(&kp.tmA2_lo, g->a2_lo, 4, a2dims, a2str, abox);
+    if (rc) return rc;
+    kp.cblocks2 = hvr_cdiv(g->a2_c, BK);
+  }
   kp.ntaps = g->ntaps;
   for (int i = 0; i < 9; ++i) {
     kp.tap_dx[i] = g->tap_dx[i];
@@ -1217,7 +1275,7 @@ extern "C" int hvr_igemm(const HvrIGemm* g, void* stream) {
   // where the epilogue sets the pace: residual layers, and short-K layers (the main loop of a tile
   // is shorter than a 3-stage pipeline needs anyway).
   const bool deep_ok = pair && !pair128 && out_tma && !g->out_f32 && !g->outT_hi && (!g->res_hi || res_tma);
-  const int total_k = g->ntaps * kp.cblocks;
+  const int total_k = g->ntaps * kp.cblocks + kp.cblocks2;
   // Measured (scripts/epilogue_bench.py, profiles/r01h_epilogue_bench.csv, and in the pipeline with
   // cold operands): the deep variant wins for K <= 512 (trunk / C5 conv3: 1.1-1.55x) and for
   // single-wave problems, whose epilogue cannot hide behind a next tile (trunk layer3 conv1 / conv2 at

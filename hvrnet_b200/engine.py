@@ -55,11 +55,12 @@ def pack_conv(w, scale, device):
 
 
 class ConvP:
-    """One packed conv(+BN)(+bias) layer."""
-    __slots__ = ('w', 'bias', 'n', 'k', 'cin', 'dilation')
+    """One packed conv(+BN)(+bias) layer.  cin2 > 0: the weights carry a second K segment of cin2
+    columns that multiplies a second input (the block's 1x1 downsample branch, _pack_conv3_down)."""
+    __slots__ = ('w', 'bias', 'n', 'k', 'cin', 'dilation', 'cin2')
 
-    def __init__(self, w, bias, n, k, cin, dilation=1):
-        self.w, self.bias, self.n, self.k, self.cin, self.dilation = w, bias, n, k, cin, dilation
+    def __init__(self, w, bias, n, k, cin, dilation=1, cin2=0):
+        self.w, self.bias, self.n, self.k, self.cin, self.dilation, self.cin2 = w, bias, n, k, cin, dilation, cin2
 
 
 def _pack_conv_bn(sd, conv, bn, device, dilation=1, bias_name=None):
@@ -79,6 +80,24 @@ def _pack_conv_bn(sd, conv, bn, device, dilation=1, bias_name=None):
     return ConvP(pack_conv(w, scale, device), b, n, w.shape[2], w.shape[1], dilation)
 
 
+# bn3(conv3(o)) + bn_d(conv_d(x)) of a block with a downsample branch (resnet.py:243-255) as ONE
+# contraction over K = [conv3 channels | downsample channels] (hvr_igemm's second A operand): the
+# 4x-wide identity tensor is neither written nor read back.  Set False for the two-GEMM evaluation.
+FUSE_DOWNSAMPLE = True
+
+
+def _pack_conv3_down(sd, q, device):
+    w3, wd = sd[q + 'conv3.weight'].double(), sd[q + 'downsample.0.weight'].double()
+    s3, b3 = _bn_fold(sd, q + 'bn3')
+    sdn, bdn = _bn_fold(sd, q + 'downsample.1')
+    n, c3, cd = w3.shape[0], w3.shape[1], wd.shape[1]
+    assert c3 % 64 == 0 and w3.shape[2] == 1 and wd.shape[2] == 1
+    w = torch.cat([(w3 * s3.view(-1, 1, 1, 1)).reshape(n, c3), (wd * sdn.view(-1, 1, 1, 1)).reshape(n, cd)], 1)
+    b = torch.zeros(round_up(n, 64), dtype=torch.float32)
+    b[:n] = (b3 + bdn).float()
+    return ConvP(pack_matrix(w, device), b.to(device), n, 1, c3, 1, cin2=cd)
+
+
 def _pack_res_layer(sd, p, blocks, dilation, device):
     out = []
     for i in range(blocks):
@@ -88,6 +107,8 @@ def _pack_res_layer(sd, p, blocks, dilation, device):
                    conv3=_pack_conv_bn(sd, q + 'conv3', q + 'bn3', device))
         if (q + 'downsample.0.weight') in sd:
             blk['down'] = _pack_conv_bn(sd, q + 'downsample.0', q + 'downsample.1', device)
+            if sd[q + 'conv3.weight'].shape[1] % 64 == 0:
+                blk['conv3d'] = _pack_conv3_down(sd, q, device)
         out.append(blk)
     return out
 
@@ -186,8 +207,11 @@ def _taps(k, dil):
     return tuple(((s - r) * dil, (t - r) * dil) for t in range(k) for s in range(k))   # (dx, dy), r-major
 
 
-def conv(a, cp, stride=1, relu=False, res=None, want_split=True, want_f32=False, passes=3, check_kernel=False):
-    """a: Split NHWC [B,H,W,C].  Returns (Split NHWC or None, fp32 NHWC or None)."""
+def conv(a, cp, stride=1, relu=False, res=None, want_split=True, want_f32=False, passes=3, check_kernel=False,
+         a2=None, a2_stride=1):
+    """a: Split NHWC [B,H,W,C].  Returns (Split NHWC or None, fp32 NHWC or None).
+    a2: second input Split NHWC [B,H2,W2,cp.cin2] sampled at (y*a2_stride, x*a2_stride) of the output
+    pixel (the 1x1 downsample branch folded into the weights, _pack_conv3_down)."""
     B, H, W, C = a.shape
     assert C == cp.cin, (C, cp.cin)
     dev = a.hi.device
@@ -203,8 +227,13 @@ def conv(a, cp, stride=1, relu=False, res=None, want_split=True, want_f32=False,
     out = Split.empty((B, Ho, Wo, n), dev) if want_split else None
     of = torch.empty((B, Ho, Wo, round_up(n, 4)), dtype=torch.float32, device=dev) if want_f32 else None
     rows = B * Ho * Wo
+    a2_view = None
+    if a2 is not None:
+        B2, H2, W2, C2 = a2.shape
+        assert C2 == cp.cin2 and B2 == B and (H2 - 1) // a2_stride + 1 == Ho and (W2 - 1) // a2_stride + 1 == Wo
+        a2_view = (C2, Wo, Ho, B, a2.hi.stride(2) * a2_stride, a2.hi.stride(1) * a2_stride, a2.hi.stride(0))
     g = ops.igemm_desc(a, cp.w, n, taps=_taps(cp.k, cp.dilation), a_view=view, out_whb=(Wo, Ho, B),
-                       bias=cp.bias, relu=relu,
+                       bias=cp.bias, relu=relu, a2=a2, a2_view=a2_view,
                        res=Split(res.hi.view(rows, -1), res.lo.view(rows, -1)) if res is not None else None,
                        out=Split(out.hi.view(rows, n), out.lo.view(rows, n)) if out is not None else None,
                        out_f32=of.view(rows, -1) if of is not None else None, passes=passes)
@@ -216,6 +245,9 @@ def bottleneck(x, blk, stride, **kw):
     """resnet.py:222-257, caffe style: stride on conv1 (and on the downsample)."""
     o, _ = conv(x, blk['conv1'], stride=stride, relu=True, **kw)
     o, _ = conv(o, blk['conv2'], relu=True, **kw)
+    if FUSE_DOWNSAMPLE and 'conv3d' in blk:
+        o, _ = conv(o, blk['conv3d'], relu=True, a2=x, a2_stride=stride, **kw)
+        return o
     idt = x
     if 'down' in blk:
         idt, _ = conv(x, blk['down'], stride=stride, **kw)

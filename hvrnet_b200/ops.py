@@ -134,7 +134,7 @@ def pick_tile(out_w, out_h):
 
 
 def igemm_desc(a, b, n, *, taps=((0, 0),), a_view=None, out_whb=None, tile=None, alpha=1.0, bias=None, res=None,
-               relu=False, out=None, out_f32=None, outT=None, passes=3, b_batch_stride=0):
+               relu=False, out=None, out_f32=None, outT=None, passes=3, b_batch_stride=0, a2=None, a2_view=None):
     """Fill an HvrIGemm.
 
     a      Split; either 2-D [M, K] (plain GEMM) or NHWC 4-D [B, H, W, C]
@@ -179,6 +179,9 @@ def igemm_desc(a, b, n, *, taps=((0, 0),), a_view=None, out_whb=None, tile=None,
         g.outT_hi, g.outT_lo, g.ld_outT = outT.hi.data_ptr(), outT.lo.data_ptr(), outT.hi.stride(0)
     g.passes = passes
     g.b_stride_batch = b_batch_stride       # elements between the per-image B matrices (0 = one shared B)
+    if a2 is not None:                      # second A operand: (C, W, H, B, stride_w, stride_h, stride_b) view
+        g.a2_hi, g.a2_lo = a2.hi.data_ptr(), a2.lo.data_ptr()
+        g.a2_c, g.a2_w, g.a2_h, g.a2_b, g.a2_stride_w, g.a2_stride_h, g.a2_stride_b = a2_view
     return g
 
 
@@ -189,7 +192,7 @@ PROFILE = None
 
 def igemm_flops(g):
     """Algorithmic FLOPs of one descriptor: 2 * rows * n * (ntaps * C)  (FLOP = 2 MAC)."""
-    return 2.0 * g.batch * g.out_h * g.out_w * g.n * g.ntaps * g.a_c
+    return 2.0 * g.batch * g.out_h * g.out_w * g.n * (g.ntaps * g.a_c + (g.a2_c if g.a2_hi else 0))
 
 
 def igemm_run(g, check_kernel=False):
@@ -201,7 +204,8 @@ def igemm_run(g, check_kernel=False):
     e0.record()
     check(fn(ctypes.byref(g), _stream()), 'hvr_igemm')
     e1.record()
-    PROFILE.append((e0, e1, igemm_flops(g), (g.batch * g.out_h * g.out_w, g.n, g.ntaps * g.a_c)))
+    PROFILE.append((e0, e1, igemm_flops(g), (g.batch * g.out_h * g.out_w, g.n,
+                                             g.ntaps * g.a_c + (g.a2_c if g.a2_hi else 0))))
 
 
 def linear(a, w, n, bias=None, relu=False, res=None, alpha=1.0, want_split=True, want_f32=False, want_T=False,

@@ -122,6 +122,15 @@ typedef struct HvrIGemm {
    * multiplies its own matrix Wt + b * b_stride_batch (elements, multiple of 8); 0 = one shared
    * matrix.  No bias / transposed output in this mode. */
   int64_t b_stride_batch;
+  /* Optional second A operand (one more K segment, 1x1 at the output pixel itself):
+   *   D[m, n] += sum_c A2[pixel(m), c] * Wt[n, ntaps*a_c + c]
+   * the residual branch's 1x1 downsample convolution evaluated inside the block's last
+   * convolution (resnet.py:243-255: out = bn3(conv3(o)) + bn_d(conv_d(x))).  a_c must be a
+   * multiple of 64; view and strides as for A. */
+  const hvr_bf16* a2_hi;
+  const hvr_bf16* a2_lo;
+  int a2_c, a2_w, a2_h, a2_b;
+  int64_t a2_stride_w, a2_stride_h, a2_stride_b;
 } HvrIGemm;
 
 /* tcgen05 / TMEM / TMA kernel.  rows = batch*out_h*out_w. */

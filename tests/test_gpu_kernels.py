@@ -287,6 +287,45 @@ def test_igemm_batched_b_matches_per_problem(cuda, V, m, K, n, kind, force):
         _lib.lib().hvr_debug_force_bn(0)
 
 
+@pytest.mark.parametrize('B,H,W,C1,C2,N,stride,force', [
+    (3, 38, 63, 512, 1024, 2048, 1, 0),      # layer4 block 0: conv3 (512) + downsample (1024)
+    (2, 76, 126, 128, 256, 512, 2, 0),       # layer2 block 0: the downsample input is sampled with stride 2
+    (1, 20, 24, 64, 64, 256, 1, 64),         # layer1 block 0 shapes on the 1-CTA kernel
+    (2, 38, 63, 256, 72, 320, 1, 512),       # second operand with a K tail (72 = 64 + 8), ragged N, pair kernel
+])
+def test_igemm_second_a_operand(cuda, B, H, W, C1, C2, N, stride, force):
+    """bn3(conv3(o)) + bn_d(conv_d(x)) as one contraction over K = [C1 | C2] (HvrIGemm.a2_*) ==
+    the two-convolution evaluation in fp64 (resnet.py:243-255), and the SIMT cross-check kernel."""
+    import torch.nn.functional as F
+    from hvrnet_b200 import _lib, engine, ops
+    g = torch.Generator().manual_seed(C1 + C2 + N)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    o = torch.randn(B, C1, Ho, Wo, generator=g)
+    x = torch.randn(B, C2, H, W, generator=g)
+    w3 = torch.randn(N, C1, 1, 1, generator=g) / math.sqrt(C1)
+    wd = torch.randn(N, C2, 1, 1, generator=g) / math.sqrt(C2)
+    bias = torch.randn(N, generator=g)
+    os_, xs = ops.nchw_to_nhwc_split(o.to(cuda)), ops.nchw_to_nhwc_split(x.to(cuda))
+    wcat = torch.cat([w3.reshape(N, C1), wd.reshape(N, C2)], 1).double()
+    b = torch.zeros(ops.round_up(N, 64))
+    b[:N] = bias
+    cp = engine.ConvP(engine.pack_matrix(wcat, cuda), b.to(cuda), N, 1, C1, 1, cin2=C2)
+    _lib.lib().hvr_debug_force_bn(force)
+    try:
+        out, _ = engine.conv(os_, cp, relu=True, a2=xs, a2_stride=stride)
+        chk, _ = engine.conv(os_, cp, relu=True, a2=xs, a2_stride=stride, check_kernel=True)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().hvr_debug_force_bn(0)
+    om, xm = ops.nhwc_split_to_nchw(os_).double().cpu(), ops.nhwc_split_to_nchw(xs).double().cpu()
+    wm = ops.merge(cp.w).double().cpu()[:N]
+    ref = F.conv2d(om, wm[:, :C1].reshape(N, C1, 1, 1)) + \
+        F.conv2d(xm, wm[:, C1:C1 + C2].reshape(N, C2, 1, 1), stride=stride) + bias.double().view(1, -1, 1, 1)
+    ref = ref.clamp_min(0)
+    assert _rel(ops.nhwc_split_to_nchw(out)[:, :N].double().cpu(), ref) < 3e-5
+    assert _rel(ops.nhwc_split_to_nchw(chk)[:, :N].double().cpu(), ref) < 3e-5
+
+
 @pytest.mark.parametrize('tile', [(16, 8), (8, 16), (32, 4), (64, 2), (128, 1)])
 def test_igemm_conv_tile_shapes(cuda, tile):
     """Every pixel-box shape of the M tile (and of the TMA epilogue box) on a 3x3 conv with residual."""

@@ -53,6 +53,7 @@ SIGNATURES = {
     'hvr_igemm': (c_int, [ctypes.POINTER(HvrIGemm), c_vp]),
     'hvr_igemm_check': (c_int, [ctypes.POINTER(HvrIGemm), c_vp]),
     'hvr_debug_force_bn': (c_int, [c_int]),
+    'hvr_debug_roi_variant': (c_int, [c_int]),
     'hvr_im2col_stem': (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp]),
     'hvr_maxpool3x3s2_split': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp]),
     'hvr_roi_align_fwd': (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_int,

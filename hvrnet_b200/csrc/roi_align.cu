@@ -18,6 +18,7 @@
 //            stay coalesced; the [C, ph*pw] tile is transposed through shared memory and
 //            leaves as one contiguous, fully coalesced block.
 #include "common.cuh"
+#include "roi_align_walk.cuh"
 
 namespace {
 
@@ -155,6 +156,78 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const float* __restrict_
   }
 }
 
+// sample_num == 2, NHWC out: the row-walk variant (roi_align_walk.cuh).  One CTA per (RoI, slice of
+// `cgs` 4-channel groups), one thread per (output row p, 4-channel group); cgs = 32 whenever C is a
+// multiple of 128, so a warp is exactly one output row and every reuse decision of the walk is
+// warp-uniform.  Loads per output vector: 16 for RoIs wider than 28 feature pixels (as
+// above), (distinct rows of the bin row) x (distinct columns of the RoI) / pw otherwise.
+struct WalkLoad {
+  const float* base;   // image base + 4-channel group
+  int WC, C;
+  __device__ __forceinline__ float4 operator()(int row, int col) const {
+    return __ldg(reinterpret_cast<const float4*>(base + row * WC + col * C));
+  }
+};
+struct WalkStore {
+  float* out;               // row p of this RoI + 4-channel group, or null
+  __nv_bfloat16 *hi, *lo;   // same position in the split rows, or null
+  int C;
+  __device__ __forceinline__ void operator()(int q, const float4& acc) const {
+    if (out) *reinterpret_cast<float4*>(out + (size_t)q * C) = acc;
+    if (hi) {
+      __nv_bfloat16 h[4], l[4];
+      split2(acc.x, h[0], l[0]); split2(acc.y, h[1], l[1]);
+      split2(acc.z, h[2], l[2]); split2(acc.w, h[3], l[3]);
+      uint2 hv, lv;
+      hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+      hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+      lv.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+      lv.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+      *reinterpret_cast<uint2*>(hi + (size_t)q * C) = hv;
+      *reinterpret_cast<uint2*>(lo + (size_t)q * C) = lv;
+    }
+  }
+};
+
+#ifndef WALK_MAX_REGS
+#define WALK_MAX_REGS 96
+#endif
+constexpr int kWalkMaxAxis = 64;   // 2 * max(ph, pw) samples per axis held in shared memory
+
+__global__ void __maxnreg__(WALK_MAX_REGS) roi_align_walk_kernel(
+    const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
+    float scale, int cgs, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
+    __nv_bfloat16* __restrict__ out_lo, long long ld_split) {
+  __shared__ AxisSample ys[kWalkMaxAxis], xs[kWalkMaxAxis];
+  const int roi = blockIdx.x;
+  const RoiGeom g = roi_geom(rois + (size_t)roi * 5, scale, ph, pw, n_imgs);
+  // same expressions as roi_align_kernel / roi_align_kernel.cu:86-98 (sn = 2)
+  for (int i = threadIdx.x; i < 2 * (ph + pw); i += blockDim.x) {
+    if (i < 2 * ph) {
+      const int iy = i & 1, p = i >> 1;
+      ys[i] = make_axis_sample(g.sh + (float)p * g.bh + ((float)iy + 0.5f) * g.bh / 2.0f, H);
+    } else {
+      const int j = i - 2 * ph;
+      const int ix = j & 1, q = j >> 1;
+      xs[j] = make_axis_sample(g.sw + (float)q * g.bw + ((float)ix + 0.5f) * g.bw / 2.0f, W);
+    }
+  }
+  __syncthreads();
+  const float* fm = feat + (size_t)g.b * H * W * C;
+  const int nbins = ph * pw;
+  for (int i = threadIdx.x; i < ph * cgs; i += blockDim.x) {
+    const int c4 = blockIdx.y * cgs + i % cgs, p = i / cgs;
+    WalkLoad ld{fm + c4 * 4, W * C, C};
+    WalkStore st;
+    st.C = C;
+    st.out = out ? out + ((size_t)roi * nbins + (size_t)p * pw) * C + c4 * 4 : nullptr;
+    const size_t so = (size_t)roi * ld_split + (size_t)p * pw * C + (size_t)c4 * 4;
+    st.hi = out_hi ? out_hi + so : nullptr;
+    st.lo = out_hi ? out_lo + so : nullptr;
+    roi_row_walk(ys + 2 * p, xs, pw, ld, st);
+  }
+}
+
 // Generic path (adaptive sample_num == 0, or very large sampling grids): reference-style, one
 // thread per output element, NHWC or NCHW output.
 __global__ void roi_align_generic_kernel(const float* __restrict__ feat, const float* __restrict__ rois, int n_rois,
@@ -191,7 +264,15 @@ __global__ void roi_align_generic_kernel(const float* __restrict__ feat, const f
   }
 }
 
+int g_roi_variant = 0;   // test hook (hvr_debug_roi_variant): 0 = heuristic, 1 = always the per-bin kernel
+
 }  // namespace
+
+extern "C" int hvr_debug_roi_variant(int v) {
+  if (v != 0 && v != 1) return HVR_ERR_ARG;
+  g_roi_variant = v;
+  return HVR_OK;
+}
 
 extern "C" int hvr_roi_align_fwd(const float* feat, int feat_nhwc, const float* rois, int n_rois, int n_imgs, int C,
                                  int H, int W, int ph, int pw, float spatial_scale, int sample_num, float* out,
@@ -223,7 +304,15 @@ extern "C" int hvr_roi_align_fwd(const float* feat, int feat_nhwc, const float* 
     HVR_LAUNCHED();
     return HVR_OK;
   }
-  if (out_layout == 1) {
+  if (out_layout == 1 && sample_num == 2 && g_roi_variant == 0 && 2 * ph <= kWalkMaxAxis && 2 * pw <= kWalkMaxAxis) {
+    const int cg = C >> 2;
+    const int cgs = cg % 32 == 0 ? 32 : cg;
+    int threads = ((ph * cgs + 31) / 32) * 32;
+    if (threads > 224) threads = 224;
+    roi_align_walk_kernel<<<dim3(n_rois, cg / cgs), threads, 0, st>>>(
+        feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, cgs, out, (__nv_bfloat16*)out_hi,
+        (__nv_bfloat16*)out_lo, ld_split);
+  } else if (out_layout == 1) {
     const size_t smem = (size_t)nsamp * sizeof(Tap);
     static bool attr1 = false;
     if (!attr1) {

@@ -5,19 +5,21 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from hvrnet_b200 import ops  # noqa: E402
+from hvrnet_b200 import _lib, ops  # noqa: E402
 
 dev = torch.device('cuda:0')
 g = torch.Generator().manual_seed(5)
-for T in (1, 15, 64):
+# (frames, RoI side range in pixels): bench.py's distribution at three batch sizes, then small / large RoIs only
+for T, lo, hi in ((1, 16, 396), (15, 16, 396), (105, 16, 396), (105, 16, 112), (105, 224, 396)):
     feat = torch.randn(T, 38, 63, 256, generator=g).to(dev)
     n = T * 300
     x1 = torch.rand(n, generator=g) * 800
     y1 = torch.rand(n, generator=g) * 450
-    wh = torch.rand(n, 2, generator=g) * 380 + 16
+    wh = torch.rand(n, 2, generator=g) * (hi - lo) + lo
     rois = torch.stack([(torch.arange(n) // 300).float(), x1, y1, (x1 + wh[:, 0]).clamp(max=999),
                         (y1 + wh[:, 1]).clamp(max=599)], 1).to(dev)
-    for resident in (False,):
+    for variant in (1, 0):     # 1 = per-bin kernel (16 loads per output vector), 0 = row-walk kernel
+        _lib.lib().hvr_debug_roi_variant(variant)
         fn = lambda: ops.roi_align(feat, rois, feat_nhwc=True, out_nhwc=True, want_split=True, want_f32=False)
         for _ in range(3):
             fn()
@@ -29,4 +31,4 @@ for T in (1, 15, 64):
         b.record()
         torch.cuda.synchronize()
         us = a.elapsed_time(b) / 10 * 1e3
-        print('T=%d resident=%s %.1f us  %.0f GB/s (algorithmic 17.51 MB/frame)' % (T, resident, us, 17510256.0 * T / us / 1e3))
+        print('T=%d side %d-%d px variant=%s %.1f us  %.0f GB/s (algorithmic 17.51 MB/frame)' % (T, lo, hi, 'row-walk' if variant == 0 else 'per-bin', us, 17510256.0 * T / us / 1e3))

@@ -459,6 +459,35 @@ def test_roi_align_bit_exact(cuda):
     assert float((m - ref).abs().max()) <= float(ref.abs().max()) * 2.0 ** -16
 
 
+@pytest.mark.parametrize('C,out_size', [(256, 7), (128, 7), (16, 7), (40, 3)])
+def test_roi_align_row_walk_equals_per_bin_kernel(cuda, C, out_size):
+    """roi_align_walk_kernel (taps reused from registers) against roi_align_kernel<false> (16 loads per
+    output vector) and the oracle: identical bits, fp32 rows and split rows, also when a warp spans
+    several output rows (C not a multiple of 128)."""
+    from hvrnet_b200 import _lib, ops
+    from oracle import cref
+    g = torch.Generator().manual_seed(21 + C)
+    feat = torch.randn(2, 38, 63, C, generator=g)
+    rois = _rois(g, 300, 2)
+    rois[4:40, 3:] = rois[4:40, 1:3] + torch.rand(36, 2, generator=g) * 60      # small RoIs: heavy reuse
+    rois[40, 1:] = torch.tensor([0., 0., 999., 599.])                            # whole frame: no reuse
+    rois[41, 1:] = torch.tensor([-17., 300., 5., 320.])
+    ref = cref.roi_align(feat, rois, out_size=out_size, feat_nhwc=True, out_nhwc=True)
+    f, r = feat.to(cuda), rois.to(cuda)
+    outs = []
+    try:
+        for variant in (0, 1):
+            assert _lib.lib().hvr_debug_roi_variant(variant) == 0
+            o, sp = ops.roi_align(f, r, out_size=out_size, feat_nhwc=True, out_nhwc=True, want_split=True)
+            outs.append((o.cpu(), sp.hi.cpu(), sp.lo.cpu()))
+    finally:
+        _lib.lib().hvr_debug_roi_variant(0)
+    assert torch.equal(outs[0][0].view(torch.int32), ref.view(torch.int32))
+    bits = lambda t: t.view(torch.int16 if t.dtype == torch.bfloat16 else torch.int32)
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(bits(a), bits(b))
+
+
 def test_roi_align_full_size(cuda):
     """BASELINE.json size: 15 frames x 300 proposals on 38x63x256 maps in ONE launch, checked
     bit-exactly against the C oracle on a sample of the RoIs."""

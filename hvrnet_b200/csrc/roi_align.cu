@@ -12,43 +12,23 @@
 // Layout of the work: one CTA per RoI.
 //   phase 1  ph*pw*sn*sn threads compute (tap offsets, weights) of every sample once
 //            -> shared memory (the reference recomputes them for each of the C channels)
-//   phase 2  NHWC out: thread = (bin, 4-channel group): 16 x LDG.128 of contiguous channel
-//            rows, 1 x STG.128 (+ optional split-bf16 copy feeding fc_new_1)
+//   phase 2  NHWC out: thread = (bin, 4-channel group): LDG.128 of contiguous channel rows,
+//            1 x STG.128 (+ optional split-bf16 copy feeding fc_new_1).  sample_num == 2 (the
+//            pipeline) runs roi_align_sn2_kernel: 8-16 loads per output vector (taps shared by
+//            the two y-samples of a bin come from registers), no validity branches, no
+//            per-iteration index arithmetic; other sample counts run roi_align_kernel<false>
+//            with 4*sn*sn loads.
 //            NCHW out (reference layout): thread = (bin, channel), lanes along C so loads
 //            stay coalesced; the [C, ph*pw] tile is transposed through shared memory and
 //            leaves as one contiguous, fully coalesced block.
 #include "common.cuh"
-#include "roi_align_walk.cuh"
+#include "roi_align_bin.cuh"
+
+#ifndef SN2_MIN_CTAS
+#define SN2_MIN_CTAS 4
+#endif
 
 namespace {
-
-struct Tap {
-  int o0, o1, o2, o3;      // element offsets (pixel index * C) of lt, rt, lb, rb
-  float w1, w2, w3, w4;
-};
-
-// roi_align_kernel.cu:16-61 -> offsets and weights instead of values.
-__device__ __forceinline__ Tap make_tap(float y, float x, int H, int W, int C) {
-  Tap t;
-  if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) {
-    t.o0 = t.o1 = t.o2 = t.o3 = -1;
-    t.w1 = t.w2 = t.w3 = t.w4 = 0.f;
-    return t;
-  }
-  if (y <= 0) y = 0;
-  if (x <= 0) x = 0;
-  int yl = (int)y, xl = (int)x, yh, xh;
-  if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else { yh = yl + 1; }
-  if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else { xh = xl + 1; }
-  const float ly = y - (float)yl, lx = x - (float)xl;
-  const float hy = 1.0f - ly, hx = 1.0f - lx;
-  t.o0 = (yl * W + xl) * C;
-  t.o1 = (yl * W + xh) * C;
-  t.o2 = (yh * W + xl) * C;
-  t.o3 = (yh * W + xh) * C;
-  t.w1 = hy * hx; t.w2 = hy * lx; t.w3 = ly * hx; t.w4 = ly * lx;
-  return t;
-}
 
 struct RoiGeom {
   float sw, sh, bw, bh;
@@ -65,6 +45,30 @@ __device__ __forceinline__ RoiGeom roi_geom(const float* __restrict__ r, float s
   g.bh = rh / (float)ph;
   g.bw = rw / (float)pw;
   return g;
+}
+
+struct TapLoad {
+  const char* base;   // image base + 4-channel group
+  __device__ __forceinline__ float4 operator()(uint32_t off) const {
+    return __ldg(reinterpret_cast<const float4*>(base + off));
+  }
+};
+
+__device__ __forceinline__ void store_bin(const float4& acc, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
+                                          __nv_bfloat16* __restrict__ out_lo, size_t o_f32, size_t o_split) {
+  if (out) *reinterpret_cast<float4*>(out + o_f32) = acc;
+  if (out_hi) {
+    __nv_bfloat16 h[4], l[4];
+    split2(acc.x, h[0], l[0]); split2(acc.y, h[1], l[1]);
+    split2(acc.z, h[2], l[2]); split2(acc.w, h[3], l[3]);
+    uint2 hv, lv;
+    hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+    hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+    lv.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+    lv.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+    *reinterpret_cast<uint2*>(out_hi + o_split) = hv;
+    *reinterpret_cast<uint2*>(out_lo + o_split) = lv;
+  }
 }
 
 template <bool NCHW_OUT>
@@ -100,33 +104,16 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const float* __restrict_
       const int c4 = i % cg, bin = i / cg;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       const Tap* tp = taps + bin * ns;
+      const TapLoad ld{reinterpret_cast<const char*>(fm + c4 * 4)};
       for (int s = 0; s < ns; ++s) {
         const Tap t = tp[s];
-        if (t.o0 < 0) continue;  // bilinear_interpolate returned 0: acc + 0 == acc
-        const float4 a = __ldg(reinterpret_cast<const float4*>(fm + t.o0) + c4);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(fm + t.o1) + c4);
-        const float4 c = __ldg(reinterpret_cast<const float4*>(fm + t.o2) + c4);
-        const float4 d = __ldg(reinterpret_cast<const float4*>(fm + t.o3) + c4);
-        acc.x = acc.x + (((t.w1 * a.x + t.w2 * b.x) + t.w3 * c.x) + t.w4 * d.x);
-        acc.y = acc.y + (((t.w1 * a.y + t.w2 * b.y) + t.w3 * c.y) + t.w4 * d.y);
-        acc.z = acc.z + (((t.w1 * a.z + t.w2 * b.z) + t.w3 * c.z) + t.w4 * d.z);
-        acc.w = acc.w + (((t.w1 * a.w + t.w2 * b.w) + t.w3 * c.w) + t.w4 * d.w);
+        if (t.o0 == kTapInvalid) continue;  // bilinear_interpolate returned 0: acc + 0 == acc
+        const float4 v = bilerp4(t, ld(t.o0), ld(t.o1), ld(t.o2), ld(t.o3));
+        acc.x = acc.x + v.x; acc.y = acc.y + v.y; acc.z = acc.z + v.z; acc.w = acc.w + v.w;
       }
       acc.x = acc.x / cnt; acc.y = acc.y / cnt; acc.z = acc.z / cnt; acc.w = acc.w / cnt;
-      if (out) *(reinterpret_cast<float4*>(out + ((size_t)roi * nbins + bin) * C) + c4) = acc;
-      if (out_hi) {
-        __nv_bfloat16 h[4], l[4];
-        split2(acc.x, h[0], l[0]); split2(acc.y, h[1], l[1]);
-        split2(acc.z, h[2], l[2]); split2(acc.w, h[3], l[3]);
-        const size_t o = (size_t)roi * ld_split + (size_t)bin * C + (size_t)c4 * 4;
-        uint2 hv, lv;
-        hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
-        hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
-        lv.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
-        lv.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
-        *reinterpret_cast<uint2*>(out_hi + o) = hv;
-        *reinterpret_cast<uint2*>(out_lo + o) = lv;
-      }
+      store_bin(acc, out, out_hi, out_lo, ((size_t)roi * nbins + bin) * C + (size_t)c4 * 4,
+                (size_t)roi * ld_split + (size_t)bin * C + (size_t)c4 * 4);
     }
   } else {
     // channel chunks of blockDim.x: lanes along C (coalesced 128 B rows), tile transposed in smem
@@ -140,9 +127,9 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const float* __restrict_
           const Tap* tp = taps + bin * ns;
           for (int s = 0; s < ns; ++s) {
             const Tap t = tp[s];
-            if (t.o0 < 0) continue;
-            const float a = __ldg(fm + t.o0 + c), b = __ldg(fm + t.o1 + c);
-            const float cc = __ldg(fm + t.o2 + c), d = __ldg(fm + t.o3 + c);
+            if (t.o0 == kTapInvalid) continue;
+            const float a = __ldg(fm + (t.o0 >> 2) + c), b = __ldg(fm + (t.o1 >> 2) + c);
+            const float cc = __ldg(fm + (t.o2 >> 2) + c), d = __ldg(fm + (t.o3 >> 2) + c);
             acc = acc + (((t.w1 * a + t.w2 * b) + t.w3 * cc) + t.w4 * d);
           }
           tile[threadIdx.x * nbins + bin] = acc / cnt;   // stride nbins (odd for 7x7): conflict-free
@@ -156,75 +143,54 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const float* __restrict_
   }
 }
 
-// sample_num == 2, NHWC out: the row-walk variant (roi_align_walk.cuh).  One CTA per (RoI, slice of
-// `cgs` 4-channel groups), one thread per (output row p, 4-channel group); cgs = 32 whenever C is a
-// multiple of 128, so a warp is exactly one output row and every reuse decision of the walk is
-// warp-uniform.  Loads per output vector: 16 for RoIs wider than 28 feature pixels (as
-// above), (distinct rows of the bin row) x (distinct columns of the RoI) / pw otherwise.
-struct WalkLoad {
-  const float* base;   // image base + 4-channel group
-  int WC, C;
-  __device__ __forceinline__ float4 operator()(int row, int col) const {
-    return __ldg(reinterpret_cast<const float4*>(base + row * WC + col * C));
-  }
-};
-struct WalkStore {
-  float* out;               // row p of this RoI + 4-channel group, or null
-  __nv_bfloat16 *hi, *lo;   // same position in the split rows, or null
-  int C;
-  __device__ __forceinline__ void operator()(int q, const float4& acc) const {
-    if (out) *reinterpret_cast<float4*>(out + (size_t)q * C) = acc;
-    if (hi) {
-      __nv_bfloat16 h[4], l[4];
-      split2(acc.x, h[0], l[0]); split2(acc.y, h[1], l[1]);
-      split2(acc.z, h[2], l[2]); split2(acc.w, h[3], l[3]);
-      uint2 hv, lv;
-      hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
-      hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
-      lv.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
-      lv.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
-      *reinterpret_cast<uint2*>(hi + (size_t)q * C) = hv;
-      *reinterpret_cast<uint2*>(lo + (size_t)q * C) = lv;
-    }
-  }
-};
-
-#ifndef WALK_MAX_REGS
-#define WALK_MAX_REGS 96
-#endif
-constexpr int kWalkMaxAxis = 64;   // 2 * max(ph, pw) samples per axis held in shared memory
-
-__global__ void __maxnreg__(WALK_MAX_REGS) roi_align_walk_kernel(
+// sample_num == 2, NHWC out (the pipeline's variant): roi_align_bin.cuh.  One CTA per RoI, thread =
+// (bin, 4-channel group) with the channel group fixed per thread (blockDim % (C/4) == 0), so the only
+// per-bin address arithmetic is base + byte offset.  Samples outside the map are rare; a RoI that has one
+// takes the per-sample path below (CTA-uniform choice), all others run without validity branches.
+__global__ void __launch_bounds__(256, SN2_MIN_CTAS) roi_align_sn2_kernel(
     const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
-    float scale, int cgs, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
-    __nv_bfloat16* __restrict__ out_lo, long long ld_split) {
-  __shared__ AxisSample ys[kWalkMaxAxis], xs[kWalkMaxAxis];
+    float scale, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+    long long ld_split) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  Tap* taps = reinterpret_cast<Tap*>(smem);   // [nbins][iy][ix]
+  const int nbins = ph * pw;
   const int roi = blockIdx.x;
   const RoiGeom g = roi_geom(rois + (size_t)roi * 5, scale, ph, pw, n_imgs);
-  // same expressions as roi_align_kernel / roi_align_kernel.cu:86-98 (sn = 2)
-  for (int i = threadIdx.x; i < 2 * (ph + pw); i += blockDim.x) {
-    if (i < 2 * ph) {
-      const int iy = i & 1, p = i >> 1;
-      ys[i] = make_axis_sample(g.sh + (float)p * g.bh + ((float)iy + 0.5f) * g.bh / 2.0f, H);
-    } else {
-      const int j = i - 2 * ph;
-      const int ix = j & 1, q = j >> 1;
-      xs[j] = make_axis_sample(g.sw + (float)q * g.bw + ((float)ix + 0.5f) * g.bw / 2.0f, W);
-    }
+  int invalid = 0;
+  for (int i = threadIdx.x; i < nbins * 4; i += blockDim.x) {
+    const int ix = i & 1, iy = (i >> 1) & 1, bin = i >> 2;
+    const int q = bin % pw, p = bin / pw;
+    const float y = g.sh + (float)p * g.bh + ((float)iy + 0.5f) * g.bh / 2.0f;
+    const float x = g.sw + (float)q * g.bw + ((float)ix + 0.5f) * g.bw / 2.0f;
+    const Tap t = make_tap(y, x, H, W, C);
+    invalid |= (t.o0 == kTapInvalid);
+    taps[i] = t;
   }
-  __syncthreads();
-  const float* fm = feat + (size_t)g.b * H * W * C;
-  const int nbins = ph * pw;
-  for (int i = threadIdx.x; i < ph * cgs; i += blockDim.x) {
-    const int c4 = blockIdx.y * cgs + i % cgs, p = i / cgs;
-    WalkLoad ld{fm + c4 * 4, W * C, C};
-    WalkStore st;
-    st.C = C;
-    st.out = out ? out + ((size_t)roi * nbins + (size_t)p * pw) * C + c4 * 4 : nullptr;
-    const size_t so = (size_t)roi * ld_split + (size_t)p * pw * C + (size_t)c4 * 4;
-    st.hi = out_hi ? out_hi + so : nullptr;
-    st.lo = out_hi ? out_lo + so : nullptr;
-    roi_row_walk(ys + 2 * p, xs, pw, ld, st);
+  const int any_invalid = __syncthreads_or(invalid);
+  const int cg = C >> 2;
+  const int c4 = threadIdx.x % cg;
+  const int bin_step = blockDim.x / cg;
+  const TapLoad ld{reinterpret_cast<const char*>(feat + (size_t)g.b * H * W * C + c4 * 4)};
+  size_t o_f32 = ((size_t)roi * nbins + threadIdx.x / cg) * C + c4 * 4;
+  size_t o_split = (size_t)roi * ld_split + (size_t)(threadIdx.x / cg) * C + c4 * 4;
+  for (int bin = threadIdx.x / cg; bin < nbins; bin += bin_step) {
+    const Tap* tp = taps + bin * 4;
+    float4 acc;
+    if (!any_invalid) {
+      acc = roi_bin_sn2(tp, ld, nullptr);
+    } else {
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < 4; ++s) {
+        const Tap t = tp[s];
+        if (t.o0 == kTapInvalid) continue;  // bilinear_interpolate returned 0: acc + 0 == acc
+        const float4 v = bilerp4(t, ld(t.o0), ld(t.o1), ld(t.o2), ld(t.o3));
+        acc.x = acc.x + v.x; acc.y = acc.y + v.y; acc.z = acc.z + v.z; acc.w = acc.w + v.w;
+      }
+      acc.x = acc.x * 0.25f; acc.y = acc.y * 0.25f; acc.z = acc.z * 0.25f; acc.w = acc.w * 0.25f;
+    }
+    store_bin(acc, out, out_hi, out_lo, o_f32, o_split);
+    o_f32 += (size_t)bin_step * C;
+    o_split += (size_t)bin_step * C;
   }
 }
 
@@ -256,8 +222,9 @@ __global__ void roi_align_generic_kernel(const float* __restrict__ feat, const f
       for (int ix = 0; ix < nw; ++ix) {
         const float x = g.sw + (float)q * g.bw + ((float)ix + 0.5f) * g.bw / (float)nw;
         const Tap t = make_tap(y, x, H, W, C);
-        if (t.o0 < 0) continue;
-        acc = acc + (((t.w1 * fm[t.o0 + c] + t.w2 * fm[t.o1 + c]) + t.w3 * fm[t.o2 + c]) + t.w4 * fm[t.o3 + c]);
+        if (t.o0 == kTapInvalid) continue;
+        acc = acc + (((t.w1 * fm[(t.o0 >> 2) + c] + t.w2 * fm[(t.o1 >> 2) + c]) + t.w3 * fm[(t.o2 >> 2) + c]) +
+                     t.w4 * fm[(t.o3 >> 2) + c]);
       }
     }
     out[i] = acc / (float)(nh * nw);
@@ -284,7 +251,7 @@ extern "C" int hvr_roi_align_fwd(const float* feat, int feat_nhwc, const float* 
   if ((out_hi == nullptr) != (out_lo == nullptr)) return HVR_ERR_ARG;
   if (out_layout != 0 && out_layout != 1) return HVR_ERR_ARG;
   if (out_hi && (out_layout != 1 || ld_split < (int64_t)ph * pw * C || ld_split % 4 != 0)) return HVR_ERR_ARG;
-  if ((size_t)H * W * C >= (1u << 31)) return HVR_ERR_ARG;
+  if ((size_t)H * W * C >= (1u << 30)) return HVR_ERR_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (!feat_nhwc) {
     if (!ws) return HVR_ERR_WORKSPACE;
@@ -304,14 +271,16 @@ extern "C" int hvr_roi_align_fwd(const float* feat, int feat_nhwc, const float* 
     HVR_LAUNCHED();
     return HVR_OK;
   }
-  if (out_layout == 1 && sample_num == 2 && g_roi_variant == 0 && 2 * ph <= kWalkMaxAxis && 2 * pw <= kWalkMaxAxis) {
-    const int cg = C >> 2;
-    const int cgs = cg % 32 == 0 ? 32 : cg;
-    int threads = ((ph * cgs + 31) / 32) * 32;
-    if (threads > 224) threads = 224;
-    roi_align_walk_kernel<<<dim3(n_rois, cg / cgs), threads, 0, st>>>(
-        feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, cgs, out, (__nv_bfloat16*)out_hi,
-        (__nv_bfloat16*)out_lo, ld_split);
+  const int cg = C >> 2;
+  if (out_layout == 1 && sample_num == 2 && g_roi_variant == 0 && 256 % cg == 0) {
+    const size_t smem = (size_t)nsamp * sizeof(Tap);
+    static bool attr2 = false;
+    if (!attr2) {
+      HVR_CUDA(cudaFuncSetAttribute(roi_align_sn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+      attr2 = true;
+    }
+    roi_align_sn2_kernel<<<n_rois, 256, smem, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out,
+                                                    (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_split);
   } else if (out_layout == 1) {
     const size_t smem = (size_t)nsamp * sizeof(Tap);
     static bool attr1 = false;

@@ -166,8 +166,8 @@ int hvr_roi_align_fwd(const float* feat, int feat_nhwc, const float* rois, int n
                       int C, int H, int W, int ph, int pw, float spatial_scale, int sample_num,
                       float* out, int out_layout, hvr_bf16* out_hi, hvr_bf16* out_lo,
                       int64_t ld_split, float* ws, void* stream);
-/* Test hook: 1 = always the per-bin kernel (16 loads per output vector, as the reference), 0 = heuristic
- * (sample_num 2 + out_layout 1 run the row-walk kernel, which reuses taps held in registers). */
+/* Test hook: 1 = always the generic per-bin kernel (16 loads per output vector, as the reference),
+ * 0 = heuristic (sample_num 2 + out_layout 1 run roi_align_sn2_kernel, which reuses taps held in registers). */
 int hvr_debug_roi_variant(int v);
 
 /* ------------------------------------------------------------------------------------

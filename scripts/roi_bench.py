@@ -18,7 +18,7 @@ for T, lo, hi in ((1, 16, 396), (15, 16, 396), (105, 16, 396), (105, 16, 112), (
     wh = torch.rand(n, 2, generator=g) * (hi - lo) + lo
     rois = torch.stack([(torch.arange(n) // 300).float(), x1, y1, (x1 + wh[:, 0]).clamp(max=999),
                         (y1 + wh[:, 1]).clamp(max=599)], 1).to(dev)
-    for variant in (1, 0):     # 1 = per-bin kernel (16 loads per output vector), 0 = row-walk kernel
+    for variant in (1, 0):     # 1 = generic per-bin kernel (16 loads per output vector), 0 = sn2 kernel
         _lib.lib().hvr_debug_roi_variant(variant)
         fn = lambda: ops.roi_align(feat, rois, feat_nhwc=True, out_nhwc=True, want_split=True, want_f32=False)
         for _ in range(3):
@@ -31,4 +31,4 @@ for T, lo, hi in ((1, 16, 396), (15, 16, 396), (105, 16, 396), (105, 16, 112), (
         b.record()
         torch.cuda.synchronize()
         us = a.elapsed_time(b) / 10 * 1e3
-        print('T=%d side %d-%d px variant=%s %.1f us  %.0f GB/s (algorithmic 17.51 MB/frame)' % (T, lo, hi, 'row-walk' if variant == 0 else 'per-bin', us, 17510256.0 * T / us / 1e3))
+        print('T=%d side %d-%d px variant=%s %.1f us  %.0f GB/s (algorithmic 17.51 MB/frame)' % (T, lo, hi, 'sn2' if variant == 0 else 'generic', us, 17510256.0 * T / us / 1e3))

@@ -459,12 +459,12 @@ def test_roi_align_bit_exact(cuda):
     assert float((m - ref).abs().max()) <= float(ref.abs().max()) * 2.0 ** -16
 
 
-@pytest.mark.parametrize('C,out_size', [(256, 7), (128, 7), (16, 7), (40, 3)])
+@pytest.mark.parametrize('C,out_size', [(256, 7), (128, 7), (512, 7), (256, 3), (16, 7), (40, 3)])
 def test_roi_align_sn2_kernel_equals_generic_per_bin_kernel(cuda, C, out_size):
     """roi_align_sn2_kernel (taps shared by the two y-samples of a bin reused from registers; RoIs with
     samples outside the map on its per-sample path) against roi_align_kernel<false> (16 loads per output
-    vector) and the oracle: identical bits, fp32 rows and split rows; C = 40 has no sn2 launch shape and
-    checks the fall-back."""
+    vector) and the oracle: identical bits, fp32 rows and split rows.  C = 512 runs two channel slices, C = 128
+    one vector per lane; C = 16 / 40 have no sn2 launch shape and check the fall-back."""
     from hvrnet_b200 import _lib, ops
     from oracle import cref
     g = torch.Generator().manual_seed(21 + C)

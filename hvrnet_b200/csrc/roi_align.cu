@@ -25,7 +25,7 @@
 #include "roi_align_bin.cuh"
 
 #ifndef SN2_MIN_CTAS
-#define SN2_MIN_CTAS 3
+#define SN2_MIN_CTAS 4
 #endif
 
 namespace {
@@ -143,21 +143,17 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const float* __restrict_
   }
 }
 
-// sample_num == 2, NHWC out (the pipeline's variant): roi_align_bin.cuh.  One CTA per RoI, one warp per
-// bin at a time (ph warps: warp = output row for the 7x7 grid), lane l owns the VPL 4-channel groups
-// l, l + 32, ...: the taps of a bin and its reuse code are read from shared memory once for VPL output
-// vectors, and the only per-bin address arithmetic is base + byte offset.  Samples outside the map are
-// rare; a RoI that has one takes the per-sample path (CTA-uniform choice), all others run without
-// validity branches.
-template <int VPL>
+// sample_num == 2, NHWC out (the pipeline's variant): roi_align_bin.cuh.  One CTA per RoI, thread =
+// (bin, 4-channel group) with the channel group fixed per thread (blockDim % (C/4) == 0), so the only
+// per-bin address arithmetic is base + byte offset.  Samples outside the map are rare; a RoI that has one
+// takes the per-sample path below (CTA-uniform choice), all others run without validity branches.
 __global__ void __launch_bounds__(256, SN2_MIN_CTAS) roi_align_sn2_kernel(
     const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
     float scale, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
     long long ld_split) {
   extern __shared__ __align__(16) uint8_t smem[];
+  Tap* taps = reinterpret_cast<Tap*>(smem);   // [nbins][iy][ix]
   const int nbins = ph * pw;
-  Tap* taps = reinterpret_cast<Tap*>(smem);                          // [nbins][iy][ix]
-  int* codes = reinterpret_cast<int*>(smem + (size_t)nbins * 4 * sizeof(Tap));   // [nbins]
   const int roi = blockIdx.x;
   const RoiGeom g = roi_geom(rois + (size_t)roi * 5, scale, ph, pw, n_imgs);
   int invalid = 0;
@@ -171,39 +167,30 @@ __global__ void __launch_bounds__(256, SN2_MIN_CTAS) roi_align_sn2_kernel(
     taps[i] = t;
   }
   const int any_invalid = __syncthreads_or(invalid);
-  if (!any_invalid) {
-    for (int bin = threadIdx.x; bin < nbins; bin += blockDim.x) codes[bin] = roi_bin_code(taps + bin * 4);
-    __syncthreads();
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const char* fm = reinterpret_cast<const char*>(feat + (size_t)g.b * H * W * C);
-  for (int cbase = 0; cbase < C; cbase += VPL * 128) {     // C > VPL * 128: further channel slices
-    for (int bin = warp; bin < nbins; bin += nwarps) {
-      Tap t[4];
-#pragma unroll
-      for (int s = 0; s < 4; ++s) t[s] = taps[bin * 4 + s];
-      const int code = any_invalid ? 0 : codes[bin];
-#pragma unroll
-      for (int j = 0; j < VPL; ++j) {
-        const int c = cbase + (lane + 32 * j) * 4;
-        const TapLoad ld{fm + (size_t)c * 4};
-        float4 acc;
-        if (!any_invalid) {
-          acc = roi_bin_sn2(code, t, ld, nullptr);
-        } else {
-          acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            if (t[s].o0 == kTapInvalid) continue;  // bilinear_interpolate returned 0: acc + 0 == acc
-            const float4 v = bilerp4(t[s], ld(t[s].o0), ld(t[s].o1), ld(t[s].o2), ld(t[s].o3));
-            acc.x = acc.x + v.x; acc.y = acc.y + v.y; acc.z = acc.z + v.z; acc.w = acc.w + v.w;
-          }
-          acc.x = acc.x * 0.25f; acc.y = acc.y * 0.25f; acc.z = acc.z * 0.25f; acc.w = acc.w * 0.25f;
-        }
-        store_bin(acc, out, out_hi, out_lo, ((size_t)roi * nbins + bin) * C + c,
-                  (size_t)roi * ld_split + (size_t)bin * C + c);
+  const int cg = C >> 2;
+  const int c4 = threadIdx.x % cg;
+  const int bin_step = blockDim.x / cg;
+  const TapLoad ld{reinterpret_cast<const char*>(feat + (size_t)g.b * H * W * C + c4 * 4)};
+  size_t o_f32 = ((size_t)roi * nbins + threadIdx.x / cg) * C + c4 * 4;
+  size_t o_split = (size_t)roi * ld_split + (size_t)(threadIdx.x / cg) * C + c4 * 4;
+  for (int bin = threadIdx.x / cg; bin < nbins; bin += bin_step) {
+    const Tap* tp = taps + bin * 4;
+    float4 acc;
+    if (!any_invalid) {
+      acc = roi_bin_sn2(tp, ld, nullptr);
+    } else {
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < 4; ++s) {
+        const Tap t = tp[s];
+        if (t.o0 == kTapInvalid) continue;  // bilinear_interpolate returned 0: acc + 0 == acc
+        const float4 v = bilerp4(t, ld(t.o0), ld(t.o1), ld(t.o2), ld(t.o3));
+        acc.x = acc.x + v.x; acc.y = acc.y + v.y; acc.z = acc.z + v.z; acc.w = acc.w + v.w;
       }
+      acc.x = acc.x * 0.25f; acc.y = acc.y * 0.25f; acc.z = acc.z * 0.25f; acc.w = acc.w * 0.25f;
     }
+    store_bin(acc, out, out_hi, out_lo, o_f32, o_split);
+    o_f32 += (size_t)bin_step * C;
+    o_split += (size_t)bin_step * C;
   }
 }
 
@@ -284,17 +271,16 @@ extern "C" int hvr_roi_align_fwd(const float* feat, int feat_nhwc, const float* 
     HVR_LAUNCHED();
     return HVR_OK;
   }
-  if (out_layout == 1 && sample_num == 2 && g_roi_variant == 0 && C % 128 == 0 && ph <= 8) {
-    const size_t smem = (size_t)nsamp * sizeof(Tap) + (size_t)ph * pw * sizeof(int);
-    const int threads = 32 * ph;
-    if (C % 256 == 0)
-      roi_align_sn2_kernel<2><<<n_rois, threads, smem, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out,
-                                                             (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
-                                                             ld_split);
-    else
-      roi_align_sn2_kernel<1><<<n_rois, threads, smem, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out,
-                                                             (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
-                                                             ld_split);
+  const int cg = C >> 2;
+  if (out_layout == 1 && sample_num == 2 && g_roi_variant == 0 && 256 % cg == 0) {
+    const size_t smem = (size_t)nsamp * sizeof(Tap);
+    static bool attr2 = false;
+    if (!attr2) {
+      HVR_CUDA(cudaFuncSetAttribute(roi_align_sn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+      attr2 = true;
+    }
+    roi_align_sn2_kernel<<<n_rois, 256, smem, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out,
+                                                    (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_split);
   } else if (out_layout == 1) {
     const size_t smem = (size_t)nsamp * sizeof(Tap);
     static bool attr1 = false;

@@ -1,11 +1,12 @@
 // Per-bin core of the RoIAlign forward kernel for sample_num == 2: one work item = one output bin of
 // one RoI for one group of 4 channels.  The reference (mmdet/ops/roi_align/src/roi_align_kernel.cu:
-// 16-61, :86-112) loads 4 taps for each of the 4 samples of a bin.  When a bin is less than two feature
-// pixels wide or high, its samples fall into the same or into adjacent bilinear cells and share taps;
-// those are taken from registers instead of being loaded again - L1 data-pipe wavefronts, not HBM
-// bytes, are what bounds the kernel (profiles/r01q_roi_align_ncu_summary.txt).  Arithmetic is untouched:
-// the same values enter the same products and sums in the same order, so the result is bit-identical to
-// the straightforward evaluation.
+// 16-61, :86-112) loads 4 taps for each of the 4 samples of a bin.  The two samples of a bin that share
+// their x position (iy = 0, 1) use the same two feature-map columns; when the bin is less than two
+// feature pixels high they also fall into the same cell (all 4 taps shared) or into vertically adjacent
+// cells (the lower taps of the first are the upper taps of the second).  Those taps are taken from
+// registers instead of being loaded again - L1 data-pipe wavefronts, not HBM bytes, are what bounds the
+// kernel.  Arithmetic is untouched: the same values enter the same products and sums in the same order,
+// so the result is bit-identical to the straightforward evaluation.
 //
 // Host- and device-compilable (tests/test_host.py builds it with g++ against the C oracle).
 #pragma once
@@ -61,73 +62,38 @@ HVR_HD hvr_f4 bilerp4(const Tap& t, const hvr_f4& lt, const hvr_f4& rt, const hv
   return v;
 }
 
-// ---- tap reuse inside a bin ------------------------------------------------------------------
-// A tap offset is rowoff(y tap) + coloff(x tap), so the 16 taps of a bin are a grid of (2..4 distinct
-// rows) x (2..4 distinct columns).  Along each axis the second sample relates to the first as
-//   kSame (0): same cell            -> the axis contributes 2 grid lines
-//   kAdj  (1): lo(1) == hi(0)       -> 3 grid lines
-//   kFar  (2): anything else        -> 4 grid lines (no reuse, the reference's 16 loads when both are far)
-// The relation is found by comparing offsets, so every substituted tap has the address of the tap it
-// replaces (clamped border cells included).
-enum { kSame = 0, kAdj = 1, kFar = 2 };
-
-// t[iy*2+ix], all four valid.  Returns ry * 3 + rx.
-HVR_HD int roi_bin_code(const Tap* t) {
-  const int ry = (t[2].o0 == t[0].o0 && t[2].o2 == t[0].o2) ? kSame : (t[2].o0 == t[0].o2 ? kAdj : kFar);
-  const int rx = (t[1].o0 == t[0].o0 && t[1].o1 == t[0].o1) ? kSame : (t[1].o0 == t[0].o1 ? kAdj : kFar);
-  return ry * 3 + rx;
-}
-
-// Grid line of tap `tap` (0 = lo, 1 = hi) of sample `smp` (0, 1) along an axis with relation REL.
-template <int REL>
-HVR_HD constexpr int grid_line(int smp, int tap) {
-  return smp == 0 ? tap : (REL == kSame ? tap : (REL == kAdj ? 1 + tap : 2 + tap));
-}
-
-// One bin, relations known at compile time: every grid point is loaded once, when its first sample needs
-// it.  ((((0 + s00) + s01) + s10) + s11) * 0.25 (roi_align_kernel.cu:100-112: iy outer, ix inner; the
-// division by 4 is exact as a product).  *loads counts the pixel loads issued (host test).
-template <int RY, int RX, class Load>
-HVR_HD hvr_f4 roi_bin_grid(const Tap* t, Load ld, int* loads) {
-  hvr_f4 G[4][4];
-  bool have[4][4] = {{false, false, false, false}, {false, false, false, false},
-                     {false, false, false, false}, {false, false, false, false}};
-  hvr_f4 acc;
-  acc.x = acc.y = acc.z = acc.w = 0.f;
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    const int iy = s >> 1, ix = s & 1;
-    const uint32_t off[4] = {t[s].o0, t[s].o1, t[s].o2, t[s].o3};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int r = grid_line<RY>(iy, k >> 1), c = grid_line<RX>(ix, k & 1);
-      if (!have[r][c]) {
-        G[r][c] = ld(off[k]);
-        have[r][c] = true;
-        if (loads) ++*loads;
-      }
-    }
-    const int r0 = grid_line<RY>(iy, 0), r1 = grid_line<RY>(iy, 1);
-    const int c0 = grid_line<RX>(ix, 0), c1 = grid_line<RX>(ix, 1);
-    const hvr_f4 v = bilerp4(t[s], G[r0][c0], G[r0][c1], G[r1][c0], G[r1][c1]);
-    acc.x = acc.x + v.x; acc.y = acc.y + v.y; acc.z = acc.z + v.z; acc.w = acc.w + v.w;
+// The two samples (iy = 0: t0, iy = 1: t1) of one bin at the same x position; both valid.
+// ld(byte offset) -> the 4 channels of that pixel.  *loads counts the pixel loads issued (host test).
+template <class Load>
+HVR_HD void roi_sample_column(const Tap& t0, const Tap& t1, Load ld, hvr_f4& v0, hvr_f4& v1, int* loads) {
+  const hvr_f4 a = ld(t0.o0), b = ld(t0.o1), c = ld(t0.o2), d = ld(t0.o3);
+  v0 = bilerp4(t0, a, b, c, d);
+  if (t1.o0 == t0.o0 && t1.o2 == t0.o2) {            // same cell
+    v1 = bilerp4(t1, a, b, c, d);
+    if (loads) *loads += 4;
+  } else if (t1.o0 == t0.o2) {                       // the cell below: its upper taps are held
+    const hvr_f4 e = ld(t1.o2), f = ld(t1.o3);
+    v1 = bilerp4(t1, c, d, e, f);
+    if (loads) *loads += 6;
+  } else {
+    const hvr_f4 e = ld(t1.o0), f = ld(t1.o1), g = ld(t1.o2), h = ld(t1.o3);
+    v1 = bilerp4(t1, e, f, g, h);
+    if (loads) *loads += 8;
   }
+}
+
+// One bin whose 4 samples t[iy*2+ix] are all valid: ((((0 + s00) + s01) + s10) + s11) / 4
+// (roi_align_kernel.cu:100-112: iy outer, ix inner; the division by 4 is exact as a product).
+template <class Load>
+HVR_HD hvr_f4 roi_bin_sn2(const Tap* t, Load ld, int* loads) {
+  hvr_f4 v00, v01, v10, v11;
+  roi_sample_column(t[0], t[2], ld, v00, v10, loads);
+  roi_sample_column(t[1], t[3], ld, v01, v11, loads);
+  hvr_f4 acc;
+  acc.x = (((0.f + v00.x) + v01.x) + v10.x) + v11.x;
+  acc.y = (((0.f + v00.y) + v01.y) + v10.y) + v11.y;
+  acc.z = (((0.f + v00.z) + v01.z) + v10.z) + v11.z;
+  acc.w = (((0.f + v00.w) + v01.w) + v10.w) + v11.w;
   acc.x = acc.x * 0.25f; acc.y = acc.y * 0.25f; acc.z = acc.z * 0.25f; acc.w = acc.w * 0.25f;
   return acc;
-}
-
-// code = roi_bin_code(t) (warp-uniform in the kernel: the lanes of a warp work on the same bin).
-template <class Load>
-HVR_HD hvr_f4 roi_bin_sn2(int code, const Tap* t, Load ld, int* loads) {
-  switch (code) {
-    case 0: return roi_bin_grid<kSame, kSame>(t, ld, loads);
-    case 1: return roi_bin_grid<kSame, kAdj>(t, ld, loads);
-    case 2: return roi_bin_grid<kSame, kFar>(t, ld, loads);
-    case 3: return roi_bin_grid<kAdj, kSame>(t, ld, loads);
-    case 4: return roi_bin_grid<kAdj, kAdj>(t, ld, loads);
-    case 5: return roi_bin_grid<kAdj, kFar>(t, ld, loads);
-    case 6: return roi_bin_grid<kFar, kSame>(t, ld, loads);
-    case 7: return roi_bin_grid<kFar, kAdj>(t, ld, loads);
-    default: return roi_bin_grid<kFar, kFar>(t, ld, loads);
-  }
 }

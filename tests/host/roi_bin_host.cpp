@@ -50,7 +50,7 @@ extern "C" long long bin_roi_align(const float* feat, const float* rois, int n_r
         hvr_f4 acc;
         int loads = 0;
         if (!any_invalid) {
-          acc = roi_bin_sn2(roi_bin_code(tp), tp, ld, &loads);
+          acc = roi_bin_sn2(tp, ld, &loads);
         } else {
           acc.x = acc.y = acc.z = acc.w = 0.f;
           for (int s = 0; s < 4; ++s) {

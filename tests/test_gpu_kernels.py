@@ -463,8 +463,8 @@ def test_roi_align_bit_exact(cuda):
 def test_roi_align_sn2_kernel_equals_generic_per_bin_kernel(cuda, C, out_size):
     """roi_align_sn2_kernel (taps shared by the two y-samples of a bin reused from registers; RoIs with
     samples outside the map on its per-sample path) against roi_align_kernel<false> (16 loads per output
-    vector) and the oracle: identical bits, fp32 rows and split rows.  C = 512 runs two channel slices, C = 128
-    one vector per lane; C = 16 / 40 have no sn2 launch shape and check the fall-back."""
+    vector) and the oracle: identical bits, fp32 rows and split rows.  C = 16: a warp spans several bins;
+    C = 40 has no sn2 launch shape (256 % (C/4) != 0) and checks the fall-back."""
     from hvrnet_b200 import _lib, ops
     from oracle import cref
     g = torch.Generator().manual_seed(21 + C)

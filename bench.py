@@ -356,7 +356,7 @@ def main():
         if peaks and 'hbm_gbs' in peaks:
             hbm_peak, src = float(peaks['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs'
         gbs = nbytes / us / 1e3
-        return {'bound': 'hbm', 'kernel': 'roi_align_kernel (one CTA per RoI, taps staged in smem, LDG.128 along C)', 'frames': Tn,
+        return {'bound': 'hbm', 'kernel': 'roi_align_sn2_kernel (one CTA per RoI, taps staged in smem, LDG.128 along C, y-sample taps reused from registers)', 'frames': Tn,
                 'rois': Tn * 300, 'us_per_launch': us, 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                 'frac': gbs / hbm_peak, 'peak_source': src, 'algorithmic_bytes': nbytes}
     roi_rf = roi_align_roofline()

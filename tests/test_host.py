@@ -277,3 +277,20 @@ def test_roi_align_bin_core_load_count(tmp_path):
     rois = np.stack([np.zeros(n), x1, y1, np.minimum(x1 + wh[:, 0], 999), np.minimum(y1 + wh[:, 1], 599)], 1)
     v = per_vec(rois)
     assert 11.0 < v < 13.0, v                                 # bench.py's distribution: ~12 instead of 16
+
+
+def test_bench_measured_peaks_lookup():
+    """bench.py reads the roofline denominators from the driver-written MEASURED_PEAKS.json whatever its exact
+    key layout, and falls back to the profiling guide's figures when the file or the entry is missing."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('hvr_bench', os.path.join(ROOT, 'bench.py'))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    flat = {'hbm_gbs': 6555.8, 'bf16_tflops_burst': 1618, 'bf16_tflops_sustained': 1354, 'sm_clock_mhz': 1237}
+    assert b._measured_peak(flat, ('bf16',), ('sustain',), 200., 5000.) == ('bf16_tflops_sustained', 1354.0)
+    assert b._measured_peak(flat, ('hbm',), ('burst', 'copy'), 1000., 10000.) == ('hbm_gbs', 6555.8)
+    nested = {'hbm': {'copy_gbs': 6555.8}, 'bf16': {'burst_tflops': 1618.0, 'sustained_tflops': 1354.0}}
+    assert b._measured_peak(nested, ('bf16',), ('sustain',), 200., 5000.) == ('bf16.sustained_tflops', 1354.0)
+    assert b._measured_peak(nested, ('hbm',), ('burst', 'copy'), 1000., 10000.) == ('hbm.copy_gbs', 6555.8)
+    assert b._measured_peak(None, ('hbm',), (), 1000., 10000.) == (None, None)
+    assert b._measured_peak({'hbm_gbs': 'n/a'}, ('hbm',), (), 1000., 10000.) == (None, None)

@@ -59,6 +59,8 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='hrnmp', choices=['hrnmp', 'selsa', 'faster_rcnn', 'hrnmp_inter'])
+    ap.add_argument('--support-select', default='ring', choices=['ring', 'similarity'],
+                    help='hrnmp_inter: inter-video supports by ring order (BASELINE.json config 5) or by video-descriptor similarity (SURVEY.md 8f N4)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--videos-per-gpu', type=int, default=0, help='key frames (of different videos) batched per step (default 7: 133 of 148 SMs busy in the trunk)')
     ap.add_argument('--no-streaming', action='store_true', help='skip the extra (labelled) streaming-scheduler figure')
@@ -258,7 +260,8 @@ def main():
             for v, t in enumerate(GraphRunner.per_frame(c4)):
                 dqs[v].append(t)
             if inter:   # configs 4-5: one all-gather of the post-fc_new_4 key rows, ring-order supports
-                return model.forward_feat_intervideo([list(d) for d in dqs], metas, n_support=4, rescale=True)
+                return model.forward_feat_intervideo([list(d) for d in dqs], metas, n_support=4, rescale=True,
+                                                     support_select=args.support_select)
             return model.forward_feat_batch([list(d) for d in dqs], metas, rescale=True)
         dq = dqs[0]
         if from_host:
@@ -441,6 +444,8 @@ def main():
                      'note': 'achieved counts algorithmic fp32-equivalent FLOPs; the kernel issues 3 bf16 MMAs per '
                              'product (tensor-pipe work = 3x), so frac <= 1/3 by construction'},
     }
+    if args.workload == 'hrnmp_inter':
+        line['config']['support_select'] = args.support_select
     line['roi_align'] = roi_rf
     # the other single-GPU configurations of BASELINE.json, measured briefly through the same public
     # call surface (one video per GPU, device-resident frames) so every config has a number on record

@@ -73,6 +73,9 @@ SIGNATURES = {
     'hvr_preprocess_u8': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_f32),
                                   ctypes.POINTER(c_f32), c_vp, c_vp]),
     'hvr_softmax_rows_split': (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    'hvr_video_descriptor_workspace_bytes': (c_sz, [c_int, c_int, c_int]),
+    'hvr_video_descriptor': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
+    'hvr_support_select': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
 }
 
 _lib = None

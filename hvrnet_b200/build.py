@@ -24,6 +24,7 @@ SOURCES = {
     'nms.cu': ['-fmad=false'],
     'igemm_tc.cu': [],
     'preprocess.cu': ['-fmad=false'],
+    'intervideo.cu': ['-fmad=false'],
 }
 
 

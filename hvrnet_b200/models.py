@@ -701,16 +701,22 @@ class HNMBRCNN(_WindowRCNN):
 
 
     def forward_feat_intervideo(self, xs, img_meta, n_support=4, rescale=False, group=None, return_aux=False,
-                                proposals=None):
+                                proposals=None, support_select='ring'):
         """BASELINE.json configs 4-5 (oracle-defined, parity unpinned by the
         reference): V local key frames, one window each; stage 4 of every key frame also attends
         to the post-fc_new_4 key rows of `n_support` other key frames (ring order over all ranks,
         intervideo.support_indices) gathered with ONE all-gather.  Every frame must yield the same
-        number of proposals P (the all-gather is fixed-size); otherwise a ValueError is raised."""
+        number of proposals P (the all-gather is fixed-size); otherwise a ValueError is raised.
+        support_select='similarity' (next row N4): the supports of a key frame are the n_support videos
+        whose descriptor - max over the window's frames of the spatially averaged C5 map, as
+        get_triplet_patches builds it (hnmb_rcnn.py:76-101) - is most similar to its own; the descriptors
+        travel inside the same all-gather."""
         from . import intervideo
+        if support_select not in ('ring', 'similarity'):
+            raise ValueError('support_select must be "ring" or "similarity", got %r' % (support_select,))
         P = self.test_cfg.rpn['max_num']
         head = self.bbox_head
-        per_video, z = [], []
+        per_video, z, desc = [], [], []
         V, T = len(xs), len(xs[0])
         if proposals is None and V > 1 and all(len(x) == T for x in xs):
             # all V windows at once: C5 / RPN / proposals / RoIAlign over the V*T frames, stages 1-3 with
@@ -729,6 +735,8 @@ class HNMBRCNN(_WindowRCNN):
             rois_p = torch.zeros((V, Npad, 5), device=dev)
             rois_p[:, :N] = rois
             rows = self.bbox_roi_extractor.roi_layers[0].forward_nhwc_split(c5, rois_p.view(-1, 5))
+            if support_select == 'similarity':
+                desc.append(ops.video_descriptor(c5, V))
             out1, f4, f4T = engine.hrnmp_stage123_batched(head.packed(dev), rows, V, N, Npad, s, P)
             for v in range(V):
                 f4v = f4[v * Npad:v * Npad + N]
@@ -738,16 +746,19 @@ class HNMBRCNN(_WindowRCNN):
             xs = []
         for vi, x in enumerate(xs):
             c4 = self._window_split(x)
-            rois, cnt, rows, _ = self._rois_and_feats(c4, img_meta, None if proposals is None else proposals[vi])
+            rois, cnt, rows, a = self._rois_and_feats(c4, img_meta, None if proposals is None else proposals[vi])
             if any(c != P for c in cnt):
                 raise ValueError('inter-video exchange needs %d proposals per frame, got %s' % (P, cnt))
+            if support_select == 'similarity':
+                desc.append(ops.video_descriptor(a['c5'], 1))
             s = self.key_dim * P
             packed = head.packed(rows.hi.device)
             out1, f4, f4T = engine.hrnmp_stage123(packed, rows, s, P)
             per_video.append((rois[s:s + P].clone(), out1, f4, f4T, s))
             z.append(f4[s:s + P])
         z_local = ops.Split(torch.cat([t.hi for t in z], 0), torch.cat([t.lo for t in z], 0))
-        supports = intervideo.gather_support(z_local, P, n_support, group)
+        supports = intervideo.gather_support(z_local, P, n_support, group,
+                                             desc_local=torch.cat(desc, 0) if desc else None)
         m = img_meta[0]
         results, aux = [], []
         for (rois_key, out1, f4, f4T, s), sup in zip(per_video, supports):

@@ -393,6 +393,37 @@ def softmax_rows_split(S, cols, ld_p=None):
     return P
 
 
+def video_descriptor(c5_nhwc, n_videos):
+    """c5_nhwc fp32 [n_videos*T, h, w, C] (the shared head's output, frames of a video contiguous) ->
+    [n_videos, C]: max over a video's frames of the per-frame spatial mean (hnmb_rcnn.py:78-81)."""
+    _need_cuda(c5_nhwc)
+    c5_nhwc = c5_nhwc.contiguous()
+    B, H, W, C = c5_nhwc.shape
+    assert n_videos > 0 and B % n_videos == 0
+    T = B // n_videos
+    L = _lib.lib()
+    nb = L.hvr_video_descriptor_workspace_bytes(n_videos, T, C)
+    ws = torch.empty(nb, dtype=torch.uint8, device=c5_nhwc.device)
+    desc = torch.empty((n_videos, C), dtype=torch.float32, device=c5_nhwc.device)
+    check(L.hvr_video_descriptor(_p(c5_nhwc), n_videos, T, H * W, C, _p(desc), _p(ws), nb, _stream()),
+          'hvr_video_descriptor')
+    return desc
+
+
+def support_select(desc, g0, n_local, n_support, want_weights=False):
+    """desc fp32 [G, C] of all videos -> int64 [n_local, n_support]: for the videos g0 .. g0+n_local-1 the
+    n_support other videos with the largest softmax similarity (hnmb_rcnn.py:85-88), ties to the lower
+    index, -1 where fewer than n_support other videos exist.  Optionally the weights [n_local, G]."""
+    _need_cuda(desc)
+    desc = desc.contiguous().float()
+    G, C = desc.shape
+    idx = torch.full((n_local, n_support), -1, dtype=torch.int64, device=desc.device)
+    w = torch.zeros((n_local, G), dtype=torch.float32, device=desc.device) if want_weights else None
+    check(_lib.lib().hvr_support_select(_p(desc), G, C, g0, n_local, n_support, _p(idx), _p(w), _stream()),
+          'hvr_support_select')
+    return (idx, w) if want_weights else idx
+
+
 def im2col_stem(img):
     img = img.contiguous().float()
     B, C, H, W = img.shape

@@ -250,6 +250,24 @@ int hvr_softmax_rows_split(const float* S, int rows, int cols, int64_t ld_s, hvr
 int hvr_preprocess_u8(const uint8_t* img, int h, int w, int new_h, int new_w, int pad_h, int pad_w,
                       const float* mean3_host, const float* std3_host, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Video-level similarity for the inter-video stage (next row N4).  Replaces, for inference, the
+ * descriptor and similarity of HNMBRCNN.get_triplet_patches (hnmb_rcnn.py:76-101), which the reference
+ * evaluates with adaptive_avg_pool2d / max / torch.mm / softmax / argmax.
+ *   hvr_video_descriptor : c5_nhwc fp32 [n_videos*T, HW, C] (the shared head's output) ->
+ *           desc [n_videos, C] = max over a video's T frames of the per-frame spatial mean (:78-81).
+ *           ws : hvr_video_descriptor_workspace_bytes(n_videos, T, C) bytes.
+ *   hvr_support_select   : desc [G, C] of ALL videos; for the n_local videos g0 .. g0+n_local-1:
+ *           w = softmax over j != g of (1/sqrt(C)) desc_g . desc_j (:85-88), idx [n_local, n_support]
+ *           (int64) = the n_support largest, ties to the lower index, -1 when fewer other videos
+ *           exist; weights (optional) [n_local, G], 0 at j == g.
+ * ---------------------------------------------------------------------------------- */
+size_t hvr_video_descriptor_workspace_bytes(int n_videos, int T, int C);
+int hvr_video_descriptor(const float* c5_nhwc, int n_videos, int T, int HW, int C, float* desc, void* ws,
+                         size_t ws_bytes, void* stream);
+int hvr_support_select(const float* desc, int G, int C, int g0, int n_local, int n_support, int64_t* idx,
+                       float* weights, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -438,6 +438,51 @@ def hrnmp_stage123_key_feats(sd, roi_feats, start, length, prefix='bbox_head.'):
 
 
 # ----------------------------------------------------------------------------
+# N4  video-level similarity  hnmb_rcnn.py:76-101 (get_triplet_patches)
+# ----------------------------------------------------------------------------
+
+
+def video_descriptor(c5):
+    """c5 (T,C,h,w), the shared head's output for the frames of one video -> (C,):
+    global average pool per frame, maximum over the frames (hnmb_rcnn.py:78-81)."""
+    return F.adaptive_avg_pool2d(c5, (1, 1)).reshape(c5.shape[0], c5.shape[1]).max(dim=0).values
+
+
+def video_similarity(queries, candidates):
+    """softmax over the candidates of (1/sqrt(C)) * q . c  (hnmb_rcnn.py:85-88, :94-96).
+    queries (Q,C), candidates (M,C) -> (Q,M)."""
+    scale = 1.0 / math.sqrt(float(queries.shape[-1]))
+    return torch.softmax(scale * torch.mm(queries, candidates.t()), dim=1)
+
+
+def triplet_patches(c5_feats_all, key_video=0, video_per_cls=3):
+    """get_triplet_patches (hnmb_rcnn.py:76-101) restated: the first `video_per_cls` videos share the
+    key video's class.  Returns [key, the LEAST similar same-class video, the other-class video MOST
+    similar to {key, that video} taken together].  Pinned by tests/golden/ref_triplet_golden.pt."""
+    d = torch.stack([video_descriptor(c) for c in c5_feats_all])
+    same = d[:video_per_cls]
+    sim = video_similarity(same[:1], same)                                    # :85-88 (row of video 0)
+    hard = int(torch.argmin(sim[:, 1:], dim=1)[0]) + 1                        # :89
+    chosen = torch.stack([same[key_video], same[hard]])                       # :91
+    other = video_similarity(chosen, d[video_per_cls:]).sum(dim=0, keepdim=True)   # :92-97
+    return [key_video, hard, int(torch.argmax(other, dim=1)[0]) + video_per_cls]    # :99-101
+
+
+def select_support_by_similarity(desc, g, n_support):
+    """Inference-time use of the same similarity (oracle-defined, parity unpinned by the reference, which
+    selects support videos only in training): the `n_support` videos other than g whose descriptors are
+    most similar to video g's - video_similarity of g against all other videos, largest first, ties to
+    the lower index.  desc (G,C).  Returns (indices, weights (G-1,) in candidate order)."""
+    G = desc.shape[0]
+    cand = [i for i in range(G) if i != g]
+    if not cand:
+        return [], desc.new_zeros(0)
+    w = video_similarity(desc[g:g + 1], desc[cand])[0]
+    order = sorted(range(len(cand)), key=lambda j: (-float(w[j]), cand[j]))
+    return [cand[j] for j in order[:min(n_support, len(cand))]], w
+
+
+# ----------------------------------------------------------------------------
 # R10s SELSA forward     selsa_bbox_head.py:203-261
 # ----------------------------------------------------------------------------
 

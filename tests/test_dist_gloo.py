@@ -60,6 +60,55 @@ def test_support_exchange_world2(V, n_support):
     assert res == {0: True, 1: True}
 
 
+def _worker_similarity(rank, world, port, V, P, D, C, n_support, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from hvrnet_b200 import intervideo
+        from hvrnet_b200.ops import Split
+        from oracle import ref_torch as R
+        G = world * V
+        gen = torch.Generator().manual_seed(7)
+        desc_all = torch.randn(G, C, generator=gen) * 3          # every rank can rebuild the global truth
+        z_all = torch.cat([(torch.arange(P, dtype=torch.float32) + 16.0 * g).view(P, 1).expand(P, D) for g in range(G)], 0)
+        lo_, hi_ = rank * V * P, (rank + 1) * V * P
+        zl = Split(z_all[lo_:hi_].to(torch.bfloat16), (-z_all[lo_:hi_]).to(torch.bfloat16))
+        calls = []
+
+        def selector(d, g0, n_local, k):                          # CPU stand-in for hvr_support_select
+            calls.append((tuple(d.shape), g0, n_local, k, bool(torch.equal(d, desc_all))))
+            return [R.select_support_by_similarity(d, g0 + i, k)[0] for i in range(n_local)]
+        sup = intervideo.gather_support(zl, P, n_support, desc_local=desc_all[rank * V:(rank + 1) * V], selector=selector)
+        ok = len(sup) == V and calls == [((G, C), rank * V, V, min(n_support, G - 1), True)]
+        for v in range(V):
+            idx = R.select_support_by_similarity(desc_all, rank * V + v, n_support)[0]
+            exp = torch.cat([z_all[i * P:(i + 1) * P] for i in idx], 0)
+            ok = ok and torch.equal(sup[v].hi, exp.to(torch.bfloat16)) and torch.equal(sup[v].lo, (-exp).to(torch.bfloat16))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('V,C,n_support', [(3, 256, 2), (2, 1500, 4)])
+def test_similarity_support_exchange_world2(V, C, n_support):
+    """Next row N4 at world_size 2: the fp32 descriptors ride in the one all-gather as carrier rows (C = 1500
+    needs two rows of D = 1024 bf16 per video), every rank sees the same [G, C] table bit for bit, and the
+    selected rows are those of the oracle's selection."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_similarity, args=(r, world, port, V, 4, 1024, C, n_support, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=150)
+    assert [p.exitcode for p in procs] == [0] * world
+    res = dict(q.get(timeout=10) for _ in range(world))
+    assert res == {0: True, 1: True}
+
+
 def test_ring_rule_and_sharding():
     from hvrnet_b200 import intervideo as iv
     assert iv.support_indices(0, 256, 4) == [1, 2, 3, 4]

@@ -676,3 +676,42 @@ def test_preprocess_bit_exact(cuda, h, w):
     assert meta == rmeta
     assert out.shape == (1,) + ref.shape
     assert np.array_equal(out[0].cpu().numpy(), ref)
+
+
+# ---------------------------------------------------------------------------------------
+# next row N4: video descriptors and similarity-based support selection
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize('V,T,hw,C', [(7, 15, (38, 63), 256), (3, 2, (5, 7), 40), (1, 1, (1, 1), 8)])
+def test_video_descriptor(cuda, V, T, hw, C):
+    """hvr_video_descriptor against adaptive_avg_pool2d + max over the frames (hnmb_rcnn.py:78-81):
+    fp32 sums in a different order, so 1e-5 relative; run twice -> identical bits (fixed order)."""
+    from hvrnet_b200 import ops
+    from oracle import ref_torch as R
+    g = torch.Generator().manual_seed(31)
+    c5 = (torch.randn(V * T, C, hw[0], hw[1], generator=g) + torch.rand(V * T, C, 1, 1, generator=g) * 2).clamp(min=0)
+    ref = torch.stack([R.video_descriptor(c5[v * T:(v + 1) * T]) for v in range(V)])
+    x = c5.permute(0, 2, 3, 1).contiguous().to(cuda)
+    d = ops.video_descriptor(x, V)
+    assert d.shape == (V, C) and _rel(d.cpu(), ref) < 1e-5
+    assert torch.equal(d, ops.video_descriptor(x, V))
+
+
+@pytest.mark.parametrize('G,C,n', [(300, 256, 4), (5, 64, 4), (2, 256, 1), (1, 16, 4), (700, 32, 8)])
+def test_support_select(cuda, G, C, n):
+    """hvr_support_select against the oracle's select_support_by_similarity (softmax of scaled dot products
+    over the other videos, hnmb_rcnn.py:85-88; largest first, ties to the lower index): indices exactly,
+    weights to 1e-5; -1 where fewer than n other videos exist."""
+    from hvrnet_b200 import ops
+    from oracle import ref_torch as R
+    g = torch.Generator().manual_seed(41 + G)
+    desc = torch.randn(G, C, generator=g).abs() * (8.0 / C ** 0.5)
+    g0, nl = (G // 3, min(G - G // 3, 9))
+    idx, w = ops.support_select(desc.to(cuda), g0, nl, n, want_weights=True)
+    for i in range(nl):
+        ri, rw = R.select_support_by_similarity(desc, g0 + i, n)
+        assert idx[i].cpu().tolist() == ri + [-1] * (n - len(ri))
+        got = torch.cat([w[i, :g0 + i], w[i, g0 + i + 1:]]).cpu()
+        assert got.numel() == 0 or float((got - rw).abs().max()) < 1e-5
+    # exact ties: identical descriptors -> the lower indices
+    same = torch.ones(6, C).to(cuda)
+    assert ops.support_select(same, 2, 2, 3).cpu().tolist() == [[0, 1, 3], [0, 1, 2]]

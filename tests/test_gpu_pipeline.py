@@ -206,6 +206,55 @@ def test_intervideo_stage4_world1(world):
         assert _rel(a.cpu(), b) < 1e-3
 
 
+def test_intervideo_similarity_selection_world1(world):
+    """Next row N4: supports chosen by video-descriptor similarity (hnmb_rcnn.py:76-101 used at inference;
+    oracle-defined) instead of ring order.  Four "videos": the same 3 C4 maps at four amplitudes, so the
+    descriptors differ by margins far above fp32 summation-order noise.  Descriptors and weights against
+    the oracle, chosen indices exactly, stage-4 outputs within 1e-3."""
+    from hvrnet_b200 import ops
+    from oracle import cref, ref_torch as R
+    m, dev, sd = world['model'], world['dev'], world['sd']
+    c4 = world['c4_ref']
+    amps = [1.0, 1.6, 0.7, 1.3]
+    with torch.no_grad():
+        auxs = [R.hnmb_forward_feat(sd, [c4[i:i + 1] * a for i in range(3)], world['metas'], 1,
+                                    roi_align_fn=cref.roi_align, return_aux=True)[1] for a in amps]
+        z = [R.hrnmp_stage123_key_feats(sd, a['roi_feats'], a['start'], a['length']) for a in auxs]
+        desc = torch.stack([R.video_descriptor(a['c5']) for a in auxs])
+        picks = [R.select_support_by_similarity(desc, v, 2)[0] for v in range(4)]
+        refs = [R.hrnmp_forward_test(sd, a['roi_feats'], a['start'], a['length'],
+                                     support_rows=torch.cat([z[i] for i in picks[v]], 0)) for v, a in enumerate(auxs)]
+    assert picks == [[1, 3], [3, 0], [1, 3], [1, 0]]                 # the largest amplitudes among the others
+    # kernels against the oracle
+    c5_dev = torch.cat([a['c5'] for a in auxs], 0).permute(0, 2, 3, 1).contiguous().to(dev)
+    d_dev = ops.video_descriptor(c5_dev, 4)
+    assert _rel(d_dev.cpu(), desc) < 1e-5
+    idx, w = ops.support_select(d_dev, 0, 4, 2, want_weights=True)
+    assert idx.cpu().tolist() == picks
+    for v in range(4):
+        wr = R.select_support_by_similarity(desc, v, 2)[1]
+        got = torch.cat([w[v, :v], w[v, v + 1:]]).cpu()
+        assert float((got - wr).abs().max()) < 1e-5 and float(w[v, v]) == 0.0
+    assert ops.support_select(d_dev, 1, 2, 5).cpu().tolist()[0][3:] == [-1, -1]     # only 3 other videos
+    # the pipeline
+    xs = [[(c4[i:i + 1] * a).to(dev) for i in range(3)] for a in amps]
+    res, aux = m.forward_feat_intervideo(xs, world['metas'], n_support=2, rescale=True, return_aux=True,
+                                         proposals=[[p.to(dev) for p in a['proposals']] for a in auxs],
+                                         support_select='similarity')
+    for v in range(4):
+        assert aux[v]['support'].hi.shape[0] == 600
+        for a, b in zip(aux[v]['cls'] + aux[v]['reg'], refs[v][0] + refs[v][1]):
+            assert _rel(a.cpu(), b) < 1e-3
+    # batched windows (no forced proposals): the descriptors of all videos come from one launch; three
+    # copies of one video tie, and ties go to the lower index
+    got, gaux = m.forward_feat_intervideo([xs[0]] * 3, world['metas'], n_support=1, rescale=True, return_aux=True,
+                                          support_select='similarity')
+    assert len(got) == 3 and [a['support'].hi.shape[0] for a in gaux] == [300] * 3
+    assert torch.equal(gaux[1]['support'].hi, gaux[2]['support'].hi)           # both picked video 0
+    with pytest.raises(ValueError):
+        m.forward_feat_intervideo(xs[:1], world['metas'], support_select='nearest')
+
+
 def test_streaming_bit_identical(world):
     """the streaming scheduler (per-frame caches of proposals and fc_new_1 rows)
     returns the same detections, bit for bit, as the as-executed window path."""

@@ -57,7 +57,9 @@ def parse():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'torch_cuda'],
+                    help="reference: the oracle port on the host cores; torch_cuda: the same port's dense stages on cuDNN / cuBLAS "
+                         "(SURVEY.md 8d: the existing-GPU-implementation bar; not run by the driver)")
     ap.add_argument('--workload', default='hrnmp', choices=['hrnmp', 'selsa', 'faster_rcnn', 'hrnmp_inter'])
     ap.add_argument('--support-select', default='ring', choices=['ring', 'similarity'],
                     help='hrnmp_inter: inter-video supports by ring order (BASELINE.json config 5) or by video-descriptor similarity (SURVEY.md 8f N4)')
@@ -148,6 +150,68 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_torch_cuda(args):
+    """SURVEY.md 8d, last row: the reference-style torch-CUDA path as the `existing GPU implementation` bar.
+    The reference package cannot be imported, so this runs the oracle port's dense stages - the calls the
+    reference makes into cuDNN / cuBLAS (F.conv2d, F.linear, torch.mm, softmax) - on cuda:0 in the same
+    as-executed schedule as our arm: trunk on the V new frames, C5 + RPN convolutions on every frame of each
+    window, the relation head on T*300 pooled rows per video.  Proposal generation, RoIAlign and NMS are NOT
+    included (the oracle has them on the CPU only; < 10 % of our own step), so the figure is an upper bound
+    for the library path.  Measured twice: strict fp32 (the precision class of our split-bf16 kernels) and
+    with TF32 allowed (about 1e-3 relative, cuDNN / cuBLAS default for convolutions)."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    import torch
+    from hvrnet_b200 import configs, synth
+    from oracle import ref_torch as R
+    dev = torch.device('cuda:0')
+    w = configs.WORKLOADS['hrnmp' if args.workload == 'hrnmp_inter' else args.workload]
+    T, V = w['t_dim'], args.videos_per_gpu or 7
+    K, W = max(1, min(args.steps, 5)), max(1, min(args.warmup, 3))
+    sd = {k: v.to(dev) for k, v in synth.make_state_dict(w['head']).items()}
+    frames = synth.make_frames(V, seed=0).to(dev)
+    g = torch.Generator().manual_seed(0)
+    feats = torch.rand(T * 300, 256, 7, 7, generator=g).to(dev)
+    key = w['key_dim'] * 300
+    torch.backends.cudnn.benchmark = True
+
+    def step():
+        with torch.no_grad():
+            c4 = R.trunk_forward(sd, frames)
+            for v in range(V):
+                win = c4[v:v + 1].expand(T, -1, -1, -1).contiguous()      # values do not matter for the timing
+                R.c5_forward(sd, win)
+                R.rpn_forward(sd, win)
+                if w['head'] == 'hrnmp':
+                    R.hrnmp_forward_test(sd, feats, key, 300)
+                elif w['head'] == 'selsa':
+                    R.selsa_forward(sd, feats, key, 300)
+                else:
+                    R.shared_fc_forward(sd, feats)
+    out = {}
+    for tf32 in (False, True):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        for _ in range(W):
+            step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(K):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / K
+        out['tf32' if tf32 else 'fp32'] = {'value': V / (ms / 1e3), 'unit': 'frames/s', 'ms_per_step': ms}
+    print(json.dumps({
+        'impl': 'torch_cuda', 'metric': 'VID key frames/sec (1000x600, 300 proposals)', 'value': out['fp32']['value'],
+        'unit': 'frames/s', 'n_gpus': 1, 'steps': K, 'warmup': W, 'ms_per_step': out['fp32']['ms_per_step'],
+        'higher_is_better': True, 'dtype': 'f32 (cuDNN / cuBLAS, TF32 off)', 'tf32_allowed': out['tf32'],
+        'data': 'synthetic', 'config': config_dict(args.workload, T, V, 1, 'eager torch ops'),
+        'note': 'oracle port of the reference path on cuDNN / cuBLAS, dense stages only (no proposal generation, '
+                'RoIAlign, NMS): an upper bound for the existing library implementation'}))
+
+
 # ----------------------------------------------------------------------------------------
 # clocks
 # ----------------------------------------------------------------------------------------
@@ -202,6 +266,8 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------
 def main():
     args = parse()
+    if args.impl == 'torch_cuda':
+        return run_torch_cuda(args)
     if args.impl == 'reference':
         return run_reference(args)
     import torch.distributed as dist

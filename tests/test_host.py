@@ -294,3 +294,45 @@ def test_bench_measured_peaks_lookup():
     assert b._measured_peak(nested, ('hbm',), ('burst', 'copy'), 1000., 10000.) == ('hbm.copy_gbs', 6555.8)
     assert b._measured_peak(None, ('hbm',), (), 1000., 10000.) == (None, None)
     assert b._measured_peak({'hbm_gbs': 'n/a'}, ('hbm',), (), 1000., 10000.) == (None, None)
+
+
+def test_window_ring_bookkeeping():
+    """runtime.WindowRing (host logic of the window graph's input buffer): over 40 steps of three videos with
+    pre-padding by a repeated frame, tail repetition and an in-place write, the ring read through the returned
+    permutation always equals the window as the caller ordered it, every slot stays inside its own video's
+    range, and one frame per video and step is copied in steady state instead of T."""
+    from collections import deque
+    from hvrnet_b200.ops import Split
+    from hvrnet_b200.runtime import WindowRing
+    V, T = 3, 5
+    ring = WindowRing(V, T)
+    buf = torch.zeros(V * T, 2)
+    frame = lambda val: Split(torch.full((1, 2), float(val)), torch.full((1, 2), -float(val)))
+    dqs = [deque(maxlen=T) for _ in range(V)]
+    n = 0
+    for v in range(V):
+        f = frame(n)
+        n += 1
+        for _ in range(T):
+            dqs[v].append(f)                                   # hnl_test.py pre-pads with one repeated frame
+    copied = []
+    for step in range(40):
+        for v in range(V):
+            if step % 7 == 3 and v == 1:
+                dqs[v].append(dqs[v][-1])                      # tail repetition
+            else:
+                dqs[v].append(frame(n))
+                n += 1
+        if step == 20:
+            dqs[0][2].hi.add_(100.)                            # written in place: must be copied again
+        wins = [list(d) for d in dqs]
+        copies, perm = ring.place(wins)
+        copied.append(len(copies))
+        for slot, p in copies:
+            buf[slot] = p.hi[0]
+        assert torch.equal(buf[perm], torch.cat([p.hi for w in wins for p in w]))
+        assert all(v * T <= perm[v * T + t] < (v + 1) * T for v in range(V) for t in range(T))
+    assert copied[0] == 2 * V and copied[20] == V + 1 and max(copied[1:]) <= V + 1 and sum(copied) < 40 * V * T // 4
+    # a caller that rebuilds its tensors every call just gets every frame copied (correct, only slower)
+    copies, perm = ring.place([[frame(7) for _ in range(T)] for _ in range(V)])
+    assert len(copies) == V * T and sorted(perm) == list(range(V * T))

@@ -280,6 +280,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # the GPU box runs with NCCL_DEBUG=VERSION: keep NCCL's banner off stdout, which carries the one JSON line
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
 
     model, sd, w = configs.build_workload(args.workload, dev)

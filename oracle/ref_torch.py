@@ -8,15 +8,21 @@ It is the checker for the CUDA product in ``hvrnet_b200``; nothing in the produc
 imports it.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 cpu_baseline / ``--impl reference`` leg may import this package.
 
-Parity status: the pieces the reference's own doctests pin (anchors, delta2bbox,
-NMS keep-set) are checked against those vectors in tests/test_oracle_golden.py and
-against the reference's own ``nms_cpu.cpp`` compiled unmodified (oracle/_ref).
-Everything past those doctests (RoIAlign forward values, relation head, proposal
-generation, multiclass NMS, end-to-end detections, inter-video stage) is
-**parity unpinned** by the reference: no test, checkpoint or expected output ships,
-and the reference package cannot be imported (missing mmcv / private
-pytorch_metric_learning fork / three missing head modules).  For those the oracle
-is a line-by-line restatement of the cited files.
+Parity status (tests/test_oracle_golden.py).  Pinned against the reference's OWN code:
+anchors, delta2bbox, bbox2roi, multiclass_nms and eval_map (its pure-Python files loaded
+standalone, tests/golden/make_golden.py); NMS (its nms_cpu.cpp compiled unmodified,
+oracle/_ref, and its doctests); both relation heads - HRNMPBBoxHead.forward_test and
+SelsaBBoxHead.forward with forward_single_selsa and _add_selsa_with_fc - and the proposal
+generation RPNHead.get_bboxes_single (the methods cut out of the files' syntax trees and
+run on bare nn.Module harnesses, tests/golden/make_heads_golden.py: heads to 1e-6,
+proposals bit for bit); the video descriptor / similarity of get_triplet_patches
+(tests/golden/make_triplet_golden.py).  The reference package itself cannot be imported
+(missing mmcv / private pytorch_metric_learning fork / three missing head modules / a broken
+unpacking in HRNMPBBoxHead.__init__).
+Still **parity unpinned** by the reference: RoIAlign forward values (CUDA-only in the
+reference; restated here and, independently, in oracle/c), the trunk / C5 / RPN convolution
+stacks as compositions (restated on the same torch library calls: F.conv2d, frozen BN),
+end-to-end detections, and the inference-time inter-video stage (oracle-defined).
 
 Every function is keyed on a flat ``state_dict`` that uses the reference's parameter
 names, so the same weights load into the oracle and into the CUDA modules.
@@ -312,12 +318,13 @@ def rpn_forward(sd, c4, prefix='rpn_head.'):
 
 
 def rpn_proposals_single(cls, reg, anchors, img_shape, nms_pre=6000, nms_post=300, max_num=300,
-                         nms_thr=0.7, return_aux=False):
+                         nms_thr=0.7, return_aux=False, min_bbox_size=0, strict_gt=True):
     """One frame.  cls (A,h,w) sigmoid logits, reg (4A,h,w).  Returns (k,5).
 
     permute(1,2,0) flatten -> sigmoid -> top nms_pre (sorted) -> decode (stds 1,
-    clamp to img_shape) -> NMS -> first nms_post -> top max_num by score
-    (rpn_head.py:63-103; min_bbox_size=0 so that filter is skipped)."""
+    clamp to img_shape) -> [min_bbox_size filter, :84-90; 0 in the configs] -> NMS -> first
+    nms_post -> top max_num by score (rpn_head.py:63-103).  Pinned against the reference's own
+    get_bboxes_single by tests/golden/ref_heads_golden.pt (strict_gt=False: its CPU NMS)."""
     logits = cls.permute(1, 2, 0).reshape(-1)
     deltas = reg.permute(1, 2, 0).reshape(-1, 4)
     if nms_pre > 0 and logits.shape[0] > nms_pre:
@@ -326,10 +333,14 @@ def rpn_proposals_single(cls, reg, anchors, img_shape, nms_pre=6000, nms_post=30
         top = torch.arange(logits.shape[0])      # the reference leaves the order alone here
     scores = logits[top].sigmoid()
     boxes = delta2bbox(anchors[top], deltas[top], max_shape=img_shape)
+    if min_bbox_size > 0:
+        w, h = boxes[:, 2] - boxes[:, 0] + 1, boxes[:, 3] - boxes[:, 1] + 1
+        valid = torch.nonzero((w >= min_bbox_size) & (h >= min_bbox_size)).reshape(-1)
+        top, scores, boxes = top[valid], scores[valid], boxes[valid]
     dets = torch.cat([boxes, scores[:, None]], dim=-1)
     # NMS sorts by its 5th column; hand it the logit so that saturated-sigmoid ties keep
     # the (logit desc, index asc) total order of repair 6.
-    keep = nms(torch.cat([boxes, logits[top][:, None]], dim=-1), nms_thr, strict_gt=True)
+    keep = nms(torch.cat([boxes, logits[top][:, None]], dim=-1), nms_thr, strict_gt=strict_gt)
     keep = keep[argsort_desc_stable(logits[top][keep])]   # identity when `top` is sorted
     keep = keep[:nms_post]
     keep = keep[:min(max_num, keep.shape[0])]             # final top-k (:100-103): same order

@@ -10,6 +10,8 @@ nn.Module harnesses whose __init__ sets the attributes the reference's __init__ 
                                                forward (:203-261)                                     (R10s)
   mmdet/models/anchor_heads/rpn_head.py        get_bboxes_single (:55-104) on the reference's own delta2bbox
                                                (core/bbox/transforms.py) and nms_cpu.cpp (oracle/_ref) (R5)
+  mmdet/models/bbox_heads/hrnmp_bbox_head.py   get_det_bboxes (:1009-1052) on the reference's own delta2bbox and
+                                               multiclass_nms (core/post_processing/bbox_nms.py)      (R11)
 
 Sizes are reduced (fixture size); weights and inputs are seeded; the q/k projections are scaled so that the
 attention is far from uniform.  The fixture stores state dicts, inputs and outputs, so the tests need neither
@@ -92,7 +94,7 @@ def load(path, name):
 
 
 def main():
-    out = {'hrnmp': [], 'selsa': [], 'rpn': []}
+    out = {'hrnmp': [], 'selsa': [], 'rpn': [], 'det': []}
     # ---- relation heads
     for seed, (t_dim, P, key, C, d) in enumerate([(3, 6, 1, 4, 32), (5, 4, 0, 2, 16), (4, 5, 3, 4, 32), (1, 7, 0, 4, 16)]):
         for kind in ('hrnmp', 'selsa'):
@@ -143,8 +145,32 @@ def main():
         props = fn(me, [cls], [reg], [anchors], img_shape, 1.0, cfg, False)
         out['rpn'].append(dict(cls=cls, reg=reg, img_shape=img_shape, nms_pre=nms_pre, max_num=max_num,
                                min_bbox_size=min_size, proposals=props.clone()))
+    # ---- decode + multiclass NMS of the two head outputs
+    wrapper = types.ModuleType('mmdet.ops.nms.nms_wrapper')
+    wrapper.nms = nms
+    for nme, m in (('mmdet', types.ModuleType('mmdet')), ('mmdet.ops', types.ModuleType('mmdet.ops')),
+                   ('mmdet.ops.nms', types.ModuleType('mmdet.ops.nms')), ('mmdet.ops.nms.nms_wrapper', wrapper)):
+        sys.modules.setdefault(nme, m)
+    sys.modules['mmdet.ops.nms'].nms_wrapper = wrapper
+    bbox_nms = load('core/post_processing/bbox_nms.py', 'ref_bbox_nms')
+    det = cut_methods('models/bbox_heads/hrnmp_bbox_head.py', 'HRNMPBBoxHead', ['get_det_bboxes'],
+                      dict(delta2bbox=transforms.delta2bbox, multiclass_nms=bbox_nms.multiclass_nms,
+                           force_fp32=lambda *a, **k: (lambda f: f)))['get_det_bboxes']
+    me = types.SimpleNamespace(target_means=[0., 0., 0., 0.], target_stds=[0.1, 0.1, 0.2, 0.2])
+    for seed, (n, sf, rescale, shift) in enumerate([(300, 1.0, False, -3.0), (300, 1.6, True, 0.5), (17, 0.625, True, -7.0)]):
+        g = torch.Generator().manual_seed(400 + seed)
+        xy = torch.rand(n, 2, generator=g) * torch.tensor([800., 450.])
+        wh = torch.rand(n, 2, generator=g) * 250 + 8
+        rois = torch.cat([torch.zeros(n, 1), xy, xy + wh], 1)
+        cls = [torch.randn(n, 31, generator=g) * 2 + torch.cat([torch.zeros(1), torch.full((30,), shift)]) for _ in range(2)]
+        reg = [torch.randn(n, 4, generator=g) * torch.tensor([1., 1., 2., 2.]) for _ in range(2)]
+        cfg = types.SimpleNamespace(score_thr=0.001, nms=dict(type='nms', iou_thr=0.3), max_per_img=300)
+        dets, labels = det(me, rois, cls, reg, (600, 1000, 3), sf, rescale, cfg)
+        out['det'].append(dict(rois=rois, cls=cls, reg=reg, scale_factor=sf, rescale=rescale,
+                               dets=[d.clone() for d in dets], labels=[l.clone() for l in labels]))
     torch.save(out, os.path.join(HERE, 'ref_heads_golden.pt'))
-    print('wrote', {k: len(v) for k, v in out.items()}, [p['proposals'].shape[0] for p in out['rpn']])
+    print('wrote', {k: len(v) for k, v in out.items()}, [p['proposals'].shape[0] for p in out['rpn']],
+          [[d.shape[0] for d in c['dets']] for c in out['det']])
 
 
 if __name__ == '__main__':

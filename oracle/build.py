@@ -10,6 +10,7 @@
 """
 import importlib.util
 import os
+import shutil
 import subprocess
 import sys
 
@@ -63,6 +64,56 @@ def load_ref():
     return mod
 
 
+ROI_SRCS = ['/root/reference/mmdet/ops/roi_align/src/roi_align_cuda.cpp',
+            '/root/reference/mmdet/ops/roi_align/src/roi_align_kernel.cu']
+ROI_NAMES = {True: 'hvr_ref_roi_align_cuda', False: 'hvr_ref_roi_align_cuda_nofma'}
+
+
+def ref_roi_so_path(fma=True):
+    p = os.path.join(REF_DIR, ROI_NAMES[fma] + '.so')
+    return p if os.path.exists(p) else None
+
+
+def build_ref_roi_align(force=False):
+    """Compiles the REFERENCE's own RoIAlign CUDA op (roi_align_cuda.cpp + roi_align_kernel.cu, unmodified,
+    where they lie) for sm_100a into oracle/_ref/, twice: with nvcc's default floating-point contraction (what
+    the reference's setup.py builds) and with -fmad=false (every product and sum rounded: the arithmetic
+    contract of the CUDA product and of oracle/c).  oracle/shim/ref_compat.h maps the torch names removed
+    since mmdetection v1 (AT_CHECK, THCudaCheck).  nvcc cross-compiles here without a GPU; the modules can only
+    RUN on the GPU box, where tests/test_gpu_kernels.py loads them if present.  Returns the built paths."""
+    if not all(os.path.exists(s) for s in ROI_SRCS):
+        return [ref_roi_so_path(True), ref_roi_so_path(False)]
+    os.makedirs(REF_DIR, exist_ok=True)
+    os.environ.setdefault('TORCH_CUDA_ARCH_LIST', '10.0a')
+    from torch.utils.cpp_extension import load
+    shim = os.path.join(HERE, 'shim', 'ref_compat.h')
+    for fma in (True, False):
+        if ref_roi_so_path(fma) and not force:
+            continue
+        bd = os.path.join(REF_DIR, 'build_' + ROI_NAMES[fma])
+        os.makedirs(bd, exist_ok=True)
+        load(name=ROI_NAMES[fma], sources=ROI_SRCS, build_directory=bd, verbose=False,
+             extra_cflags=['-O2', '-w', '-include', shim],
+             extra_cuda_cflags=['-O2', '-w', '-include', shim, '-gencode', 'arch=compute_100a,code=sm_100a'] +
+                               ([] if fma else ['-fmad=false']))
+        os.replace(os.path.join(bd, ROI_NAMES[fma] + '.so'), os.path.join(REF_DIR, ROI_NAMES[fma] + '.so'))
+        shutil.rmtree(bd, ignore_errors=True)
+    return [ref_roi_so_path(True), ref_roi_so_path(False)]
+
+
+def load_ref_roi_align(fma=True):
+    """Import a compiled reference RoIAlign module (None if it was never built).  Needs a CUDA device to run."""
+    p = ref_roi_so_path(fma)
+    if p is None:
+        return None
+    import torch  # noqa: F401
+    spec = importlib.util.spec_from_file_location(ROI_NAMES[fma], p)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 if __name__ == '__main__':
     print(build_c(force='--force' in sys.argv))
     print(build_ref(force='--force' in sys.argv))
+    print(build_ref_roi_align(force='--force' in sys.argv))

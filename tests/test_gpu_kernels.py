@@ -459,6 +459,44 @@ def test_roi_align_bit_exact(cuda):
     assert float((m - ref).abs().max()) <= float(ref.abs().max()) * 2.0 ** -16
 
 
+def test_roi_align_vs_reference_cuda_op(cuda):
+    """R8 against the REFERENCE's own CUDA op: mmdet/ops/roi_align/src/roi_align_cuda.cpp + roi_align_kernel.cu,
+    compiled unmodified for sm_100a in the build container (oracle/build.py::build_ref_roi_align, output in
+    oracle/_ref, shipped to the GPU box) and called through its pybind `forward` exactly as roi_align.py:12-30
+    does.  Built with -fmad=false (every product and sum rounded - the contract of this repo's kernels and of
+    oracle/c) the reference kernel, both of our kernels and the C oracle agree BIT FOR BIT; against the default
+    build (nvcc contracts a*b+c into FMAs) the results agree to 1e-5 relative."""
+    from hvrnet_b200 import ops
+    from oracle import build, cref
+    ref_fma, ref_strict = build.load_ref_roi_align(True), build.load_ref_roi_align(False)
+    if ref_fma is None or ref_strict is None:
+        pytest.skip('oracle/_ref reference RoIAlign op not built (needs /root/reference at build time)')
+    g = torch.Generator().manual_seed(17)
+    feat = torch.randn(3, 256, 38, 63, generator=g)
+    rois = _rois(g, 400, 3)
+    f, r = feat.to(cuda), rois.to(cuda)
+
+    def reference(mod, out_size, scale, sn, ff=f, rr=r):
+        out = ff.new_zeros(rr.shape[0], ff.shape[1], out_size, out_size)        # roi_align.py:23
+        assert mod.forward(ff, rr, out_size, out_size, scale, sn, out) == 1
+        torch.cuda.synchronize()
+        return out
+    strict = reference(ref_strict, 7, 1 / 16., 2)
+    ours = ops.roi_align(f, r)                                                  # reference layout (NCHW)
+    assert torch.equal(ours.view(torch.int32), strict.view(torch.int32))
+    rows = ops.roi_align(ops.nchw_to_nhwc(f), r, feat_nhwc=True, out_nhwc=True)  # the pipeline's sn2 kernel
+    assert torch.equal(rows.permute(0, 3, 1, 2).contiguous().view(torch.int32), strict.view(torch.int32))
+    assert torch.equal(cref.roi_align(feat, rois).view(torch.int32), strict.cpu().view(torch.int32))
+    assert _rel(ours, reference(ref_fma, 7, 1 / 16., 2)) < 1e-5
+    # adaptive sampling (sample_num = 0) and another geometry: the generic kernel
+    f2 = torch.randn(2, 16, 15, 15, generator=g).to(cuda)
+    r2 = torch.tensor([[0, 0, 0, 50, 50], [0, 10, 30, 43, 55], [1, 67, 40, 110, 120]], dtype=torch.float32).to(cuda)
+    for sn in (0, 2, 3):
+        a = ops.roi_align(f2, r2, out_size=3, spatial_scale=1 / 8., sample_num=sn)
+        b = reference(ref_strict, 3, 1 / 8., sn, f2, r2)
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32)), sn
+
+
 @pytest.mark.parametrize('C,out_size', [(256, 7), (128, 7), (512, 7), (256, 3), (16, 7), (40, 3)])
 def test_roi_align_sn2_kernel_equals_generic_per_bin_kernel(cuda, C, out_size):
     """roi_align_sn2_kernel (taps shared by the two y-samples of a bin reused from registers; RoIs with

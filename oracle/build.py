@@ -101,6 +101,49 @@ def build_ref_roi_align(force=False):
     return [ref_roi_so_path(True), ref_roi_so_path(False)]
 
 
+NMS_CUDA_SRCS = ['/root/reference/mmdet/ops/nms/src/nms_cuda.cpp', '/root/reference/mmdet/ops/nms/src/nms_kernel.cu']
+NMS_CUDA_NAME = 'hvr_ref_nms_cuda'
+
+
+def ref_nms_cuda_so_path():
+    p = os.path.join(REF_DIR, NMS_CUDA_NAME + '.so')
+    return p if os.path.exists(p) else None
+
+
+def build_ref_nms_cuda(force=False):
+    """Compiles the REFERENCE's own NMS CUDA op (nms_cuda.cpp + nms_kernel.cu, unmodified, where they lie) for
+    sm_100a into oracle/_ref/.  oracle/shim/ref_compat_nms.h + shim/include/THC/THC.h stand in for the THC
+    names torch removed (THCState, THCudaMalloc/Free, THCCeilDiv, THCudaCheck).  Runs only on the GPU box."""
+    if not all(os.path.exists(s) for s in NMS_CUDA_SRCS):
+        return ref_nms_cuda_so_path()
+    if ref_nms_cuda_so_path() and not force:
+        return ref_nms_cuda_so_path()
+    os.makedirs(REF_DIR, exist_ok=True)
+    os.environ.setdefault('TORCH_CUDA_ARCH_LIST', '10.0a')
+    from torch.utils.cpp_extension import load
+    shim, inc = os.path.join(HERE, 'shim', 'ref_compat_nms.h'), os.path.join(HERE, 'shim', 'include')
+    bd = os.path.join(REF_DIR, 'build_' + NMS_CUDA_NAME)
+    os.makedirs(bd, exist_ok=True)
+    load(name=NMS_CUDA_NAME, sources=NMS_CUDA_SRCS, build_directory=bd, verbose=False,
+         extra_cflags=['-O2', '-w', '-include', shim, '-I', inc],
+         extra_cuda_cflags=['-O2', '-w', '-include', shim, '-I', inc, '-gencode', 'arch=compute_100a,code=sm_100a'])
+    os.replace(os.path.join(bd, NMS_CUDA_NAME + '.so'), os.path.join(REF_DIR, NMS_CUDA_NAME + '.so'))
+    shutil.rmtree(bd, ignore_errors=True)
+    return ref_nms_cuda_so_path()
+
+
+def load_ref_nms_cuda():
+    """Import the compiled reference NMS CUDA module (None if it was never built).  Needs a CUDA device to run."""
+    p = ref_nms_cuda_so_path()
+    if p is None:
+        return None
+    import torch  # noqa: F401
+    spec = importlib.util.spec_from_file_location(NMS_CUDA_NAME, p)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def load_ref_roi_align(fma=True):
     """Import a compiled reference RoIAlign module (None if it was never built).  Needs a CUDA device to run."""
     p = ref_roi_so_path(fma)
@@ -117,3 +160,4 @@ if __name__ == '__main__':
     print(build_c(force='--force' in sys.argv))
     print(build_ref(force='--force' in sys.argv))
     print(build_ref_roi_align(force='--force' in sys.argv))
+    print(build_ref_nms_cuda(force='--force' in sys.argv))

@@ -593,6 +593,27 @@ def test_nms_bit_exact(cuda, n, thr):
         assert torch.equal(got, ref)
 
 
+@pytest.mark.parametrize('n,thr', [(1, 0.5), (64, 0.5), (65, 0.7), (1000, 0.3), (6000, 0.7)])
+def test_nms_vs_reference_cuda_op(cuda, n, thr):
+    """R7 against the REFERENCE's own CUDA op: mmdet/ops/nms/src/nms_cuda.cpp + nms_kernel.cu compiled unmodified
+    for sm_100a in the build container (oracle/build.py::build_ref_nms_cuda -> oracle/_ref) and called through its
+    pybind `nms` as nms_wrapper.py:50-58 does: same kept indices (strict `>`, ascending), without score ties
+    (the reference's device sort is not stable)."""
+    from hvrnet_b200 import ops
+    from oracle import build, cref
+    ref = build.load_ref_nms_cuda()
+    if ref is None:
+        pytest.skip('oracle/_ref reference NMS CUDA op not built (needs /root/reference at build time)')
+    g = torch.Generator().manual_seed(100 + n)
+    d = _dets(g, n, spread=300. if n < 2000 else 900.)
+    d[:, 4] = torch.randperm(n, generator=g).float() / n            # distinct scores
+    keep_ref = ref.nms(d.to(cuda), thr)
+    torch.cuda.synchronize()
+    assert keep_ref.dtype == torch.int64
+    assert torch.equal(ops.nms(d.to(cuda), thr).cpu(), keep_ref.cpu())
+    assert torch.equal(cref.nms(d, thr, strict_gt=True), keep_ref.cpu())
+
+
 # ---------------------------------------------------------------------------------------
 # RPN proposals: bit-exact anchor indices, boxes to 1e-4 px
 # ---------------------------------------------------------------------------------------

@@ -7,9 +7,11 @@
  *
  * Compile with -ffp-contract=off: every product and sum is rounded separately
  * (strict IEEE fp32), which is the arithmetic contract the CUDA kernels follow
- * with __fmul_rn/__fadd_rn.  Parity for RoIAlign forward values is unpinned by the
- * reference (it ships no expected outputs); NMS is pinned by nms_wrapper.py:25-35
- * and by the reference's own nms_cpu.cpp built into oracle/_ref.
+ * with __fmul_rn/__fadd_rn.  RoIAlign forward values are pinned on the GPU box against the
+ * reference's own CUDA kernel compiled unmodified with -fmad=false (bit for bit;
+ * tests/test_gpu_kernels.py::test_roi_align_vs_reference_cuda_op); NMS is pinned by
+ * nms_wrapper.py:25-35, by the reference's own nms_cpu.cpp and by its CUDA op, both built into
+ * oracle/_ref.
  */
 #include <math.h>
 #include <stdint.h>

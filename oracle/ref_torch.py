@@ -24,9 +24,11 @@ RPNHead.forward_single, tests/golden/make_convs_golden.py: identical bits), the 
 multiclass NMS step (HRNMPBBoxHead.get_det_bboxes) and the detector's control flow end to
 end (HNMBRCNN.forward_feat / simple_test_bboxes with the oracle's C RoIAlign as the only
 substituted piece, tests/golden/make_e2e_golden.py) are pinned the same way.
-Still **parity unpinned** by the reference: RoIAlign forward values (CUDA-only in the
-reference; restated here and, independently, in oracle/c) and the inference-time
-inter-video stage (oracle-defined).
+RoIAlign forward values and the GPU NMS semantic are pinned on the GPU box by the reference's
+own CUDA ops compiled unmodified into oracle/_ref (tests/test_gpu_kernels.py::
+test_roi_align_vs_reference_cuda_op, ::test_nms_vs_reference_cuda_op).
+Still **parity unpinned** by the reference: the inference-time inter-video stage
+(oracle-defined; the reference has it in training only).
 
 Every function is keyed on a flat ``state_dict`` that uses the reference's parameter
 names, so the same weights load into the oracle and into the CUDA modules.

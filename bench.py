@@ -32,6 +32,26 @@ CONV_GFLOP_PER_WINDOW_FRAME = 74.05 + 22.74  # C5 + RPN
 
 
 
+
+_REAL_STDOUT = None
+
+
+def _stdout_to_stderr():
+    """Point file descriptor 1 at stderr for the rest of the process and keep the real stdout aside: native
+    libraries (NCCL's version banner) write to fd 1 directly, and the driver reads ONE JSON line from stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def _emit(text):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(text + '\n')
+    out.flush()
+
+
 def _measured_peak(peaks, must, prefer, lo, hi):
     """Pick a figure from the driver-written MEASURED_PEAKS.json (schema not under our control): the first
     numeric entry whose (nested) key contains every word of `must` and whose value lies in [lo, hi] - GB/s
@@ -280,8 +300,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        # the GPU box runs with NCCL_DEBUG=VERSION: keep NCCL's banner off stdout, which carries the one JSON line
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        _stdout_to_stderr()      # NCCL prints its version banner on fd 1; stdout must carry the one JSON line only
         dist.init_process_group('nccl', device_id=dev)
 
     model, sd, w = configs.build_workload(args.workload, dev)
@@ -558,7 +577,7 @@ def main():
             line['cpu_baseline'] = {'value': 1.0 / sec, 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': 'port',
                                     'sample': '%d key frame, trunk on 1 new frame + forward_feat over %d frames '
                                               '(oracle port of the reference PyTorch-CPU path)' % (done, T)}
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -336,3 +336,25 @@ def test_window_ring_bookkeeping():
     # a caller that rebuilds its tensors every call just gets every frame copied (correct, only slower)
     copies, perm = ring.place([[frame(7) for _ in range(T)] for _ in range(V)])
     assert len(copies) == V * T and sorted(perm) == list(range(V * T))
+
+
+def test_bench_keeps_native_prints_off_stdout():
+    """Multi-GPU bench: after bench._stdout_to_stderr() anything written to file descriptor 1 by native code
+    (NCCL prints its version banner there) or by print() lands on stderr; only bench._emit() reaches the real
+    stdout, which must carry the one JSON line."""
+    import subprocess
+    import sys
+    import textwrap
+    code = textwrap.dedent('''
+        import importlib.util, os
+        spec = importlib.util.spec_from_file_location('hvr_bench', %r)
+        b = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(b)
+        b._stdout_to_stderr()
+        os.write(1, b"NCCL version 2.28.9+cuda12.9\\n")
+        print("a print after the redirect")
+        b._emit('{"ok": 1}')
+    ''' % os.path.join(ROOT, 'bench.py'))
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout == '{"ok": 1}\n'
+    assert 'NCCL version' in r.stderr and 'a print after the redirect' in r.stderr

@@ -9,8 +9,14 @@ registered detectors.
   last frame    appended (W+1)/2 times (clipped to the video length), one detection per repeat;
                 short videos are topped up with more random frames first
 
+With ``video_shuffle=True`` (the hrnmp config's relation_setup, cfg:156; the only mode the reference's
+loop files results for) the frames of a video ARRIVE in a np.random.shuffle order
+(imagenet_vid_sequence.py:203-210), drawn before the loop's own padding draws, so a window holds
+frames from all over the video - SELSA's global aggregation.  The default here is temporal order.
+
 ``window_schedule`` is the pure-Python schedule (frame indices only) - the CPU tests compare it
-with the oracle's restatement; ``detect_video`` drives a detector with it.
+with the oracle's restatement and with a trace of the reference's own loop
+(tests/golden/ref_loop_golden.pt); ``detect_video`` drives a detector with it.
 """
 import numpy as np
 
@@ -22,12 +28,15 @@ def pre_padding_indices(seg_len, num, rng=np.random):
     return rng.choice(video_index, num, replace=num > seg_len).tolist()
 
 
-def window_schedule(seg_len, window, rng=np.random):
+def window_schedule(seg_len, window, rng=np.random, video_shuffle=False):
     """Yields (window_frame_indices, window_offsets, key_offset) for every detection of a video
     of `seg_len` frames, in the order the reference produces them.  Offsets are -1 for padding
     frames (their detections are never emitted)."""
     half = int((window - 1) / 2)
     frames, offs = [], []
+    order = np.arange(seg_len).tolist()                      # arrival order of the frame offsets
+    if video_shuffle:
+        rng.shuffle(order)                                   # imagenet_vid_sequence.py:203-205
 
     def push(f, o):
         frames.append(f)
@@ -43,12 +52,12 @@ def window_schedule(seg_len, window, rng=np.random):
             pad = pre_padding_indices(seg_len, half, rng)
             for f in pad:
                 push(f, -1)
-            push(0, 0)
+            push(order[0], order[0])
             if not last:
                 continue
         if not last:                                         # key_frame_flag == 2
             full = len(frames) >= window - 1
-            push(t, t)
+            push(order[t], order[t])
             if full:
                 yield list(frames), list(offs), offs[half]
             continue
@@ -58,7 +67,7 @@ def window_schedule(seg_len, window, rng=np.random):
             offs.pop()
         end_counter = 0
         while end_counter < min(seg_len, int((window + 1) / 2)):
-            push(t, t)
+            push(order[t], order[t])
             end_counter += 1
             if len(frames) < window - 1:
                 for f in pre_padding_indices(seg_len, window - len(frames), rng):
@@ -66,7 +75,7 @@ def window_schedule(seg_len, window, rng=np.random):
             yield list(frames), list(offs), offs[half]
 
 
-def detect_video(model, frames, img_meta, window=None, rng=np.random, rescale=True):
+def detect_video(model, frames, img_meta, window=None, rng=np.random, rescale=True, video_shuffle=False):
     """frames: sequence of preprocessed [1,3,H,W] CUDA tensors of ONE video.  Returns
     {frame_offset: result} with one entry per emitted key frame (forward_feat results)."""
     window = int(window or model.bbox_head.t_dim)
@@ -79,7 +88,7 @@ def detect_video(model, frames, img_meta, window=None, rng=np.random, rescale=Tr
 
     out = {}
     metas = [img_meta] * window
-    for idxs, offs, key in window_schedule(len(frames), window, rng):
+    for idxs, offs, key in window_schedule(len(frames), window, rng, video_shuffle):
         if key < 0 or len(idxs) != window:
             continue
         out[key] = model(x=[feat(i) for i in idxs], img=None, img_meta=metas, forward_feat=True, return_loss=False,

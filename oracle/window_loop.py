@@ -8,20 +8,27 @@ from collections import deque
 import numpy as np
 
 
-def trace(seg_len, all_frame_interval, rng=np.random):
+def trace(seg_len, all_frame_interval, rng=np.random, video_shuffle=False):
+    """video_shuffle (hrnmp cfg:156): the data set hands the frames of a video out in a shuffled order drawn
+    when its first frame is fetched (imagenet_vid_sequence.py:203-210), i.e. before the loop's padding draws.
+    Pinned against a trace of the reference's own loop, tests/golden/ref_loop_golden.pt."""
     events = []
     feat_list = frame_offset_list = None
+    video_index = np.arange(seg_len).tolist()
+    if video_shuffle:
+        rng.shuffle(video_index)
 
     def pre_padding_imgs(num):                                             # :293-296
         video_index = np.arange(seg_len).tolist()
         rng.shuffle(video_index)
         return rng.choice(video_index, num, replace=num > seg_len).tolist()
 
-    for frame_offset in range(seg_len):
+    for tid in range(seg_len):
+        frame_offset = video_index[tid]
         if seg_len == 1:
             flags = [0, 1]                    # a single frame is both the first and the last of its video
         else:
-            flags = [0] if frame_offset == 0 else ([1] if frame_offset == seg_len - 1 else [2])
+            flags = [0] if tid == 0 else ([1] if tid == seg_len - 1 else [2])
         for key_frame_flag in flags:
             if key_frame_flag == 0:                                            # :359-383
                 feat_list = deque(maxlen=all_frame_interval)

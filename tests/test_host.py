@@ -358,3 +358,32 @@ def test_bench_keeps_native_prints_off_stdout():
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout == '{"ok": 1}\n'
     assert 'NCCL version' in r.stderr and 'a print after the redirect' in r.stderr
+
+
+def test_window_schedule_matches_trace_of_reference_loop():
+    """R15 against the REFERENCE's own loop: tests/golden/ref_loop_golden.pt is a trace of multi_hnl_gpu_test and
+    pre_padding_imgs (tools/hnl_test.py:293-475) driven by VIDSeqDataset.prepare_test_img / __getitem__
+    (imagenet_vid_sequence.py:192-293), all executed unmodified around recording stand-ins
+    (tests/golden/make_loop_golden.py).  video.window_schedule and the oracle's restatement reproduce every
+    forward_feat call (which frames, in which order) and where each result is filed, across consecutive
+    videos sharing one np.random stream: video_shuffle=True (the config's mode), windows 3 / 5 / 15 / 21, videos
+    shorter than the window; and the call sequence in temporal order (video_shuffle=False, for which the
+    reference's loop files nothing)."""
+    import numpy as np
+    from hvrnet_b200 import video
+    from oracle import window_loop
+    cases = torch.load(os.path.join(ROOT, 'tests', 'golden', 'ref_loop_golden.pt'))
+    assert sum(c['video_shuffle'] for c in cases) >= 5
+    for c in cases:
+        for impl in (video.window_schedule, window_loop.trace):
+            np.random.seed(c['seed'])
+            calls, filed, start = [], [None] * sum(c['seg_lens']), 1
+            for L in c['seg_lens']:
+                for idxs, offs, key in impl(L, c['window'], np.random, c['video_shuffle']):
+                    calls.append(idxs)
+                    filed[start + key - 1] = idxs                      # hnl_test.py:399-409
+                    assert [o for o in offs if o >= 0] == [i for i, o in zip(idxs, offs) if o >= 0]
+                start += L
+            assert calls == c['calls'] and len(calls) == c['n_calls']
+            if c['video_shuffle']:
+                assert filed == c['filed']

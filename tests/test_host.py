@@ -387,3 +387,20 @@ def test_window_schedule_matches_trace_of_reference_loop():
             assert calls == c['calls'] and len(calls) == c['n_calls']
             if c['video_shuffle']:
                 assert filed == c['filed']
+
+
+def test_plugin_machinery_matches_reference_transcript():
+    """Boundary: tests/golden/ref_registry_golden.json is a transcript of the REFERENCE's own
+    Registry / build_from_cfg (mmdet/utils/registry.py) and build (mmdet/models/builder.py:8-15) on a scripted
+    scenario - return values, reprs, exception types and messages.  Replaying the script on hvrnet_b200.registry
+    and hvrnet_b200.builder gives the identical transcript."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location('hvr_make_registry_golden',
+                                                  os.path.join(ROOT, 'tests', 'golden', 'make_registry_golden.py'))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    from hvrnet_b200.builder import build
+    from hvrnet_b200.registry import Registry, build_from_cfg
+    ref = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'ref_registry_golden.json')))
+    assert len(ref) == 21 and mk.scenario(Registry, build_from_cfg, build) == ref

@@ -404,3 +404,30 @@ def test_plugin_machinery_matches_reference_transcript():
     from hvrnet_b200.registry import Registry, build_from_cfg
     ref = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'ref_registry_golden.json')))
     assert len(ref) == 21 and mk.scenario(Registry, build_from_cfg, build) == ref
+
+
+def test_abi_argument_checks_without_a_gpu():
+    """Error behaviour of the C ABI (include/hvr_b200.h: 0 = ok, negative = error, nothing exits): argument and
+    workspace checks return before any CUDA call, so they can be exercised on a CPU-only box."""
+    from hvrnet_b200 import _lib
+    L = _lib.lib()
+    null = ctypes.c_void_p(0)
+    one = ctypes.c_void_p(8)                                  # non-null, never dereferenced by the checks
+    ARG, WS = -1, -3
+    # RoIAlign: empty input is a no-op; null tensors / impossible shapes are argument errors
+    assert L.hvr_roi_align_fwd(null, 1, null, 0, 1, 256, 38, 63, 7, 7, 0.0625, 2, null, 1, null, null, 0, null, null) == 0
+    assert L.hvr_roi_align_fwd(null, 1, one, 4, 1, 256, 38, 63, 7, 7, 0.0625, 2, one, 1, null, null, 0, null, null) == ARG
+    assert L.hvr_roi_align_fwd(one, 1, one, 4, 1, 256, 38, 63, 7, 7, 0.0625, 2, null, 1, null, null, 0, null, null) == ARG
+    assert L.hvr_roi_align_fwd(one, 1, one, 4, 1, 256, 38, 63, 7, 7, 0.0625, 2, one, 2, null, null, 0, null, null) == ARG
+    assert L.hvr_roi_align_fwd(one, 0, one, 4, 1, 256, 38, 63, 7, 7, 0.0625, 2, one, 0, null, null, 0, null, null) == WS
+    assert L.hvr_debug_roi_variant(5) == ARG and L.hvr_debug_roi_variant(0) == 0
+    # video descriptor / support selection (next row N4)
+    nb = L.hvr_video_descriptor_workspace_bytes(7, 15, 256)
+    assert nb == 7 * 15 * 16 * 256 * 4
+    assert L.hvr_video_descriptor(null, 0, 15, 2394, 256, null, null, 0, null) == 0
+    assert L.hvr_video_descriptor(null, 7, 15, 2394, 256, one, one, nb, null) == ARG
+    assert L.hvr_video_descriptor(one, 7, 15, 2394, 256, one, one, nb - 1, null) == WS
+    assert L.hvr_support_select(null, 8, 256, 0, 2, 4, one, null, null) == ARG
+    assert L.hvr_support_select(one, 8, 256, 7, 2, 4, one, null, null) == ARG            # g0 + n_local > G
+    assert L.hvr_support_select(one, 8, 256, 0, 0, 4, one, null, null) == 0              # nothing to select
+    assert L.hvr_strerror(ARG) not in (b'', b'ok')

@@ -26,11 +26,28 @@ def support_indices(g, total, n_support):
 
 
 def shard_range(n_items, world, rank):
-    """Contiguous shard [lo, hi) of n_items for `rank` (videos are sliced contiguously per rank,
-    as imagenet_vid_sequence.py:117-158 does for the reference's distributed test)."""
+    """Contiguous, count-balanced shard [lo, hi) of n_items for `rank` (key frames of bench.py's synthetic
+    videos, which all have the same length; real videos go through shard_videos below)."""
     base, rem = divmod(n_items, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_videos(seg_lens, world):
+    """Whole videos to ranks as the reference's distributed test does (VIDSeqDataset.get_indices,
+    imagenet_vid_sequence.py:117-158): videos stay in order; a rank takes videos while its frame count stays
+    within ceil(total_frames / world), the video that would exceed it opens the next rank, and the last rank
+    takes everything that is left.  Returns, per rank, the list of video indices (pinned against the
+    reference's own method by tests/golden/ref_shard_golden.json)."""
+    avg = -(-int(sum(seg_lens)) // world)
+    out = [[] for _ in range(world)]
+    rank, used = 0, 0
+    for v, n in enumerate(seg_lens):
+        if used + n > avg and rank != world - 1:
+            rank, used = rank + 1, 0
+        out[rank].append(v)
+        used += n
+    return out
 
 
 def all_gather_rows(z, group=None):

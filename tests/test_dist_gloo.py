@@ -131,3 +131,18 @@ def test_single_process_is_identity():
     sup = iv.gather_support(z, 2, 4)
     assert [tuple(s.hi.shape) for s in sup] == [(4, 4)] * 3
     assert torch.equal(sup[2].hi, torch.cat([z.hi[0:2], z.hi[2:4]]))
+
+
+def test_shard_videos_matches_reference_get_indices():
+    """Multi-GPU partition of real videos: tests/golden/ref_shard_golden.json holds what the REFERENCE's own
+    VIDSeqDataset.get_indices (imagenet_vid_sequence.py:117-158, cut out of the file and run on a bare object,
+    tests/golden/make_shard_golden.py) hands to each rank for 20 seeded (video lengths, world size) cases,
+    including ranks that receive nothing; intervideo.shard_videos reproduces every one."""
+    import json
+    from hvrnet_b200 import intervideo as iv
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_shard_golden.json')))
+    assert len(cases) == 20 and any([] in c['videos'] for c in cases)
+    for c in cases:
+        got = iv.shard_videos(c['seg_lens'], c['world'])
+        assert got == c['videos']
+        assert [sum(c['seg_lens'][v] for v in r) for r in got] == c['frames']

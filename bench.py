@@ -452,27 +452,63 @@ def main():
         wh = torch.rand(Tn * 300, 2, generator=g) * 380 + 16
         rois = torch.stack([(torch.arange(Tn * 300) // 300).float(), x1, y1, (x1 + wh[:, 0]).clamp(max=999),
                             (y1 + wh[:, 1]).clamp(max=599)], 1).to(dev)
-        fn = lambda: ops.roi_align(feat, rois, feat_nhwc=True, out_nhwc=True, want_split=True, want_f32=False)
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        reps = 10
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        us = a.elapsed_time(b) / reps * 1e3
+        def time_us(fn, reps=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps * 1e3
+        # the pipeline's variant (separable FMA evaluation, 1e-5 relative to the strict one) and its bit-exact twin
+        us = time_us(lambda: ops.roi_align(feat, rois, feat_nhwc=True, out_nhwc=True, want_split=True, want_f32=False,
+                                           arithmetic='fast'))
+        us_strict = time_us(lambda: ops.roi_align(feat, rois, feat_nhwc=True, out_nhwc=True, want_split=True,
+                                                  want_f32=False, arithmetic='strict'))
         nbytes = 17510256.0 * Tn           # write 15 052 800 + map 2 451 456 + rois 6 000 per frame
         hbm_peak, src = 6650.0, 'fallback (B200_PROFILING.md: 6.65 TB/s)'
         k_, v_ = _measured_peak(peaks, ('hbm',), ('burst', 'copy'), 1000.0, 10000.0)
         if k_:
             hbm_peak, src = v_, 'MEASURED_PEAKS.json ' + k_
         gbs = nbytes / us / 1e3
-        return {'bound': 'hbm', 'kernel': 'roi_align_sn2_kernel (one CTA per RoI, taps staged in smem, LDG.128 along C, y-sample taps reused from registers)', 'frames': Tn,
-                'rois': Tn * 300, 'us_per_launch': us, 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
-                'frac': gbs / hbm_peak, 'peak_source': src, 'algorithmic_bytes': nbytes}
+        out = {'bound': 'hbm', 'kernel': 'roi_align_sep_kernel (one CTA per RoI, thread = output column x 4 channels, rows of the RoI '
+                                         'interpolated once along x with merged column taps, LDG.128 along C, FMA)', 'frames': Tn,
+               'rois': Tn * 300, 'us_per_launch': us, 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+               'frac': gbs / hbm_peak, 'peak_source': src, 'algorithmic_bytes': nbytes,
+               'strict_twin': {'kernel': 'roi_align_sn2_kernel (bit-exact with the reference built -fmad=false)',
+                               'us_per_launch': us_strict, 'achieved': nbytes / us_strict / 1e3,
+                               'frac': nbytes / us_strict / 1e3 / hbm_peak}}
+        # SURVEY.md 8d last row, "existing GPU kernel" bar: the REFERENCE's own RoIAlign / NMS CUDA ops, compiled
+        # unmodified for sm_100a into oracle/_ref (checker code: timed here beside ours, after every timed region of
+        # the product; never on the product path), on the same launch.  NCHW fp32 in / out as the reference lays it out.
+        try:
+            from oracle import build as obuild
+            ref_roi, ref_nms = obuild.load_ref_roi_align(True), obuild.load_ref_nms_cuda()
+        except Exception:                                     # noqa: BLE001
+            ref_roi = ref_nms = None
+        if ref_roi is not None:
+            fc = feat.permute(0, 3, 1, 2).contiguous()
+            o_ref = fc.new_zeros(Tn * 300, 256, 7, 7)
+            us_ref = time_us(lambda: ref_roi.forward(fc, rois, 7, 7, 1 / 16., 2, o_ref), reps=5)
+            del o_ref, fc
+            out['vs_reference_kernel'] = {'reference_us_per_launch': us_ref, 'speedup': us_ref / us,
+                                          'speedup_strict_twin': us_ref / us_strict,
+                                          'reference': 'mmdet/ops/roi_align/src/roi_align_kernel.cu built unmodified for sm_100a '
+                                                       '(oracle/_ref), NCHW fp32 output'}
+        if ref_nms is not None:
+            n = 6000
+            c = torch.rand(n, 2, generator=g) * torch.tensor([900., 500.])
+            wh_ = torch.rand(n, 2, generator=g) * 200 + 8
+            d = torch.cat([c, c + wh_, torch.rand(n, 1, generator=g)], 1).to(dev)
+            us_nms_ref = time_us(lambda: ref_nms.nms(d, 0.7), reps=5)
+            us_nms = time_us(lambda: ops.nms(d, 0.7), reps=5)
+            out['nms_6000'] = {'us_per_call': us_nms, 'reference_us_per_call': us_nms_ref, 'speedup': us_nms_ref / us_nms,
+                               'note': 'hvr_nms vs mmdet/ops/nms/src/nms_kernel.cu (oracle/_ref), n = 6000, IoU 0.7, both '
+                                       'include their count read-back; identical kept indices (tests)'}
+        return out
     roi_rf = roi_align_roofline()
 
     # extra, clearly separate figure: the streaming scheduler - per-frame caches of

@@ -58,6 +58,8 @@ SIGNATURES = {
     'hvr_maxpool3x3s2_split': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp]),
     'hvr_roi_align_fwd': (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_int,
                                   c_vp, c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    'hvr_roi_align_fwd_fast': (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_int,
+                                       c_vp, c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),
     'hvr_nms_workspace_bytes': (c_sz, [c_int]),
     'hvr_nms': (c_int, [c_vp, c_int, c_f32, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'hvr_rpn_workspace_bytes': (c_sz, [c_int, c_int, c_int]),
@@ -70,9 +72,14 @@ SIGNATURES = {
     'hvr_det_postprocess_batched': (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int,
                                             ctypes.POINTER(c_f32), c_f32, c_f32, c_f32, c_int, c_f32, c_f32, c_int,
                                             c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'hvr_det_postprocess_batched_ex': (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int,
+                                               ctypes.POINTER(c_f32), c_f32, c_f32, c_f32, c_int, c_f32, c_f32, c_int,
+                                               c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'hvr_preprocess_u8': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_f32),
                                   ctypes.POINTER(c_f32), c_vp, c_vp]),
     'hvr_softmax_rows_split': (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    'hvr_softmax_rows_split_masked': (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_int,
+                                              c_vp]),
     'hvr_video_descriptor_workspace_bytes': (c_sz, [c_int, c_int, c_int]),
     'hvr_video_descriptor': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
     'hvr_support_select': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),

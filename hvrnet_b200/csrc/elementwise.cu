@@ -269,10 +269,22 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* red, 
 }
 // One CTA per row.  Vector path (ld_s % 4 == 0, ld_p % 4 == 0, 16-byte aligned rows): LDG.128 of
 // the logits, row cached in registers, 8-byte packed bf16 stores of hi and lo.
+// Optional key mask (ragged proposal sets inside fixed row blocks): the columns are n_segs blocks of `slot`
+// keys (the frames of a window, then the support key frames); only the first counts[problem][seg] keys of a
+// block are proposals, the rest take no part in the softmax (probability exactly 0).  problem = row /
+// rows_per_problem.  counts == nullptr: no mask (the arithmetic below is then untouched).
+struct SegMask {
+  const int* counts;
+  int n_segs, slot, rows_per_problem;
+};
+__device__ __forceinline__ int seg_limit(const SegMask& m, int row, int c) {
+  const int seg = c / m.slot;
+  return seg * m.slot + m.counts[(size_t)(row / m.rows_per_problem) * m.n_segs + seg];
+}
 __global__ void __launch_bounds__(SM_THREADS) softmax_rows_kernel(const float* __restrict__ S, int cols, long long ld_s,
                                                                   __nv_bfloat16* __restrict__ phi,
                                                                   __nv_bfloat16* __restrict__ plo, long long ld_p,
-                                                                  int vec_ok) {
+                                                                  int vec_ok, const SegMask mask) {
   __shared__ float red[SM_THREADS / 32];
   __shared__ float bcast;
   const int row = blockIdx.x, tid = threadIdx.x;
@@ -292,12 +304,20 @@ __global__ void __launch_bounds__(SM_THREADS) softmax_rows_kernel(const float* _
         if (c + 1 >= cols) v[j].y = -INFINITY;
         if (c + 2 >= cols) v[j].z = -INFINITY;
         if (c + 3 >= cols) v[j].w = -INFINITY;
+        if (mask.counts) {                   // slot % 4 == 0 on this path: the group lies inside one block
+          const int lim = seg_limit(mask, row, c);
+          if (c >= lim) v[j].x = -INFINITY;
+          if (c + 1 >= lim) v[j].y = -INFINITY;
+          if (c + 2 >= lim) v[j].z = -INFINITY;
+          if (c + 3 >= lim) v[j].w = -INFINITY;
+        }
         mx = fmaxf(mx, fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w)));
       } else {
         v[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
       }
     }
     mx = block_reduce(mx, true, red, &bcast);
+    if (mx == -INFINITY) mx = 0.f;           // every key masked: probabilities 0 (exp(-inf) = 0, inv = 0 below)
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < SM_VEC; ++j) {
@@ -307,7 +327,7 @@ __global__ void __launch_bounds__(SM_THREADS) softmax_rows_kernel(const float* _
       sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
     }
     sum = block_reduce(sum, false, red, &bcast);
-    const float inv = 1.0f / sum;
+    const float inv = sum > 0.f ? 1.0f / sum : 0.f;
     const int npv = (int)(ld_p >> 2);
 #pragma unroll
     for (int j = 0; j < SM_VEC; ++j) {
@@ -333,16 +353,20 @@ __global__ void __launch_bounds__(SM_THREADS) softmax_rows_kernel(const float* _
     return;
   }
   // scalar path: any alignment, any length (re-reads the row)
+  auto live = [&](int c) { return mask.counts == nullptr || c < seg_limit(mask, row, c); };
   float mx = -INFINITY;
-  for (int c = tid; c < cols; c += SM_THREADS) mx = fmaxf(mx, __ldg(s + c));
+  for (int c = tid; c < cols; c += SM_THREADS)
+    if (live(c)) mx = fmaxf(mx, __ldg(s + c));
   mx = block_reduce(mx, true, red, &bcast);
+  if (mx == -INFINITY) mx = 0.f;
   float sum = 0.f;
-  for (int c = tid; c < cols; c += SM_THREADS) sum += expf(__ldg(s + c) - mx);
+  for (int c = tid; c < cols; c += SM_THREADS)
+    if (live(c)) sum += expf(__ldg(s + c) - mx);
   sum = block_reduce(sum, false, red, &bcast);
-  const float inv = 1.0f / sum;
+  const float inv = sum > 0.f ? 1.0f / sum : 0.f;
   for (int c = tid; c < ld_p; c += SM_THREADS) {
     __nv_bfloat16 h, l;
-    split2(c < cols ? expf(__ldg(s + c) - mx) * inv : 0.f, h, l);
+    split2((c < cols && live(c)) ? expf(__ldg(s + c) - mx) * inv : 0.f, h, l);
     ph[c] = h;
     pl[c] = l;
   }
@@ -448,7 +472,21 @@ extern "C" int hvr_softmax_rows_split(const float* S, int rows, int cols, int64_
   const int vec_ok = (ld_s % 4 == 0) && (ld_p % 4 == 0) && ((reinterpret_cast<uintptr_t>(S) & 15u) == 0) &&
                      ((reinterpret_cast<uintptr_t>(p_hi) & 7u) == 0) && ((reinterpret_cast<uintptr_t>(p_lo) & 7u) == 0);
   softmax_rows_kernel<<<rows, SM_THREADS, 0, ST(stream)>>>(S, cols, ld_s, (__nv_bfloat16*)p_hi,
-                                                           (__nv_bfloat16*)p_lo, ld_p, vec_ok);
+                                                           (__nv_bfloat16*)p_lo, ld_p, vec_ok, SegMask{nullptr, 0, 1, 1});
+  HVR_LAUNCHED();
+  return HVR_OK;
+}
+extern "C" int hvr_softmax_rows_split_masked(const float* S, int rows, int cols, int64_t ld_s, hvr_bf16* p_hi,
+                                             hvr_bf16* p_lo, int64_t ld_p, const int* seg_counts, int n_segs,
+                                             int slot, int rows_per_problem, void* stream) {
+  if (!S || !p_hi || !p_lo || cols < 1 || cols > ld_s || cols > ld_p) return HVR_ERR_ARG;
+  if (!seg_counts || n_segs < 1 || slot < 1 || rows_per_problem < 1 || (int64_t)n_segs * slot < cols) return HVR_ERR_ARG;
+  if (rows == 0) return HVR_OK;
+  const int vec_ok = (ld_s % 4 == 0) && (ld_p % 4 == 0) && (slot % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(S) & 15u) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(p_hi) & 7u) == 0) && ((reinterpret_cast<uintptr_t>(p_lo) & 7u) == 0);
+  softmax_rows_kernel<<<rows, SM_THREADS, 0, ST(stream)>>>(S, cols, ld_s, (__nv_bfloat16*)p_hi, (__nv_bfloat16*)p_lo,
+                                                           ld_p, vec_ok, SegMask{seg_counts, n_segs, slot, rows_per_problem});
   HVR_LAUNCHED();
   return HVR_OK;
 }

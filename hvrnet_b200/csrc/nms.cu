@@ -500,9 +500,17 @@ __global__ void det_decode_kernel(const float* __restrict__ rois, const float* _
                                   const float* __restrict__ reg, long long ld_reg, int n, int n_cls, float s0,
                                   float s1, float s2, float s3, float img_h, float img_w, float scale_factor,
                                   int rescale, float max_ratio, float* __restrict__ scores,
-                                  float4* __restrict__ boxes) {
+                                  float4* __restrict__ boxes, const int* __restrict__ n_valid = nullptr,
+                                  int rows_per_problem = 0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (n_valid != nullptr && (i % rows_per_problem) >= n_valid[i / rows_per_problem]) {
+    // row beyond this problem's proposal count (a frame that yielded fewer than max_num proposals):
+    // score 0 in every class -> below any score threshold, never a candidate
+    for (int k = 0; k < n_cls; ++k) scores[(size_t)i * n_cls + k] = 0.f;
+    boxes[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
   const float* c = cls + (size_t)i * ld_cls;
   float mx = -INFINITY;
   for (int k = 0; k < n_cls; ++k) mx = fmaxf(mx, c[k]);
@@ -641,9 +649,11 @@ __global__ void __launch_bounds__(256) det_emit_batched_kernel(const int* __rest
                                                                const float4* __restrict__ boxes, int n, int n_cls,
                                                                int max_per_img, float* __restrict__ dets,
                                                                long long* __restrict__ labels,
-                                                               int* __restrict__ n_dets) {
+                                                               int* __restrict__ n_dets,
+                                                               int* __restrict__ roi_idx = nullptr) {
   const int total = (n_cls - 1) * n;
   const int g = blockIdx.y;
+  if (roi_idx) roi_idx += (size_t)g * max_per_img;
   flags += (size_t)g * total;
   fscan += (size_t)g * total;          // exclusive scan over ALL problems: subtract this problem's base
   pos_sorted += (size_t)g * total;
@@ -662,6 +672,7 @@ __global__ void __launch_bounds__(256) det_emit_batched_kernel(const int* __rest
       dets[o * 5 + 0] = b.x; dets[o * 5 + 1] = b.y; dets[o * 5 + 2] = b.z; dets[o * 5 + 3] = b.w;
       dets[o * 5 + 4] = scores[(size_t)i * n_cls + c];
       labels[o] = c - 1;
+      if (roi_idx) roi_idx[o] = i;
     }
   } else {
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < max_per_img; o += gridDim.x * blockDim.x) {
@@ -671,6 +682,7 @@ __global__ void __launch_bounds__(256) det_emit_batched_kernel(const int* __rest
       dets[o * 5 + 0] = b.x; dets[o * 5 + 1] = b.y; dets[o * 5 + 2] = b.z; dets[o * 5 + 3] = b.w;
       dets[o * 5 + 4] = scores[(size_t)i * n_cls + c];
       labels[o] = c - 1;
+      if (roi_idx) roi_idx[o] = i;
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) n_dets[g] = min(count, max_per_img);
@@ -782,6 +794,17 @@ extern "C" int hvr_det_postprocess_batched(const float* rois, const float* cls, 
                                            float img_h, float img_w, float scale_factor, int rescale,
                                            float score_thr, float iou_thr, int max_per_img, float* dets,
                                            int64_t* labels, int* n_dets, void* ws, size_t ws_bytes, void* stream) {
+  return hvr_det_postprocess_batched_ex(rois, cls, ld_cls, reg, ld_reg, G, n, n_cls, stds4_host, img_h, img_w,
+                                        scale_factor, rescale, score_thr, iou_thr, max_per_img, nullptr, dets, labels,
+                                        n_dets, nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int hvr_det_postprocess_batched_ex(const float* rois, const float* cls, int64_t ld_cls, const float* reg,
+                                              int64_t ld_reg, int G, int n, int n_cls, const float* stds4_host,
+                                              float img_h, float img_w, float scale_factor, int rescale,
+                                              float score_thr, float iou_thr, int max_per_img, const int* n_valid,
+                                              float* dets, int64_t* labels, int* n_dets, int* roi_idx, void* ws,
+                                              size_t ws_bytes, void* stream) {
   if (G < 1 || n < 1 || n_cls < 2 || !dets || !labels || !n_dets || max_per_img < 1 || !stds4_host) return HVR_ERR_ARG;
   if (!rois || !cls || !reg) return HVR_ERR_ARG;
   if (n > 2048 || G > 4096) return HVR_ERR_UNSUPPORTED;
@@ -807,7 +830,7 @@ extern "C" int hvr_det_postprocess_batched(const float* rois, const float* cls, 
   det_decode_kernel<<<hvr_cdiv((int64_t)G * n, 128), 128, 0, st>>>(rois, cls, ld_cls, reg, ld_reg, G * n, n_cls,
                                                                   stds4_host[0], stds4_host[1], stds4_host[2],
                                                                   stds4_host[3], img_h, img_w, scale_factor, rescale,
-                                                                  max_ratio, scores, boxes);
+                                                                  max_ratio, scores, boxes, n_valid, n);
   HVR_LAUNCHED();
   nms_mask_kernel<<<dim3(nw, nw, G), 64, 0, st>>>(boxes, nullptr, n, nw, iou_thr, 1, 0, mask);
   HVR_LAUNCHED();
@@ -830,7 +853,8 @@ extern "C" int hvr_det_postprocess_batched(const float* rois, const float* cls, 
   HVR_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, keys_in, keys_out, pos_in, pos_out, total, 0, 32 + gbits, st));
   g_hvr_launches.fetch_add(1);
   det_emit_batched_kernel<<<dim3(hvr_cdiv(per, 256), G), 256, 0, st>>>(flags, fscan, pos_out, scores, boxes, n, n_cls,
-                                                                      max_per_img, dets, (long long*)labels, n_dets);
+                                                                      max_per_img, dets, (long long*)labels, n_dets,
+                                                                      roi_idx);
   HVR_LAUNCHED();
   return HVR_OK;
 }

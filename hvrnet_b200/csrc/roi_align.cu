@@ -23,6 +23,7 @@
 //            leaves as one contiguous, fully coalesced block.
 #include "common.cuh"
 #include "roi_align_bin.cuh"
+#include "roi_align_sep.cuh"
 
 #ifndef SN2_MIN_CTAS
 #define SN2_MIN_CTAS 4
@@ -194,6 +195,33 @@ __global__ void __launch_bounds__(256, SN2_MIN_CTAS) roi_align_sn2_kernel(
   }
 }
 
+// Fast variant of the pipeline's path (sample_num == 2, NHWC rows out): the separable evaluation of
+// roi_align_sep.cuh.  One CTA per RoI, thread = (output column q, 4-channel group); the 2*ph y samples of the
+// RoI are computed once into shared memory, the <= 4 merged column taps of q live in registers; every thread
+// walks the RoI's rows top to bottom and writes its ph outputs.  All branches depend on the RoI only (rows)
+// or on q only (warp-uniform when C % 128 == 0).  Explicit fmaf: independent of this file's -fmad=false.
+template <int MINB>
+__global__ void __launch_bounds__(448, MINB) roi_align_sep_kernel(
+    const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
+    float scale, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+    long long ld_split) {
+  __shared__ RowTap rows[32];
+  const int roi = blockIdx.x;
+  const RoiGeom g = roi_geom(rois + (size_t)roi * 5, scale, ph, pw, n_imgs);
+  if ((int)threadIdx.x < 2 * ph) rows[threadIdx.x] = row_tap_sn2(g.sh, g.bh, threadIdx.x, H, (uint32_t)(W * C) * 4u);
+  const int cg = C >> 2;
+  const int q = threadIdx.x / cg, c4 = threadIdx.x - q * cg;
+  const ColTaps ct = col_taps_sn2(g.sw, g.bw, q, W, (uint32_t)C * 4u);
+  __syncthreads();
+  const TapLoad ld{reinterpret_cast<const char*>(feat + (size_t)g.b * H * W * C + c4 * 4)};
+  const size_t o_f32 = ((size_t)roi * ph * pw + q) * C + c4 * 4;
+  const size_t o_split = (size_t)roi * ld_split + (size_t)q * C + c4 * 4;
+  const size_t step = (size_t)pw * C;
+  roi_column_sep_sn2(rows, ph, ct, ld,
+                     [&](int p, const float4& v) { store_bin(v, out, out_hi, out_lo, o_f32 + p * step, o_split + p * step); },
+                     nullptr);
+}
+
 // Generic path (adaptive sample_num == 0, or very large sampling grids): reference-style, one
 // thread per output element, NHWC or NCHW output.
 __global__ void roi_align_generic_kernel(const float* __restrict__ feat, const float* __restrict__ rois, int n_rois,
@@ -232,12 +260,46 @@ __global__ void roi_align_generic_kernel(const float* __restrict__ feat, const f
 }
 
 int g_roi_variant = 0;   // test hook (hvr_debug_roi_variant): 0 = heuristic, 1 = always the per-bin kernel
+int g_sep_minb = 2;      // test hook (hvr_debug_roi_variant 2 / 3): resident CTAs per SM the fast kernel is built for
 
 }  // namespace
 
 extern "C" int hvr_debug_roi_variant(int v) {
+  if (v == 2 || v == 3) {          // occupancy variant of the fast kernel (experiments)
+    g_sep_minb = v;
+    return HVR_OK;
+  }
   if (v != 0 && v != 1) return HVR_ERR_ARG;
   g_roi_variant = v;
+  return HVR_OK;
+}
+
+// Fast arithmetic (roi_align_sep.cuh) where it applies - NHWC rows out, sample_num == 2, one CTA of
+// pw * C/4 <= 448 threads per RoI - else the strict kernels of hvr_roi_align_fwd.
+extern "C" int hvr_roi_align_fwd_fast(const float* feat, int feat_nhwc, const float* rois, int n_rois, int n_imgs,
+                                      int C, int H, int W, int ph, int pw, float spatial_scale, int sample_num,
+                                      float* out, int out_layout, hvr_bf16* out_hi, hvr_bf16* out_lo,
+                                      int64_t ld_split, float* ws, void* stream) {
+  const bool sep = feat_nhwc && out_layout == 1 && sample_num == 2 && C >= 4 && C % 4 == 0 && pw * (C >> 2) <= 448 &&
+                   2 * ph <= 32 && g_roi_variant == 0;
+  if (!sep)
+    return hvr_roi_align_fwd(feat, feat_nhwc, rois, n_rois, n_imgs, C, H, W, ph, pw, spatial_scale, sample_num, out,
+                             out_layout, out_hi, out_lo, ld_split, ws, stream);
+  if (n_rois == 0) return HVR_OK;
+  if (!feat || !rois || n_rois < 0 || n_imgs < 1 || H < 1 || W < 1 || ph < 1 || pw < 1) return HVR_ERR_ARG;
+  if (!out && !out_hi) return HVR_ERR_ARG;
+  if ((out_hi == nullptr) != (out_lo == nullptr)) return HVR_ERR_ARG;
+  if (out_hi && (ld_split < (int64_t)ph * pw * C || ld_split % 4 != 0)) return HVR_ERR_ARG;
+  if ((size_t)H * W * C >= (1u << 30)) return HVR_ERR_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int threads = pw * (C >> 2);
+  if (g_sep_minb == 3)
+    roi_align_sep_kernel<3><<<n_rois, threads, 0, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out,
+                                                        (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_split);
+  else
+    roi_align_sep_kernel<2><<<n_rois, threads, 0, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out,
+                                                        (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_split);
+  HVR_LAUNCHED();
   return HVR_OK;
 }
 

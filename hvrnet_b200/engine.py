@@ -184,6 +184,12 @@ def pack_head(sd, device, kind='hrnmp', prefix='bbox_head.', roi_channels=256, r
             s = 'selsa_%d.' % k
             P['q%d' % k] = lin(s + 'q_data_fc_%d' % k)
             P['k%d' % k] = lin(s + 'k_data_fc_%d' % k)
+            # stages whose queries are all rows (1, 3): q_data_fc_k and k_data_fc_k read the same X
+            # (hrnmp_bbox_head.py:282-291) -> ONE GEMM with N = 2048, columns [Q | K]; X is streamed once
+            if k % 2 == 1:
+                P['qk%d' % k] = pack_linear(
+                    torch.cat([sd[prefix + s + 'q_data_fc_%d.weight' % k], sd[prefix + s + 'k_data_fc_%d.weight' % k]], 0),
+                    torch.cat([sd[prefix + s + 'q_data_fc_%d.bias' % k], sd[prefix + s + 'k_data_fc_%d.bias' % k]], 0), device)
             P['o%d' % k] = lin(s + 'linear_out_%d' % k)
     # fc_cls and fc_reg share their input: one GEMM, columns [cls | reg]
     def clsreg(c, r):
@@ -304,6 +310,18 @@ def lin(a, lp, relu=False, res=None, want_split=True, want_f32=False, want_T=Fal
     return (out if want_split else None), of, oT
 
 
+# q_data_fc_k and k_data_fc_k of an all-row stage as one N = 2048 GEMM (False: two GEMMs, the same bits)
+FUSE_QK = True
+
+
+def _qk(P, idx, X, **kw):
+    """-> (Q, K) as column halves of one [M, 2048] product (row pitch 2048)."""
+    lp = P['qk%d' % idx]
+    D = lp.n // 2
+    QK, _, _ = lin(X, lp, **kw)
+    return Split(QK.hi[:, :D], QK.lo[:, :D]), Split(QK.hi[:, D:2 * D], QK.lo[:, D:2 * D])
+
+
 def relation(P, idx, X, XT, q_range=None, res=None, relu=True, extra=None, **kw):
     """SELSA relation block idx on X Split [N,D] (XT = X^T Split [D, ld>=N]).
     Returns relu(res + NL(X)) (Split [Nq, D]).  hrnmp_bbox_head.py:216-355.
@@ -317,9 +335,12 @@ def relation(P, idx, X, XT, q_range=None, res=None, relu=True, extra=None, **kw)
         XkT.lo[:, :Nk] = Xk.lo.t()
     else:
         Xk, Nk, XkT = X, N, XT
-    Xq = X if q_range is None else X[q_range[0]:q_range[0] + q_range[1]]
-    Q, _, _ = lin(Xq, P['q%d' % idx], **kw)
-    K, _, _ = lin(Xk, P['k%d' % idx], **kw)
+    if q_range is None and extra is None and FUSE_QK and ('qk%d' % idx) in P:
+        Q, K = _qk(P, idx, X, **kw)
+    else:
+        Xq = X if q_range is None else X[q_range[0]:q_range[0] + q_range[1]]
+        Q, _, _ = lin(Xq, P['q%d' % idx], **kw)
+        K, _, _ = lin(Xk, P['k%d' % idx], **kw)
     # S = Q K^T / sqrt(D)  (1/32 for D=1024: exact power of two)
     _, S, _ = ops.linear(Q, K, Nk, alpha=1.0 / math.sqrt(float(D)), want_split=False, want_f32=True, **kw)
     Pm = ops.softmax_rows_split(S, Nk)
@@ -344,12 +365,12 @@ def _key_rows(X, V, Npad, s, n):
 
 def relation_batched(P, idx, X, XT, V, N, Npad, q_range=None, res=None, relu=True, **kw):
     D = X.shape[1]
-    if q_range is None:
-        Xq, nq = X, Npad
+    if q_range is None and FUSE_QK and ('qk%d' % idx) in P:
+        Q, K = _qk(P, idx, X, **kw)
     else:
-        Xq, nq = _key_rows(X, V, Npad, q_range[0], q_range[1]), q_range[1]
-    Q, _, _ = lin(Xq, P['q%d' % idx], **kw)
-    K, _, _ = lin(X, P['k%d' % idx], **kw)
+        Xq = X if q_range is None else _key_rows(X, V, Npad, q_range[0], q_range[1])
+        Q, _, _ = lin(Xq, P['q%d' % idx], **kw)
+        K, _, _ = lin(X, P['k%d' % idx], **kw)
     # the V per-video products Q_v K_v^T and P_v X_v as ONE launch each (hvr_igemm with a per-image B
     # matrix): S [V*nq, N], softmax over all V*nq rows at once, O [V*nq, D]
     _, S = ops.bmm(Q, K, V, N, Npad * K.hi.stride(0), alpha=1.0 / math.sqrt(float(D)), want_split=False,

@@ -86,13 +86,17 @@ class _Packed(nn.Module):
     def __init__(self):
         super().__init__()
         self._hvr_packed = None
+        self._hvr_version = 0      # bumped whenever the parameters may have changed (CUDA graphs hold raw pointers
+                                   # into the packed copies: runtime.GraphRunner re-captures on a version change)
 
     def _load_from_state_dict(self, *args, **kwargs):
         self._hvr_packed = None
+        self._hvr_version += 1
         return super()._load_from_state_dict(*args, **kwargs)
 
     def _apply(self, fn, *a, **k):
         self._hvr_packed = None
+        self._hvr_version += 1
         return super()._apply(fn, *a, **k)
 
     def packed(self, device):
@@ -268,10 +272,14 @@ class RoIAlign(nn.Module):
             raise NotImplementedError   # roi_align.py:27-28
         return ops.roi_align(features, rois, self.out_size[0], self.spatial_scale, self.sample_num)
 
+    # arithmetic of the pipeline variant below: 'fast' (separable FMA evaluation, 1e-5 relative to the strict
+    # one) or 'strict' (bit-exact with the reference kernel).  forward() - the reference-facing op - is always strict.
+    pipeline_arithmetic = 'fast'
+
     def forward_nhwc_split(self, feat_nhwc, rois):
         """Pipeline variant: NHWC fp32 map -> Split [n, out*out*C] rows for fc_new_1."""
         return ops.roi_align(feat_nhwc, rois, self.out_size[0], self.spatial_scale, self.sample_num, feat_nhwc=True,
-                             out_nhwc=True, want_split=True, want_f32=False)[1]
+                             out_nhwc=True, want_split=True, want_f32=False, arithmetic=self.pipeline_arithmetic)[1]
 
     def __repr__(self):
         return '{}(out_size={}, spatial_scale={}, sample_num={})'.format(self.__class__.__name__, self.out_size,
@@ -403,6 +411,12 @@ class SelsaBBoxHead(BBoxHead):
                  dim=(1024, 1024, 1024), output_cur_only=False, conv_z=None, conv_g=None, *args, **kwargs):
         super().__init__(*args, **kwargs)
         assert tuple(dim) == (fc_feat_dim,) * 3 and not non_cur_space
+        # what _add_selsa_with_fc builds with the configs' defaults (hrnmp_bbox_head.py:146-149,339-347): no value
+        # projection v_data_fc_k (conv_g False), output projection linear_out_k present (conv_z True).  Other
+        # settings would need layers this path does not evaluate: refuse them instead of computing something else.
+        assert conv_z is None or all(bool(z) for z in conv_z), 'conv_z=False (no linear_out_k) is not on the hot path'
+        assert conv_g is None or not any(bool(g) for g in conv_g), 'conv_g=True (v_data_fc_k) is not on the hot path'
+        assert not output_cur_only, 'output_cur_only is not on the hot path'
         self.feat_dim = self.in_channels * self.roi_feat_area
         self.sampler_num, self.t_dim, self.imgs_per_video = sampler_num, t_dim, imgs_per_video
         self.nongt_dim = sampler_num * t_dim
@@ -523,6 +537,10 @@ class TwoStageDetector(nn.Module):
         pass
 
     _runner = None
+
+    def weights_version(self):
+        """Changes whenever a load_state_dict / .to() / _apply touched any packed module."""
+        return tuple(m._hvr_version for m in self.modules() if isinstance(m, _Packed))
 
     def enable_cuda_graphs(self, flag=True, capture=True):
         """Run the trunk and the window stage through captured CUDA graphs (runtime.GraphRunner):

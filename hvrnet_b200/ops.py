@@ -265,10 +265,14 @@ def bmm(a, b, V, n, b_batch_stride, alpha=1.0, want_split=True, want_f32=False, 
 # ----------------------------------------------------------------------------------------
 
 def roi_align(feat, rois, out_size=7, spatial_scale=1 / 16., sample_num=2, feat_nhwc=False, out_nhwc=False,
-              want_split=False, ld_split=None, want_f32=True):
+              want_split=False, ld_split=None, want_f32=True, arithmetic='strict'):
     """feat fp32 NCHW (reference layout) or NHWC; rois [n,5].  Returns fp32 output in the
     reference layout [n,C,ph,pw] (or [n,ph,pw,C] when out_nhwc), plus an optional Split
-    [n, ld_split] copy in NHWC order."""
+    [n, ld_split] copy in NHWC order.
+    arithmetic: 'strict' = every product and sum rounded in the reference's order (bit-exact with the
+    reference kernel built with -fmad=false and with the C oracle); 'fast' = the separable FMA evaluation
+    (hvr_roi_align_fwd_fast; NHWC in / NHWC out / sample_num 2, else the strict kernels), 1e-5 relative."""
+    assert arithmetic in ('strict', 'fast')
     _need_cuda(feat, rois)
     feat = feat.contiguous()
     rois = rois.contiguous().float()
@@ -288,10 +292,11 @@ def roi_align(feat, rois, out_size=7, spatial_scale=1 / 16., sample_num=2, feat_
         ld_split = ld_split or ph * pw * C
         sp = Split.empty((n, ld_split), dev)
     ws = None if feat_nhwc else torch.empty(feat.numel(), dtype=torch.float32, device=dev)
-    check(_lib.lib().hvr_roi_align_fwd(_p(feat), int(feat_nhwc), _p(rois), n, B, C, H, W, ph, pw, float(spatial_scale),
-                                       int(sample_num), _p(out), 1 if out_nhwc else 0,
-                                       _p(sp.hi) if sp else None, _p(sp.lo) if sp else None,
-                                       ld_split or 0, _p(ws), _stream()), 'hvr_roi_align_fwd')
+    fn = _lib.lib().hvr_roi_align_fwd_fast if arithmetic == 'fast' else _lib.lib().hvr_roi_align_fwd
+    check(fn(_p(feat), int(feat_nhwc), _p(rois), n, B, C, H, W, ph, pw, float(spatial_scale),
+             int(sample_num), _p(out), 1 if out_nhwc else 0,
+             _p(sp.hi) if sp else None, _p(sp.lo) if sp else None,
+             ld_split or 0, _p(ws), _stream()), 'hvr_roi_align_fwd')
     return (out, sp) if want_split else out
 
 
@@ -357,10 +362,14 @@ def det_postprocess(rois, cls, reg, img_shape, scale_factor=1.0, rescale=False, 
 
 
 def det_postprocess_batched(rois, cls, reg, G, img_shape, scale_factor=1.0, rescale=False, stds=(0.1, 0.1, 0.2, 0.2),
-                            score_thr=0.001, iou_thr=0.3, max_per_img=300, n_cls=None):
+                            score_thr=0.001, iou_thr=0.3, max_per_img=300, n_cls=None, n_valid=None, want_idx=False,
+                            out=None):
     """G problems of n rois each in one launch per stage: rois [G*n,5], cls [G*n,>=n_cls], reg [G*n,>=4]
     (row-strided views allowed; problem g = rows [g*n, (g+1)*n)).  Returns dets [G,max_per_img,5],
-    labels [G,max_per_img] int64, n_dets [G] int32; per problem bit-identical to det_postprocess."""
+    labels [G,max_per_img] int64, n_dets [G] int32; per problem bit-identical to det_postprocess.
+    n_valid: optional device int32 [G] - only the first n_valid[g] rows of problem g are proposals.
+    want_idx: also return roi_idx int32 [G,max_per_img] (the row every detection came from).
+    out: optional preallocated (dets, labels, n_dets) - e.g. views of one packed result buffer."""
     _need_cuda(rois, cls, reg)
     L = _lib.lib()
     dev = rois.device
@@ -371,25 +380,41 @@ def det_postprocess_batched(rois, cls, reg, G, img_shape, scale_factor=1.0, resc
     assert cls.stride(1) == 1 and reg.stride(1) == 1
     wsb = L.hvr_det_batched_workspace_bytes(G, n, n_cls)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-    dets = torch.zeros((G, max_per_img, 5), dtype=torch.float32, device=dev)
-    labels = torch.zeros((G, max_per_img), dtype=torch.long, device=dev)
-    nd = torch.zeros(G, dtype=torch.int32, device=dev)
+    if out is None:
+        dets = torch.zeros((G, max_per_img, 5), dtype=torch.float32, device=dev)
+        labels = torch.zeros((G, max_per_img), dtype=torch.long, device=dev)
+        nd = torch.zeros(G, dtype=torch.int32, device=dev)
+    else:
+        dets, labels, nd = out
+        assert dets.is_contiguous() and labels.is_contiguous() and nd.is_contiguous()
+        assert dets.numel() == G * max_per_img * 5 and labels.dtype == torch.long and nd.dtype == torch.int32
+    idx = torch.zeros((G, max_per_img), dtype=torch.int32, device=dev) if want_idx else None
     stds_c = (ctypes.c_float * 4)(*stds)
-    check(L.hvr_det_postprocess_batched(_p(rois), _p(cls), cls.stride(0), _p(reg), reg.stride(0), G, n, n_cls, stds_c,
-                                        float(img_shape[0]), float(img_shape[1]), float(scale_factor), int(rescale),
-                                        float(score_thr), float(iou_thr), int(max_per_img), _p(dets), _p(labels),
-                                        _p(nd), _p(ws), wsb, _stream()), 'hvr_det_postprocess_batched')
-    return dets, labels, nd
+    check(L.hvr_det_postprocess_batched_ex(_p(rois), _p(cls), cls.stride(0), _p(reg), reg.stride(0), G, n, n_cls,
+                                           stds_c, float(img_shape[0]), float(img_shape[1]), float(scale_factor),
+                                           int(rescale), float(score_thr), float(iou_thr), int(max_per_img),
+                                           _p(n_valid), _p(dets), _p(labels), _p(nd), _p(idx), _p(ws), wsb, _stream()),
+          'hvr_det_postprocess_batched_ex')
+    return (dets, labels, nd, idx) if want_idx else (dets, labels, nd)
 
 
-def softmax_rows_split(S, cols, ld_p=None):
-    """S fp32 [rows, ld_s] -> Split P [rows, ld_p], softmax over the first `cols` columns."""
+def softmax_rows_split(S, cols, ld_p=None, seg_counts=None, slot=0, rows_per_problem=0):
+    """S fp32 [rows, ld_s] -> Split P [rows, ld_p], softmax over the first `cols` columns.
+    seg_counts (device int32 [n_problems, n_segs]): key mask for ragged proposal sets - of every block of `slot`
+    columns only the first seg_counts[row // rows_per_problem][block] take part (hvr_softmax_rows_split_masked)."""
     _need_cuda(S)
     rows = S.shape[0]
     ld_p = ld_p or round_up(cols, 64)
     P = Split.empty((rows, ld_p), S.device)
-    check(_lib.lib().hvr_softmax_rows_split(_p(S), rows, cols, S.stride(0), _p(P.hi), _p(P.lo), ld_p, _stream()),
-          'hvr_softmax_rows_split')
+    if seg_counts is None:
+        check(_lib.lib().hvr_softmax_rows_split(_p(S), rows, cols, S.stride(0), _p(P.hi), _p(P.lo), ld_p, _stream()),
+              'hvr_softmax_rows_split')
+    else:
+        assert seg_counts.dtype == torch.int32 and seg_counts.is_contiguous() and seg_counts.dim() == 2
+        check(_lib.lib().hvr_softmax_rows_split_masked(_p(S), rows, cols, S.stride(0), _p(P.hi), _p(P.lo), ld_p,
+                                                       _p(seg_counts), seg_counts.shape[1], int(slot),
+                                                       int(rows_per_problem), _stream()),
+              'hvr_softmax_rows_split_masked')
     return P
 
 

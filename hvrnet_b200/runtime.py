@@ -78,7 +78,20 @@ class GraphRunner:
         self._window = {}
         self.replayed_launches = 0      # kernels launched through graph replays (bench.py gpu_launches)
         self._copy_stream = None
-        self._staged = None             # (id of the prefetched tensor, trunk already run, ready event)
+        self._staged = None             # (the prefetched tensor, trunk already run, ready event)
+        self._version = model.weights_version()
+
+    def _check_weights(self):
+        """The captured graphs read the packed weight tensors through raw pointers; a load_state_dict / .to() /
+        load_checkpoint after the capture frees them (models._Packed).  Drop every capture then: the next call
+        re-packs and re-captures."""
+        v = self.m.weights_version()
+        if v != self._version:
+            torch.cuda.synchronize()
+            self._trunk.clear()
+            self._window.clear()
+            self._staged = None
+            self._version = v
 
     # ------------------------------------------------------------------ input prefetch
     def prefetch(self, img, trunk=True):
@@ -86,6 +99,7 @@ class GraphRunner:
         (trunk=True) replay the trunk graph on them, so both overlap the current step's window
         graph; ``extract`` picks the result up when it is handed the same tensor.  All of the work
         still happens once per step, inside whatever region the caller times."""
+        self._check_weights()
         key = tuple(img.shape)
         c = self._trunk.get(key)
         if c is None:
@@ -100,7 +114,7 @@ class GraphRunner:
                 self._replay(c)
             ev = torch.cuda.Event()
             ev.record()
-        self._staged = (id(img), trunk, ev)
+        self._staged = (img, trunk, ev)             # holds the tensor: identity cannot be recycled while staged
 
     # ------------------------------------------------------------------ capture helper
     def _capture(self, fn):
@@ -133,6 +147,7 @@ class GraphRunner:
 
     # ------------------------------------------------------------------ trunk
     def extract(self, img):
+        self._check_weights()
         key = tuple(img.shape)
         c = self._trunk.get(key)
         if c is None:
@@ -144,11 +159,11 @@ class GraphRunner:
             c = self._capture(fn)
             c.inputs = buf
             self._trunk[key] = c
-        if self._staged is not None and self._staged[0] == id(img):
-            _, trunk_done, ev = self._staged
-            self._staged = None
-            torch.cuda.current_stream().wait_event(ev)   # frames (and trunk) staged by prefetch()
-            if not trunk_done:
+        staged, self._staged = self._staged, None
+        if staged is not None:
+            torch.cuda.current_stream().wait_event(staged[2])   # the side stream is done with the static buffers
+        if staged is not None and staged[0] is img and tuple(staged[0].shape) == key:
+            if not staged[1]:                                   # frames staged by prefetch(), trunk still to run
                 self._replay(c)
         else:
             c.inputs.copy_(img, non_blocking=True)      # H2D (pinned host) or D2D into the static buffer
@@ -176,6 +191,7 @@ class GraphRunner:
         RoIAlign run over all V*T frames at once, the relation head once per video).
         Returns, per video, the list of per-output (dets, labels) host tensors, or None for
         the videos whose speculation (every frame yields max_num proposals) failed."""
+        self._check_weights()
         m = self.m
         V, T = len(windows), len(windows[0])
         meta = img_meta[0]

@@ -77,8 +77,23 @@ def window_schedule(seg_len, window, rng=np.random, video_shuffle=False):
 
 def detect_video(model, frames, img_meta, window=None, rng=np.random, rescale=True, video_shuffle=False):
     """frames: sequence of preprocessed [1,3,H,W] CUDA tensors of ONE video.  Returns
-    {frame_offset: result} with one entry per emitted key frame (forward_feat results)."""
+    {frame_offset: result} with one entry per emitted key frame (forward_feat results).
+
+    C4 maps are kept only while a scheduled window can still use them: the schedule is drawn first (it is pure
+    index arithmetic on the RNG), the last use of every frame index is looked up, and a map is dropped right
+    after it - at most `window` + the current pad frames are alive (the reference's deque holds `window` maps,
+    tools/hnl_test.py:359-463), instead of one ~20 MB map per frame of a 2000-frame video.
+    Deviation from the reference's loop (documented next to the golden-trace test of window_schedule): windows
+    whose centre is a padding frame (offset -1), or that are shorter than `window`, are skipped here; the
+    reference still runs forward_feat on them and files the result under offset -1, where the later frames
+    overwrite it and the evaluation never reads it (tools/hnl_test.py:421-433)."""
     window = int(window or model.bbox_head.t_dim)
+    sched = [(idxs, key) for idxs, offs, key in window_schedule(len(frames), window, rng, video_shuffle)
+             if key >= 0 and len(idxs) == window]
+    last_use = {}
+    for n, (idxs, _) in enumerate(sched):
+        for i in idxs:
+            last_use[i] = n
     cache = {}
 
     def feat(i):
@@ -88,9 +103,10 @@ def detect_video(model, frames, img_meta, window=None, rng=np.random, rescale=Tr
 
     out = {}
     metas = [img_meta] * window
-    for idxs, offs, key in window_schedule(len(frames), window, rng, video_shuffle):
-        if key < 0 or len(idxs) != window:
-            continue
+    for n, (idxs, key) in enumerate(sched):
         out[key] = model(x=[feat(i) for i in idxs], img=None, img_meta=metas, forward_feat=True, return_loss=False,
                          rescale=rescale)
+        for i in set(idxs):
+            if last_use[i] == n:
+                del cache[i]
     return out

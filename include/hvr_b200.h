@@ -167,8 +167,20 @@ int hvr_roi_align_fwd(const float* feat, int feat_nhwc, const float* rois, int n
                       float* out, int out_layout, hvr_bf16* out_hi, hvr_bf16* out_lo,
                       int64_t ld_split, float* ws, void* stream);
 /* Test hook: 1 = always the generic per-bin kernel (16 loads per output vector, as the reference),
- * 0 = heuristic (sample_num 2 + out_layout 1 run roi_align_sn2_kernel, which reuses taps held in registers). */
+ * 0 = heuristic (sample_num 2 + out_layout 1 run roi_align_sn2_kernel, which reuses taps held in registers);
+ * 2 / 3 = resident CTAs per SM the fast kernel below is compiled for (experiments). */
 int hvr_debug_roi_variant(int v);
+/* Fast arithmetic for the pipeline (feat_nhwc = 1, out_layout = 1, sample_num = 2): the same average of
+ * bilinear samples evaluated separably - every map row of the RoI is interpolated once along x with the
+ * merged column weights of an output column, then combined along y - with fused multiply-adds
+ * (csrc/roi_align_sep.cuh).  Same sample positions, validity and clamping rules as the strict kernels; the
+ * summation order differs, so values agree with hvr_roi_align_fwd to a few ulp of the largest term (1e-5
+ * relative, the agreement between the reference's own default build, which nvcc contracts into FMAs, and its
+ * -fmad=false build), not bit for bit.  Other argument combinations run the strict kernels. */
+int hvr_roi_align_fwd_fast(const float* feat, int feat_nhwc, const float* rois, int n_rois, int n_imgs,
+                           int C, int H, int W, int ph, int pw, float spatial_scale, int sample_num,
+                           float* out, int out_layout, hvr_bf16* out_hi, hvr_bf16* out_lo,
+                           int64_t ld_split, float* ws, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * NMS.  Replaces nms_cuda.nms (nms_kernel.cu:71-136, strict `>`; strict_gt=0 gives
@@ -231,6 +243,18 @@ int hvr_det_postprocess_batched(const float* rois, const float* cls, int64_t ld_
                                 float score_thr, float iou_thr, int max_per_img, float* dets,
                                 int64_t* labels, int* n_dets, void* ws, size_t ws_bytes, void* stream);
 
+/* Extended form.  n_valid (optional, device int32 [G]): only the first n_valid[g] rows of problem g are
+ * proposals (a frame that yielded fewer than max_num proposals keeps its fixed row block; the rows behind
+ * the count score 0 in every class and never become candidates) - results equal those of a call with
+ * n = n_valid[g] rows.  roi_idx (optional, device int32 [G, max_per_img]): the row (roi) of every detection,
+ * i.e. the index information bbox_nms.py:36-61 carries implicitly (parity reports). */
+int hvr_det_postprocess_batched_ex(const float* rois, const float* cls, int64_t ld_cls, const float* reg,
+                                   int64_t ld_reg, int G, int n, int n_cls, const float* stds4_host,
+                                   float img_h, float img_w, float scale_factor, int rescale,
+                                   float score_thr, float iou_thr, int max_per_img, const int* n_valid,
+                                   float* dets, int64_t* labels, int* n_dets, int* roi_idx, void* ws,
+                                   size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Relation-head row softmax (hrnmp_bbox_head.py:332): P = softmax(S, dim=keys), written
  * as split bf16 for the P.V contraction.  S [rows, ld_s] fp32, P [rows, ld_p].
@@ -238,6 +262,15 @@ int hvr_det_postprocess_batched(const float* rois, const float* cls, int64_t ld_
  * ---------------------------------------------------------------------------------- */
 int hvr_softmax_rows_split(const float* S, int rows, int cols, int64_t ld_s, hvr_bf16* p_hi,
                            hvr_bf16* p_lo, int64_t ld_p, void* stream);
+/* The same with a key mask for ragged proposal sets kept in fixed row blocks (hnmb_rcnn.py:582-599 builds the
+ * key set from the ACTUAL per-frame proposal counts): the columns are n_segs blocks of `slot` keys - the T
+ * frames of the window, then the support key frames - and only the first seg_counts[problem][seg] keys of a
+ * block are proposals; the others get probability exactly 0 and do not enter the row maximum or sum, so a
+ * row equals the softmax over the compacted key set.  problem = row / rows_per_problem (one window per
+ * problem); seg_counts is a DEVICE int32 [n_problems, n_segs] array (no host round trip, CUDA-graph safe). */
+int hvr_softmax_rows_split_masked(const float* S, int rows, int cols, int64_t ld_s, hvr_bf16* p_hi,
+                                  hvr_bf16* p_lo, int64_t ld_p, const int* seg_counts, int n_segs, int slot,
+                                  int rows_per_problem, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Test-time image pipeline (next row N2).  Replaces the CPU DataLoader path Resize(keep_ratio)

@@ -18,9 +18,13 @@ for T, lo, hi in ((1, 16, 396), (15, 16, 396), (105, 16, 396), (105, 16, 112), (
     wh = torch.rand(n, 2, generator=g) * (hi - lo) + lo
     rois = torch.stack([(torch.arange(n) // 300).float(), x1, y1, (x1 + wh[:, 0]).clamp(max=999),
                         (y1 + wh[:, 1]).clamp(max=599)], 1).to(dev)
-    for variant in (1, 0):     # 1 = generic per-bin kernel (16 loads per output vector), 0 = sn2 kernel
+    # generic = per-bin kernel (16 loads per output vector), sn2 = strict tap-reuse kernel, fast2 / fast3 = the
+    # separable FMA kernel compiled for 2 / 3 resident CTAs per SM
+    for name, variant, arith in (('generic', 1, 'strict'), ('sn2', 0, 'strict'), ('fast2', 2, 'fast'), ('fast3', 3, 'fast')):
+        _lib.lib().hvr_debug_roi_variant(0)
         _lib.lib().hvr_debug_roi_variant(variant)
-        fn = lambda: ops.roi_align(feat, rois, feat_nhwc=True, out_nhwc=True, want_split=True, want_f32=False)
+        fn = lambda: ops.roi_align(feat, rois, feat_nhwc=True, out_nhwc=True, want_split=True, want_f32=False,
+                                   arithmetic=arith)
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
@@ -31,4 +35,26 @@ for T, lo, hi in ((1, 16, 396), (15, 16, 396), (105, 16, 396), (105, 16, 112), (
         b.record()
         torch.cuda.synchronize()
         us = a.elapsed_time(b) / 10 * 1e3
-        print('T=%d side %d-%d px variant=%s %.1f us  %.0f GB/s (algorithmic 17.51 MB/frame)' % (T, lo, hi, 'sn2' if variant == 0 else 'generic', us, 17510256.0 * T / us / 1e3))
+        print('T=%d side %d-%d px variant=%s %.1f us  %.0f GB/s (algorithmic 17.51 MB/frame)' % (T, lo, hi, name, us, 17510256.0 * T / us / 1e3))
+    _lib.lib().hvr_debug_roi_variant(0)
+    _lib.lib().hvr_debug_roi_variant(2)
+    # the reference's own CUDA op (oracle/_ref, compiled unmodified for sm_100a): NCHW map in, NCHW fp32 out
+    try:
+        from oracle import build as obuild
+        ref = obuild.load_ref_roi_align(True)
+    except Exception:                                         # noqa: BLE001
+        ref = None
+    if ref is not None:
+        fc = feat.permute(0, 3, 1, 2).contiguous()
+        out = fc.new_zeros(n, 256, 7, 7)
+        for _ in range(2):
+            ref.forward(fc, rois, 7, 7, 1 / 16., 2, out)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            ref.forward(fc, rois, 7, 7, 1 / 16., 2, out)
+        b.record()
+        torch.cuda.synchronize()
+        us = a.elapsed_time(b) / 5 * 1e3
+        print('T=%d side %d-%d px variant=reference_kernel %.1f us  %.0f GB/s' % (T, lo, hi, us, 17510256.0 * T / us / 1e3))

@@ -527,6 +527,59 @@ def test_roi_align_sn2_kernel_equals_generic_per_bin_kernel(cuda, C, out_size):
         assert torch.equal(bits(a), bits(b))
 
 
+@pytest.mark.parametrize('C,out_size', [(256, 7), (128, 7), (256, 3), (16, 7), (40, 3), (512, 7)])
+def test_roi_align_fast_variant_vs_strict(cuda, C, out_size):
+    """hvr_roi_align_fwd_fast (roi_align_sep_kernel: separable, fused multiply-add) against the strict kernel and
+    the C oracle.  Tolerance (the contract in include/hvr_b200.h): every element within 1e-5 of the largest
+    |reference| value of its RoI; bins the oracle evaluates to exactly 0 are exactly 0; the split rows are the
+    split of the fp32 rows.  C = 512 has no fast launch shape (7 * 128 threads > 448) and must fall back to the
+    strict kernel bit for bit."""
+    from hvrnet_b200 import ops
+    from oracle import cref
+    g = torch.Generator().manual_seed(31 + C)
+    feat = torch.randn(2, 38, 63, C, generator=g)
+    rois = _rois(g, 300, 2)
+    rois[4:40, 3:] = rois[4:40, 1:3] + torch.rand(36, 2, generator=g) * 60
+    rois[40, 1:] = torch.tensor([0., 0., 999., 599.])
+    rois[41, 1:] = torch.tensor([-17., 300., 5., 320.])
+    rois[42, 1:] = 0.                                                            # the pad RoI of a batched window
+    ref = cref.roi_align(feat, rois, out_size=out_size, feat_nhwc=True, out_nhwc=True)
+    f, r = feat.to(cuda), rois.to(cuda)
+    o, sp = ops.roi_align(f, r, out_size=out_size, feat_nhwc=True, out_nhwc=True, want_split=True, arithmetic='fast')
+    o = o.cpu()
+    if C == 512:
+        assert torch.equal(o.view(torch.int32), ref.view(torch.int32))
+        return
+    scale = ref.abs().flatten(1).amax(1).clamp_min(1e-30).view(-1, 1, 1, 1)
+    assert float(((o.double() - ref.double()).abs() / scale).max()) < 1e-5
+    dead = ref.abs().flatten(1).amax(1) == 0
+    assert bool(dead.any()) and not bool(o[dead].any())
+    sp2 = ops.split(o.to(cuda).view(o.shape[0], -1))
+    assert torch.equal(sp.hi.view(torch.int16), sp2.hi.view(torch.int16))
+    assert torch.equal(sp.lo.view(torch.int16), sp2.lo.view(torch.int16))
+    # split rows only (the pipeline's call) give the same bits
+    _, sp3 = ops.roi_align(f, r, out_size=out_size, feat_nhwc=True, out_nhwc=True, want_split=True, want_f32=False,
+                           arithmetic='fast')
+    assert torch.equal(sp.hi.view(torch.int16), sp3.hi.view(torch.int16))
+
+
+def test_roi_align_fast_variant_full_size(cuda):
+    """BASELINE.json size (15 frames x 300 proposals, 38x63x256 maps, one launch) through the fast variant:
+    1e-5 of each RoI's largest value against the C oracle on a sample of the RoIs."""
+    from hvrnet_b200 import ops
+    from oracle import cref
+    g = torch.Generator().manual_seed(13)
+    T, P = 15, 300
+    feat = torch.randn(T, 38, 63, 256, generator=g)
+    rois = _rois(g, T * P, T)
+    rois[:, 0] = torch.arange(T * P) // P
+    o = ops.roi_align(feat.to(cuda), rois.to(cuda), feat_nhwc=True, out_nhwc=True, arithmetic='fast')
+    pick = torch.arange(0, T * P, 37)
+    ref = cref.roi_align(feat, rois[pick], feat_nhwc=True, out_nhwc=True)
+    scale = ref.abs().flatten(1).amax(1).clamp_min(1e-30).view(-1, 1, 1, 1)
+    assert float(((o[pick].cpu().double() - ref.double()).abs() / scale).max()) < 1e-5
+
+
 def test_roi_align_full_size(cuda):
     """BASELINE.json size: 15 frames x 300 proposals on 38x63x256 maps in ONE launch, checked
     bit-exactly against the C oracle on a sample of the RoIs."""

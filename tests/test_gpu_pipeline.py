@@ -80,6 +80,26 @@ def test_head_hrnmp_and_selsa(world):
     assert _rel(c.cpu(), c_ref) < 1e-3 and _rel(r.cpu(), r_ref) < 1e-3
 
 
+def test_fused_qk_projection_bit_identical(world):
+    """The all-row stages evaluate q_data_fc_k and k_data_fc_k (hrnmp_bbox_head.py:282-291) as ONE GEMM with
+    N = 2048 (engine.FUSE_QK): per output element the same contraction in the same order, so the head outputs
+    are bit-identical to the two-GEMM evaluation."""
+    from hvrnet_b200 import engine
+    m, dev = world['model'], world['dev']
+    g = torch.Generator().manual_seed(9)
+    feats = torch.rand(640, 256, 7, 7, generator=g).to(dev)
+    outs = []
+    try:
+        for flag in (True, False):
+            engine.FUSE_QK = flag
+            cls, reg = m.bbox_head.forward_test(feats, [dict(start=128, length=200)])
+            outs.append([t.clone() for t in cls + reg])
+    finally:
+        engine.FUSE_QK = True
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
 def _match(res, ref, iou_thr=0.9, score_tol=2e-2):
     """Fraction of oracle detections (score > 0.05) matched by class, IoU and score."""
     import numpy as np

@@ -279,6 +279,79 @@ def test_roi_align_bin_core_load_count(tmp_path):
     assert 11.0 < v < 13.0, v                                 # bench.py's distribution: ~12 instead of 16
 
 
+def _sep_host_lib(tmp_path):
+    """g++ build of the fast variant's core (csrc/roi_align_sep.cuh) behind tests/host/roi_sep_host.cpp."""
+    import subprocess
+    so = str(tmp_path / 'libroi_sep_host.so')
+    subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-shared', '-fPIC', '-o', so,
+                           os.path.join(ROOT, 'tests', 'host', 'roi_sep_host.cpp')])
+    lib = ctypes.CDLL(so)
+    lib.sep_roi_align.restype = ctypes.c_longlong
+    return lib
+
+
+def _sep_host(lib, feat, rois, out_size=7, scale=1 / 16.):
+    import numpy as np
+    fp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    B, H, W, C = feat.shape
+    out = np.zeros((len(rois), out_size, out_size, C), np.float32)
+    loads = lib.sep_roi_align(fp(feat), fp(rois), len(rois), B, C, H, W, out_size, out_size, ctypes.c_float(scale),
+                              fp(out))
+    return out, loads
+
+
+def test_roi_align_separable_core_vs_oracle(tmp_path):
+    """The fast (separable, fused multiply-add) evaluation of roi_align_sep_kernel - same header, host build -
+    against the oracle's strict evaluation on the RoI population of the bit-exact test above: same sample
+    positions, validity and clamping, different summation order.  Tolerance (written here): every element within
+    1e-5 of the largest |reference| value of its RoI - the agreement the reference's own default (FMA-contracted)
+    build shows against its -fmad=false build - and bins the oracle evaluates to exactly 0 (all samples
+    outside the map) are exactly 0."""
+    import numpy as np
+    from oracle import cref
+    lib = _sep_host_lib(tmp_path)
+    rng = np.random.default_rng(0)
+    B, H, W, C = 2, 38, 63, 8
+    feat = rng.standard_normal((B, H, W, C)).astype(np.float32)
+    n = 3000
+    x1, y1 = rng.uniform(-40, 1000, n), rng.uniform(-40, 620, n)
+    w, h = np.exp(rng.uniform(0, np.log(1100), n)), np.exp(rng.uniform(0, np.log(700), n))
+    rois = np.stack([rng.integers(0, B, n).astype(np.float64), x1, y1, x1 + w, y1 + h], 1).astype(np.float32)
+    edge = np.array([[0, 0, 0, 999, 599], [1, -500, -500, -100, -100], [0, 990, 590, 1100, 700],
+                     [0, 100, 100, 100, 100], [1, 100, 100, 90, 90], [0, -16, -16, 0, 0], [0, 0, 0, 1007, 607],
+                     [1, 1500, 100, 1600, 200], [0, 1007, 607, 1007, 607], [1, -17, 300, 5, 320],
+                     [0, 300, -17.5, 320, 4], [0, 0, 0, 0, 0]], dtype=np.float32)
+    rois = np.concatenate([rois, edge])
+    for out_size in (7, 3):
+        out, loads = _sep_host(lib, feat, rois, out_size)
+        ref = cref.roi_align(torch.from_numpy(feat), torch.from_numpy(rois), out_size=out_size, feat_nhwc=True,
+                             out_nhwc=True).numpy()
+        scale = np.abs(ref).reshape(len(rois), -1).max(1).reshape(-1, 1, 1, 1)
+        err = np.abs(out.astype(np.float64) - ref) / np.maximum(scale, 1e-30)
+        assert float(err.max()) < 1e-5, float(err.max())
+        dead = (np.abs(ref).reshape(len(rois), -1).max(1) == 0)
+        assert dead.any() and not out[dead].any()
+        assert 0 < loads < 16 * len(rois) * out_size * out_size * C // 4
+
+
+def test_roi_align_separable_core_load_count(tmp_path):
+    """Pixel loads per output vector of the fast variant on bench.py's RoI distribution: the figure DESIGN.md
+    quotes (about 6, against 16 for the reference and ~12 for the tap-reuse kernel)."""
+    import numpy as np
+    lib = _sep_host_lib(tmp_path)
+    rng = np.random.default_rng(5)
+    feat = rng.standard_normal((1, 38, 63, 4)).astype(np.float32)
+    per_vec = lambda rois: _sep_host(lib, feat, np.asarray(rois, np.float32))[1] / (len(rois) * 49.)
+    n = 4000
+    x1, y1 = rng.uniform(0, 800, n), rng.uniform(0, 450, n)
+    wh = rng.uniform(16, 396, (n, 2))
+    rois = np.stack([np.zeros(n), x1, y1, np.minimum(x1 + wh[:, 0], 999), np.minimum(y1 + wh[:, 1], 599)], 1)
+    v = per_vec(rois)
+    print("loads per output vector:", v)
+    assert 4.0 < v < 8.0, v
+    assert per_vec([[0, 0, 0, 0, 0]]) <= 4.0 / 7 + 1e-9       # the pad RoI of a batched window: two rows x two columns
+
+
 def test_bench_measured_peaks_lookup():
     """bench.py reads the roofline denominators from the driver-written MEASURED_PEAKS.json whatever its exact
     key layout, and falls back to the profiling guide's figures when the file or the entry is missing."""

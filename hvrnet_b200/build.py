@@ -25,6 +25,7 @@ SOURCES = {
     'igemm_tc.cu': [],
     'preprocess.cu': ['-fmad=false'],
     'intervideo.cu': ['-fmad=false'],
+    'window.cu': ['-fmad=false'],
 }
 
 

@@ -351,70 +351,136 @@ def relation(P, idx, X, XT, q_range=None, res=None, relu=True, extra=None, **kw)
 
 
 # ----------------------------------------------------------------------------------------
-# Batched-over-videos head: V windows of N rows each, laid out [V*Npad, D] (Npad = N rounded up to
-# 64; pad rows are finite garbage that never reaches a result).  Every row-wise GEMM (fc_new_k,
-# Q/K/out projections, cls|reg) runs ONCE over all videos (M = V*Npad fills the machine with
-# 256-row tile pairs); QK^T and P.V are one batched launch each (ops.bmm: a per-video B matrix), the
-# softmax one launch over all V*Nq rows.  Per-row arithmetic and the per-video attention operands are
-# those of the single-window functions above, so the results are bit-identical to them.
+# Batched-over-videos head: V windows of N = T*slot rows each, laid out [V*Npad, D] (Npad = N rounded up to
+# 64; pad rows are finite garbage that never reaches a result).  Every row-wise GEMM (fc_new_k, Q/K/out
+# projections, cls|reg) runs ONCE over all videos (M = V*Npad fills the machine with 256-row tile pairs); QK^T
+# and P.V are one batched launch each (ops.bmm: a per-video B matrix), the softmax one launch over all V*Nq
+# rows.  Per-row arithmetic and the per-video attention operands are those of the single-window functions
+# above, so the results are bit-identical to them.
+#
+# Ragged proposal sets (hnmb_rcnn.py:582-599 uses the ACTUAL per-frame counts): every frame keeps a fixed block
+# of `slot` rows; `mask` = KeyMask(seg_counts int32 [V, n_segs] on the device, slot) tells the softmax which keys
+# of each block are proposals.  Rows behind a frame's count are finite garbage: as keys they get probability 0,
+# as queries they are never read.  With every count == slot the mask changes no bit.
 # ----------------------------------------------------------------------------------------
-def _key_rows(X, V, Npad, s, n):
-    D = X.shape[1]
-    return Split(X.hi.view(V, Npad, D)[:, s:s + n].reshape(V * n, D), X.lo.view(V, Npad, D)[:, s:s + n].reshape(V * n, D))
+class KeyMask:
+    __slots__ = ('seg', 'slot')
+
+    def __init__(self, seg, slot):
+        self.seg, self.slot = seg, slot
 
 
-def relation_batched(P, idx, X, XT, V, N, Npad, q_range=None, res=None, relu=True, **kw):
-    D = X.shape[1]
+def key_rows(X, V, Npad, s, n):
+    """Rows [s, s+n) of every video's block as one Split [V*n, D] (one gather launch)."""
+    out = Split.empty((V * n, X.shape[1]), X.hi.device)
+    return ops.gather_rows(X, out, V, n, src_rpp=Npad, src_row0=s, dst_rpp=n)
+
+
+def attention_batched(Q, K, XT, V, nk, nk_pad, mask=None):
+    """softmax(Q_v K_v^T / sqrt(D)) X_v for V videos.  Q Split [V*nq, D]; K Split [V*nk_pad, D] (video-major
+    blocks, first nk rows of a block are keys); XT Split [D, V*nk_pad] (values = un-projected rows, conv_g
+    False).  One launch each: QK^T (hvr_igemm with a per-image B matrix), row softmax, P.V."""
+    D = Q.shape[1]
+    nq = Q.shape[0] // V
+    _, S = ops.bmm(Q, K, V, nk, nk_pad * K.hi.stride(0), alpha=1.0 / math.sqrt(float(D)), want_split=False,
+                   want_f32=True)
+    Pm = ops.softmax_rows_split(S, nk, ld_p=nk_pad, seg_counts=mask.seg if mask is not None else None,
+                                slot=mask.slot if mask is not None else 0, rows_per_problem=nq)
+    O, _ = ops.bmm(Pm, XT, V, D, nk_pad)
+    return O
+
+
+def relation_batched(P, idx, X, XT, V, N, Npad, q_range=None, Xkey=None, res=None, relu=True, mask=None, **kw):
+    """Relation block idx for V videos.  q_range None: all rows are queries (res = X); else the key rows
+    (Xkey = key_rows(X, ...), also the residual)."""
     if q_range is None and FUSE_QK and ('qk%d' % idx) in P:
         Q, K = _qk(P, idx, X, **kw)
     else:
-        Xq = X if q_range is None else _key_rows(X, V, Npad, q_range[0], q_range[1])
+        if q_range is None:
+            Xq = X
+        else:
+            Xq = Xkey if Xkey is not None else key_rows(X, V, Npad, q_range[0], q_range[1])
         Q, _, _ = lin(Xq, P['q%d' % idx], **kw)
         K, _, _ = lin(X, P['k%d' % idx], **kw)
-    # the V per-video products Q_v K_v^T and P_v X_v as ONE launch each (hvr_igemm with a per-image B
-    # matrix): S [V*nq, N], softmax over all V*nq rows at once, O [V*nq, D]
-    _, S = ops.bmm(Q, K, V, N, Npad * K.hi.stride(0), alpha=1.0 / math.sqrt(float(D)), want_split=False,
-                   want_f32=True)
-    Pm = ops.softmax_rows_split(S, N, ld_p=Npad)
-    O, _ = ops.bmm(Pm, XT, V, D, Npad)
+    O = attention_batched(Q, K, XT, V, N, Npad, mask)
     out, _, _ = lin(O, P['o%d' % idx], relu=relu, res=res, **kw)
     return out
 
 
-def hrnmp_stage123_batched(P, rows, V, N, Npad, start, length, **kw):
-    """Stages 1-3 + fc_new_4 for V windows at once.  rows Split [V*Npad, 12544].  Returns
-    (out1 fp32 [V*length, 64], f4 Split [V*Npad, D], f4^T Split [D, V*Npad])."""
+def hrnmp_stage123_batched(P, rows, V, N, Npad, start, length, mask=None, f1=None, f1T=None, **kw):
+    """Stages 1-3 + fc_new_4 for V windows at once.  rows Split [V*Npad, 12544] (or f1 / f1T: the cached
+    fc_new_1 rows of the streaming scheduler).  Returns (out1 fp32 [V*length, 64], f4 Split [V*Npad, D],
+    f4^T Split [D, V*Npad])."""
     s, n = start, length
-    f1, _, f1T = lin(rows, P['fc1'], want_T=True, **kw)
-    a1 = relation_batched(P, 1, f1, f1T, V, N, Npad, res=f1, **kw)
+    if f1 is None:
+        f1, _, f1T = lin(rows, P['fc1'], want_T=True, **kw)
+    a1 = relation_batched(P, 1, f1, f1T, V, N, Npad, res=f1, mask=mask, **kw)
     f2, _, f2T = lin(a1, P['fc2'], want_T=True, **kw)
-    a2k = relation_batched(P, 2, f2, f2T, V, N, Npad, q_range=(s, n), res=_key_rows(f2, V, Npad, s, n), **kw)
+    f2k = key_rows(f2, V, Npad, s, n)
+    a2k = relation_batched(P, 2, f2, f2T, V, N, Npad, q_range=(s, n), Xkey=f2k, res=f2k, mask=mask, **kw)
     _, out1, _ = lin(a2k, P['out1'], want_split=False, want_f32=True, **kw)
-    D = f1.shape[1]
-    x3 = Split(f1.hi.clone(), f1.lo.clone())
-    x3.hi.view(V, Npad, D)[:, s:s + n] = a2k.hi.view(V, n, D)
-    x3.lo.view(V, Npad, D)[:, s:s + n] = a2k.lo.view(V, n, D)
+    # input of stage 3: the fc_new_1 rows with the key rows replaced by stage 2's output (hrnmp_bbox_head.py:865-868)
+    x3 = Split.empty(tuple(f1.shape), f1.hi.device)
+    ops.gather_rows(f1, x3, 1, V * Npad)
+    ops.gather_rows(a2k, x3, V, n, src_rpp=n, dst_rpp=Npad, dst_row0=s)
     f3, _, f3T = lin(x3, P['fc3'], want_T=True, **kw)
-    a3 = relation_batched(P, 3, f3, f3T, V, N, Npad, res=f3, **kw)
+    a3 = relation_batched(P, 3, f3, f3T, V, N, Npad, res=f3, mask=mask, **kw)
     f4, _, f4T = lin(a3, P['fc4'], want_T=True, **kw)
     return out1, f4, f4T
 
 
-def hrnmp_forward_batched(P, rows, V, N, Npad, start, length, **kw):
-    """rows Split [V*Npad, 12544].  Returns fp32 (out1, out2) of shape [V*length, 64]."""
+def hrnmp_stage4_batched(P, f4, f4T, V, N, Npad, start, length, mask=None, f4k=None, **kw):
     s, n = start, length
-    out1, f4, f4T = hrnmp_stage123_batched(P, rows, V, N, Npad, s, n, **kw)
-    a4 = relation_batched(P, 4, f4, f4T, V, N, Npad, q_range=(s, n), res=_key_rows(f4, V, Npad, s, n), **kw)
+    if f4k is None:
+        f4k = key_rows(f4, V, Npad, s, n)
+    a4 = relation_batched(P, 4, f4, f4T, V, N, Npad, q_range=(s, n), Xkey=f4k, res=f4k, mask=mask, **kw)
     _, out2, _ = lin(a4, P['out2'], want_split=False, want_f32=True, **kw)
-    return out1, out2
+    return out2
 
 
-def selsa_forward_batched(P, rows, V, N, Npad, start, length, **kw):
+def hrnmp_forward_batched(P, rows, V, N, Npad, start, length, mask=None, f1=None, f1T=None, **kw):
+    """rows Split [V*Npad, 12544].  Returns fp32 (out1, out2) of shape [V*length, 64]."""
+    out1, f4, f4T = hrnmp_stage123_batched(P, rows, V, N, Npad, start, length, mask=mask, f1=f1, f1T=f1T, **kw)
+    return out1, hrnmp_stage4_batched(P, f4, f4T, V, N, Npad, start, length, mask=mask, **kw)
+
+
+def hrnmp_stage4_inter_batched(P, f4, f4k, Kown, sup_rows, V, N, Npad, length, n_sup_rows, mask=None, **kw):
+    """Stage 4 with inter-video support rows (hrnmp_bbox_head.py:740-795 at inference):
+    the key / value set of video v = its own N window rows followed by its n_sup_rows support rows
+    (sup_rows Split [V*n_sup_rows, D]: the post-fc_new_4 key rows of the chosen other key frames, already
+    gathered).  Kown = k_data_fc_4(f4) [V*Npad, D] (computed while the exchange is in flight), f4k = the key rows
+    (queries and residual).  mask: seg_counts with the support blocks filled in."""
+    D = f4.shape[1]
+    n = length
+    nk = N + n_sup_rows
+    nk_pad = round_up(nk, 64)
+    dev = f4.hi.device
+    Q, _, _ = lin(f4k, P['q4'], **kw)
+    Ksup, _, _ = lin(sup_rows, P['k4'], **kw)
+    # assemble per video [own N rows | support rows | zero pad] for the keys and the values
+    Kall = Split.empty((V * nk_pad, D), dev)
+    Xall = Split.empty((V * nk_pad, D), dev)
+    for src_own, src_sup, dst in ((Kown, Ksup, Kall), (f4, sup_rows, Xall)):
+        ops.gather_rows(src_own, dst, V, N, src_rpp=Npad, dst_rpp=nk_pad)
+        ops.gather_rows(src_sup, dst, V, n_sup_rows, src_rpp=n_sup_rows, dst_rpp=nk_pad, dst_row0=N)
+    if nk_pad > nk:   # zero the pad rows of the value set (P is exactly 0 there; 0 * garbage must stay 0)
+        zero_idx = torch.full((V * (nk_pad - nk),), -1, dtype=torch.int32, device=dev)
+        ops.gather_rows(f4, Xall, V, nk_pad - nk, idx=zero_idx, dst_rpp=nk_pad, dst_row0=nk)
+    XallT = ops.transpose_split(Xall, D)
+    O = attention_batched(Q, Kall, XallT, V, nk, nk_pad, mask)
+    a4, _, _ = lin(O, P['o4'], relu=True, res=f4k, **kw)
+    _, out2, _ = lin(a4, P['out2'], want_split=False, want_f32=True, **kw)
+    return out2
+
+
+def selsa_forward_batched(P, rows, V, N, Npad, start, length, mask=None, f1=None, f1T=None, **kw):
     s, n = start, length
-    f1, _, f1T = lin(rows, P['fc1'], want_T=True, **kw)
-    a1 = relation_batched(P, 1, f1, f1T, V, N, Npad, res=f1, **kw)
+    if f1 is None:
+        f1, _, f1T = lin(rows, P['fc1'], want_T=True, **kw)
+    a1 = relation_batched(P, 1, f1, f1T, V, N, Npad, res=f1, mask=mask, **kw)
     f2, _, f2T = lin(a1, P['fc2'], want_T=True, **kw)
-    a2k = relation_batched(P, 2, f2, f2T, V, N, Npad, q_range=(s, n), res=_key_rows(f2, V, Npad, s, n), **kw)
+    f2k = key_rows(f2, V, Npad, s, n)
+    a2k = relation_batched(P, 2, f2, f2T, V, N, Npad, q_range=(s, n), Xkey=f2k, res=f2k, mask=mask, **kw)
     _, out1, _ = lin(a2k, P['out1'], want_split=False, want_f32=True, **kw)
     return out1
 

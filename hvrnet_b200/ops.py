@@ -418,6 +418,46 @@ def softmax_rows_split(S, cols, ld_p=None, seg_counts=None, slot=0, rows_per_pro
     return P
 
 
+def window_rois(props, counts, perm, V, T, key_dim, n_segs=None):
+    """props [F,P,5], counts [F] int32 (hvr_rpn_proposals outputs), perm int64 [V*T] or None -> (rois [V*Npad,5],
+    rois_key [V*P,5], seg_counts int32 [V,n_segs], key_counts int32 [V]); see hvr_window_rois."""
+    _need_cuda(props, counts)
+    P = props.shape[1]
+    Npad = round_up(T * P, 64)
+    n_segs = n_segs or T
+    dev = props.device
+    rois = torch.empty((V * Npad, 5), dtype=torch.float32, device=dev)
+    rois_key = torch.empty((V * P, 5), dtype=torch.float32, device=dev)
+    seg = torch.zeros((V, n_segs), dtype=torch.int32, device=dev)
+    kc = torch.empty(V, dtype=torch.int32, device=dev)
+    assert props.is_contiguous() and counts.dtype == torch.int32 and (perm is None or perm.dtype == torch.int64)
+    check(_lib.lib().hvr_window_rois(_p(props), _p(counts), _p(perm), V, T, P, key_dim, Npad, _p(rois), _p(rois_key),
+                                     _p(seg), n_segs, _p(kc), _stream()), 'hvr_window_rois')
+    return rois, rois_key, seg, kc
+
+
+def gather_rows(src, dst, n_problems, n_rows, idx=None, src_rpp=0, src_row0=0, dst_rpp=0, dst_row0=0, cols=None):
+    """dst[p*dst_rpp + dst_row0 + j] = src[idx[p*n_rows + j]] (or src[p*src_rpp + src_row0 + j] when idx is None);
+    Split matrices, negative index -> zero row.  See hvr_gather_rows_split."""
+    cols = cols or src.shape[1]
+    assert idx is None or (idx.dtype == torch.int32 and idx.is_contiguous())
+    check(_lib.lib().hvr_gather_rows_split(_p(src.hi), _p(src.lo), src.hi.stride(0), _p(idx), src_rpp, src_row0,
+                                           _p(dst.hi), _p(dst.lo), dst.hi.stride(0), n_problems, n_rows, dst_rpp,
+                                           dst_row0, cols, _stream()), 'hvr_gather_rows_split')
+    return dst
+
+
+def support_index(sel, pool_counts, P, T, seg_counts):
+    """sel int64 [V,S], pool_counts int32 [G] -> idx int32 [V, S*P] (rows of the pool), and fills the support
+    blocks [T, T+S) of seg_counts [V, n_segs] in place.  See hvr_support_index."""
+    V, S = sel.shape
+    idx = torch.empty((V, S * P), dtype=torch.int32, device=sel.device)
+    assert sel.dtype == torch.int64 and sel.is_contiguous() and pool_counts.dtype == torch.int32
+    check(_lib.lib().hvr_support_index(_p(sel), _p(pool_counts), V, S, P, T, _p(idx), _p(seg_counts),
+                                       seg_counts.shape[1], _stream()), 'hvr_support_index')
+    return idx
+
+
 def video_descriptor(c5_nhwc, n_videos):
     """c5_nhwc fp32 [n_videos*T, h, w, C] (the shared head's output, frames of a video contiguous) ->
     [n_videos, C]: max over a video's frames of the per-frame spatial mean (hnmb_rcnn.py:78-81)."""

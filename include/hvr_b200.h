@@ -273,6 +273,37 @@ int hvr_softmax_rows_split_masked(const float* S, int rows, int cols, int64_t ld
                                   int rows_per_problem, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Window bookkeeping on the device (csrc/window.cu).  Replaces the host-side assembly of a window in
+ * HNMBRCNN.simple_test_bboxes / get_roi_feat (hnmb_rcnn.py:580-599: bbox2roi per frame, cur_range from the
+ * per-frame counts, torch.cat) for V windows of T frames at once, with every frame keeping a fixed block of P
+ * (= max_num) rows so that launch geometry never depends on the counts; the counts travel as device masks.
+ *   props  [F, P, 5] / counts [F] : hvr_rpn_proposals outputs of the F >= V*T frames held in the C5 buffer
+ *   perm   [V*T] int64 (or NULL = identity): buffer slot of window position (v, t)
+ *   rois       [V, Npad, 5]  (slot, x1, y1, x2, y2) for RoIAlign, rows t*P + j; rows >= T*P are zero
+ *   rois_key   [V*P, 5]      (0, x1, y1, x2, y2) of the key frames (bbox2roi([props_key]))
+ *   seg_counts [V, n_segs] int32: entries [0, T) = proposal count of every window frame (the key mask of the
+ *                            relation stages); entries >= T (support blocks) are left to hvr_support_index
+ *   key_counts [V] int32     proposal count of the key frames (n_valid of the post-processing)
+ * ---------------------------------------------------------------------------------- */
+int hvr_window_rois(const float* props, const int* counts, const int64_t* perm, int V, int T, int P,
+                    int key_dim, int Npad, float* rois, float* rois_key, int* seg_counts, int n_segs,
+                    int* key_counts, void* stream);
+/* Row gather on split matrices (16-byte vectors; cols % 8 == 0):
+ *   dst[p*dst_rows_per_problem + dst_row0 + j, :cols] = src[row(p, j), :cols],  j < n_rows, p < n_problems
+ *   row(p, j) = idx ? idx[p*n_rows + j] : p*src_rows_per_problem + src_row0 + j;  a negative index gives zeros.
+ * Assembles the key / value sets of the relation stages (hrnmp_bbox_head.py:865-868: key rows of stage 2 put
+ * back among the window's rows; :740-752: support rows appended) without host-side torch.cat. */
+int hvr_gather_rows_split(const hvr_bf16* src_hi, const hvr_bf16* src_lo, int64_t ld_src, const int* idx,
+                          int64_t src_rows_per_problem, int src_row0, hvr_bf16* dst_hi, hvr_bf16* dst_lo,
+                          int64_t ld_dst, int n_problems, int n_rows, int64_t dst_rows_per_problem,
+                          int dst_row0, int cols, void* stream);
+/* Support selection -> row indices into the gathered pool [G*P, D] and the support blocks of the key mask:
+ *   idx[v][s*P + j] = sel[v][s]*P + j (-1 when sel < 0), seg_counts[v][T + s] = pool_counts[sel[v][s]] (0 when
+ *   absent).  sel [V, S] int64 (ring order or hvr_support_select), pool_counts [G] int32. */
+int hvr_support_index(const int64_t* sel, const int* pool_counts, int V, int S, int P, int T, int* idx,
+                      int* seg_counts, int n_segs, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Test-time image pipeline (next row N2).  Replaces the CPU DataLoader path Resize(keep_ratio)
  * -> Normalize -> Pad(16) -> ImageToTensor (mmdet/datasets/pipelines/transforms.py:111-125,
  * 240-322; formating.py:48-56), i.e. mmcv.imrescale = cv2.resize(INTER_LINEAR) on uint8

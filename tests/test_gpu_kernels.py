@@ -543,6 +543,8 @@ def test_roi_align_fast_variant_vs_strict(cuda, C, out_size):
     rois[40, 1:] = torch.tensor([0., 0., 999., 599.])
     rois[41, 1:] = torch.tensor([-17., 300., 5., 320.])
     rois[42, 1:] = 0.                                                            # the pad RoI of a batched window
+    rois[43, 1:] = torch.tensor([1500., 100., 1600., 200.])                      # entirely outside the map: all zero
+    rois[44, 1:] = torch.tensor([100., -500., 200., -100.])
     ref = cref.roi_align(feat, rois, out_size=out_size, feat_nhwc=True, out_nhwc=True)
     f, r = feat.to(cuda), rois.to(cuda)
     o, sp = ops.roi_align(f, r, out_size=out_size, feat_nhwc=True, out_nhwc=True, want_split=True, arithmetic='fast')

@@ -131,25 +131,57 @@ def test_forward_feat_end_to_end(world):
     with torch.no_grad():
         ref, raux = R.hnmb_forward_feat(sd, [c for c in world['c4_ref'].split(1)], world['metas'], 1,
                                         roi_align_fn=cref.roi_align, return_aux=True)
-    # proposals: same count; boxes agree to 1e-3 relative of the image size for >= 99 % of the rows
-    # (a near-tie in RPN logits may legitimately reorder neighbours between fp32 summation orders)
+    # proposals: same per-frame counts; the index lists are compared exactly in test_index_parity (replay) - here the
+    # free-running sets must overlap at the measured rate (profiles/r02a_parity_report.txt: >= 0.98 per frame)
     for t in range(3):
         a = aux['proposals'][t, :aux['counts'][t]].cpu()
         b = raux['proposals'][t]
         assert a.shape == b.shape
         d = (a[:, None, :4] - b[None, :, :4]).abs().amax(-1)          # set match: greedy NMS is order
-        same = (d.min(0)[0] < 1.0).float().mean()                      # sensitive, positions may shift
-        assert same > 0.95, float(same)
+        same = (d.min(0)[0] < 1e-2).float().mean()                     # sensitive, positions may shift
+        assert same >= 0.97, float(same)
     # with the oracle's proposals forced in, the whole second stage must agree to 1e-3
     res2, aux2 = m(x=c4s, img=None, img_meta=world['metas'], forward_feat=True, return_loss=False, rescale=True,
                    proposals=[p.to(dev) for p in raux['proposals']], return_aux=True)
     for a, b in zip(aux2['cls'] + aux2['reg'], raux['cls'] + raux['reg']):
         assert _rel(a.cpu(), b) < 1e-3
     for o in range(2):
-        hit, tot = _match(res2[o], ref[o])
-        assert tot == 0 or hit / tot > 0.98, (hit, tot)
-        hit, tot = _match(res[o], ref[o])
-        assert tot == 0 or hit / tot > 0.95, (hit, tot)
+        # identical rois: every oracle detection above 0.05 is found (same class, IoU > 0.99, score within 1e-3)
+        hit, tot = _match(res2[o], ref[o], iou_thr=0.99, score_tol=1e-3)
+        assert hit == tot, (hit, tot)
+        hit, tot = _match(res[o], ref[o], iou_thr=0.99, score_tol=1e-3)
+        assert tot == 0 or hit / tot >= 0.96, (hit, tot)
+
+
+@pytest.mark.parametrize('workload,seed', [('hrnmp', 5), ('hrnmp', 6), ('hrnmp', 7), ('selsa', 5), ('faster_rcnn', 5)])
+def test_index_parity_full_size(cuda, workload, seed):
+    """north_star: bit-exact proposal / NMS indices.  tests/parity_tools.py at the BASELINE.json sizes (hrnmp: T = 15
+    frames, 4500 proposals; SELSA: T = 3; Faster-RCNN: one frame), from frames, through the registered detectors:
+      (A) REPLAY - the oracle's index logic (rpn_head.py:72-103 top-k + NMS, bbox_nms.py:36-61 per-class NMS + top-k)
+          run on the DEVICE's own RPN maps / head outputs returns the device's anchor indices and (label, roi) lists
+          bit for bit, in order, for every frame and every head output: the CUDA index logic is exact;
+      (B) FREE-RUNNING - against the oracle on its own tensors, every first divergence is a near-tie: a margin below
+          (4x) the measured arithmetic error of the compared quantity, which is itself inside the 1e-3 tolerance;
+          set overlaps at the rates measured in profiles/r02a_parity_report.txt (proposal anchors >= 0.98 per frame,
+          detections >= 0.967)."""
+    from hvrnet_b200 import configs, synth
+    from tests import parity_tools as PT
+    m, sd, w = configs.build_workload(workload, cuda)
+    T = w['t_dim']
+    frames = synth.make_frames(T, seed=seed)
+    metas = [synth.make_img_meta() for _ in range(T)]
+    r = PT.window_parity(m, sd, frames, metas, w['key_dim'], head=w['head'], dev=cuda)
+    print(PT.format_report('%s seed %d' % (workload, seed), r))
+    assert r['rpn_logit_rel'] < 1e-3
+    assert r['frames_replay_exact'] == T and r['replay_box_err_px'] < 1e-3
+    assert all(e['near_tie'] for e in r['proposal_divergences']), r['proposal_divergences']
+    assert r['proposal_set_overlap_min'] >= 0.97
+    n_out = r['n_outputs']
+    assert all(r['head_rel_%d' % o] < 1e-3 for o in range(n_out))
+    assert r['det_replay_exact'] == n_out
+    assert all(e['near_tie'] for e in r['det_divergences']), r['det_divergences']
+    assert all(r['det_set_overlap_forced_%d' % o] >= 0.96 for o in range(n_out))
+    assert all(r['det_free_set_overlap_%d' % o] >= 0.96 for o in range(n_out))
 
 
 def test_faster_rcnn_simple_test(cuda):
@@ -163,8 +195,8 @@ def test_faster_rcnn_simple_test(cuda):
     with torch.no_grad():
         ref = R.faster_rcnn_simple_test(sd, img, meta, roi_align_fn=cref.roi_align)
     assert len(res) == 30
-    hit, tot = _match(res, ref)
-    assert tot == 0 or hit / tot > 0.95, (hit, tot)
+    hit, tot = _match(res, ref, iou_thr=0.99, score_tol=1e-3)
+    assert tot == 0 or hit / tot >= 0.96, (hit, tot)
 
 
 def test_cuda_graph_runner_matches_eager(world):
@@ -445,12 +477,12 @@ def test_full_size_hrnmp_window_T15(cuda):
     for a, b in zip(aux['cls'] + aux['reg'], raux['cls'] + raux['reg']):
         assert a.shape == b.shape == (300, b.shape[1]) and _rel(a.cpu(), b) < 1e-3
     for o in range(2):
-        hit, tot = _match(res[o], ref[o])
-        assert tot == 0 or hit / tot > 0.98, (hit, tot)
+        hit, tot = _match(res[o], ref[o], iou_thr=0.99, score_tol=1e-3)     # identical rois: every detection found
+        assert hit == tot, (hit, tot)
     res_free = m(x=c4s, img=None, img_meta=metas, forward_feat=True, return_loss=False, rescale=True)
     for o in range(2):
-        hit, tot = _match(res_free[o], ref[o])
-        assert tot == 0 or hit / tot > 0.9, (hit, tot)
+        hit, tot = _match(res_free[o], ref[o], iou_thr=0.99, score_tol=1e-3)
+        assert tot == 0 or hit / tot >= 0.96, (hit, tot)                    # measured: 0.967-1.0 (test_index_parity)
 
 
 def test_prefetch_pipelining_same_results(world):

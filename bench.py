@@ -88,6 +88,8 @@ def parse():
     ap.add_argument('--no-streaming', action='store_true', help='skip the extra (labelled) streaming-scheduler figure')
     ap.add_argument('--no-other-workloads', action='store_true', help='skip the short side measurements of the other BASELINE.json configs')
     ap.add_argument('--eager', action='store_true', help='disable CUDA graphs (per-kernel Python launches)')
+    ap.add_argument('--no-inter-video', action='store_true', help='N > 1: skip the config-5 inter-video block')
+    ap.add_argument('--inter-keys-per-gpu', type=int, default=32, help='key frames per rank of the config-5 block')
     ap.add_argument('--gemm-report', default=None, help='write a per-shape table of the igemm launches (csv)')
     return ap.parse_args()
 
@@ -281,6 +283,68 @@ class ClockSampler:
         return out
 
 
+def inter_video_block(args, dev, world, rank, dist, steps=4, warm=2):
+    """BASELINE.json configs[4]: `--inter-keys-per-gpu` key frames per rank, every key frame's stage 4 also attends to
+    the key rows of 4 other key frames of the whole job (ring order).  Returns the block added to the JSON line."""
+    from collections import deque
+    from hvrnet_b200 import configs, synth
+    from hvrnet_b200.runtime import GraphRunner
+    torch.cuda.empty_cache()
+    model, sd, w = configs.build_workload('hrnmp_inter', dev)
+    T = w['t_dim']
+    V = args.inter_keys_per_gpu
+    metas = [synth.make_img_meta() for _ in range(T)]
+    pool = 3
+    frames = synth.make_frames(T + pool, seed=100 + rank)
+    devV = [torch.cat([frames[(i + v) % (T + pool)][None] for v in range(V)]).to(dev) for i in range(T + pool)]
+    model.enable_cuda_graphs(True)
+    dqs = [deque(maxlen=T) for _ in range(V)]
+    for i in range(T):
+        c4 = model(img=devV[i], img_meta=[metas[0]] * V, backbone_feat=True)[0]
+        for v, t in enumerate(GraphRunner.per_frame(c4)):
+            dqs[v].append(t)
+
+    def step(i):
+        c4 = model(img=devV[T + i % pool], img_meta=[metas[0]] * V, backbone_feat=True)[0]
+        for v, t in enumerate(GraphRunner.per_frame(c4)):
+            dqs[v].append(t)
+        return model.forward_feat_intervideo([list(d) for d in dqs], metas, n_support=4, rescale=True)
+    for i in range(warm):
+        step(i)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ag = []
+    e0.record()
+    for i in range(steps):
+        step(warm + i)
+        ag.append(model._runner.last_all_gather_ms())     # events on the communication stream; the step has ended
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms, max(ag), sum(ag) / len(ag)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ag_max, ag_mean = [float(x) for x in t.tolist()]
+    st = model._runner.last_inter.state['st']
+    send_bytes = st.send.numel() * 2
+    recv_bytes = send_bytes * (world - 1)
+    model.enable_cuda_graphs(False)
+    del model
+    torch.cuda.empty_cache()
+    return {'workload': 'HVRNet hrnmp batched inference, %d key-frames/GPU, NCCL all-gather of inter-video proposal features' % V,
+            'value': world * V * steps / (ms / 1e3), 'unit': 'frames/s', 'ms_per_step': ms / steps, 'steps': steps,
+            'key_frames_per_gpu': V, 'n_support': 4, 'launch': 'cuda graphs: trunk + three window graphs around the all-gather',
+            'all_gather': {'ms_mean': ag_mean, 'ms_max': ag_max, 'bytes_sent_per_rank': send_bytes,
+                           'bytes_received_per_rank': recv_bytes,
+                           'achieved_GBs_per_rank': recv_bytes / (ag_mean / 1e3) / 1e9 if ag_mean > 0 else None,
+                           'nvlink_reference_GBs': 770.0, 'share_of_step': ag_mean / (ms / steps),
+                           'note': 'device time between events on the communication stream around the ONE collective of a '
+                                   'step; it runs under the branch post-processing and the k_4 projection (graph B)'},
+            'input': 'device-resident frames (%dx3x608x1008 fp32 per step per rank)' % V}
+
+
 # ----------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------
@@ -363,7 +427,7 @@ def main():
     def timed(from_host, K, W, profile=False):
         # the roofline leg brackets individual launches with events, which needs the eager path
         # (the runner's launch sequence - batched head, forked branches - re-issued eagerly: capture=False)
-        graphs_ok = not args.eager and args.workload != 'faster_rcnn'                                # inter: trunk graph only
+        graphs_ok = not args.eager and args.workload != 'faster_rcnn'
         model.enable_cuda_graphs(graphs_ok, capture=not profile)
         dq = prefill()
         for i in range(W):
@@ -440,6 +504,11 @@ def main():
     if k_:
         peak, peak_src = v_, 'MEASURED_PEAKS.json ' + k_
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    ncu = {}
+    try:
+        ncu = json.load(open(os.path.join(ROOT, 'profiles', 'igemm_ncu_step.json')))
+    except (OSError, ValueError):
+        pass
 
     # second named figure of the metric: RoIAlign achieved HBM GB/s on the step's batched launch
     # (T frames x 300 proposals, 256-channel 38x63 maps, NHWC in -> split rows out)
@@ -556,11 +625,12 @@ def main():
                      'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                      'tensor_work_tflops': 3.0 * achieved, 'tensor_work_frac': 3.0 * achieved / peak,
                      'peak_source': peak_src,
-                     # ncu dram__bytes_read.sum + dram__bytes_write.sum, average per igemm launch of one step
-                     # (profiles/r01n_igemm_ncu_metrics_step_V7.txt; the algorithmic FLOPs above are per step)
-                     'traffic': 377.6e6 if (args.workload == 'hrnmp' and V == 7) else None,
-                     'traffic_source': 'profiles/r01n_igemm_ncu_metrics_step_V7.txt',
-                     'ncu_tensor_pipe_active_pct': 83.5 if (args.workload == 'hrnmp' and V == 7) else None,
+                     # ncu dram__bytes_read.sum + dram__bytes_write.sum, average per igemm launch of one step, and the
+                     # time-weighted tensor-pipe activity: read from the summary file scripts/ncu_metrics_summary.py writes
+                     # from an ncu range capture of exactly this command's timed region (never constants in this file)
+                     'traffic': ncu.get('traffic_bytes_per_launch') if (args.workload == 'hrnmp' and V == 7) else None,
+                     'traffic_source': ncu.get('source'),
+                     'ncu_tensor_pipe_active_pct': ncu.get('tensor_pipe_active_pct') if (args.workload == 'hrnmp' and V == 7) else None,
                      'algorithmic_gflop_per_step': gemm_flops / K / 1e9, 'launches_per_step': len(prof) / K,
                      'kernel_ms_per_step': gemm_ms / K, 'share_of_step': gemm_ms / ms_prof,
                      'profiled_ms_per_step': ms_prof / K,
@@ -607,6 +677,11 @@ def main():
         model = None
     if streaming is not None:
         line['streaming'] = streaming
+    # BASELINE.json configs[4] at N > 1: 32 key frames per rank, inter-video stage with ONE NCCL all-gather
+    # of the post-fc_new_4 key rows per step, three CUDA graphs around it (runtime.GraphRunner.detect_inter).  Device-
+    # resident frames; timed like the headline (events, barrier, max over ranks).
+    if world > 1 and args.workload == 'hrnmp' and not args.eager and not args.no_inter_video:
+        line['inter_video'] = inter_video_block(args, dev, world, rank, dist)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             sec, done = cpu_key_frame_seconds(args.workload, max_seconds=60.0, steps=1)

@@ -83,7 +83,7 @@ SIGNATURES = {
     'hvr_window_rois': (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     'hvr_gather_rows_split': (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_int, c_int, c_i64,
                                       c_int, c_int, c_vp]),
-    'hvr_support_index': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
+    'hvr_support_index': (c_int, [c_vp, c_vp, c_i64, c_int, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     'hvr_video_descriptor_workspace_bytes': (c_sz, [c_int, c_int, c_int]),
     'hvr_video_descriptor': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
     'hvr_support_select': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),

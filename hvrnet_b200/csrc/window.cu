@@ -69,23 +69,24 @@ __global__ void gather_rows_kernel(const uint4* __restrict__ shi, const uint4* _
   }
 }
 
-// Row indices of the support rows of every local key frame inside the gathered pool:
-// idx[v][s * P + j] = sel[v][s] * P + j   (sel < 0: no such support video -> -1 = zero rows), and the key mask
-// entries of the support blocks: seg_counts[v][T + s] = pool_counts[sel[v][s]] (0 when absent).
-__global__ void support_index_kernel(const long long* __restrict__ sel, const int* __restrict__ pool_counts, int V,
-                                     int S, int P, int T, int* __restrict__ idx, int* __restrict__ seg_counts,
-                                     int n_segs) {
+// Row indices of the support rows of every local key frame inside the gathered pool, and the key-mask entries of
+// the support blocks.  Global key frame g = sel[v][s] lives on rank g / vpr as local key frame g % vpr:
+//   idx[v][s * P + j]      = (g / vpr) * rank_stride_rows + (g % vpr) * P + j      (g < 0: -1 = zero rows)
+//   seg_counts[v][T + s]   = pool_counts[(g / vpr) * counts_rank_stride + g % vpr]  (g < 0: 0)
+__global__ void support_index_kernel(const long long* __restrict__ sel, const int* __restrict__ pool_counts,
+                                     long long counts_rank_stride, int vpr, long long rank_stride_rows, int V, int S,
+                                     int P, int T, int* __restrict__ idx, int* __restrict__ seg_counts, int n_segs) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < V * S * P) {
     const int v = i / (S * P), r = i - v * S * P;
     const int s = r / P, j = r - s * P;
     const long long g = sel[v * S + s];
-    idx[i] = g < 0 ? -1 : (int)(g * P + j);
+    idx[i] = g < 0 ? -1 : (int)((g / vpr) * rank_stride_rows + (g % vpr) * P + j);
   }
   if (i < V * S) {
     const int v = i / S, s = i - v * S;
     const long long g = sel[i];
-    seg_counts[(size_t)v * n_segs + T + s] = g < 0 ? 0 : pool_counts[g];
+    seg_counts[(size_t)v * n_segs + T + s] = g < 0 ? 0 : pool_counts[(g / vpr) * counts_rank_stride + g % vpr];
   }
 }
 
@@ -126,12 +127,14 @@ extern "C" int hvr_gather_rows_split(const hvr_bf16* src_hi, const hvr_bf16* src
   return HVR_OK;
 }
 
-extern "C" int hvr_support_index(const int64_t* sel, const int* pool_counts, int V, int S, int P, int T, int* idx,
-                                 int* seg_counts, int n_segs, void* stream) {
-  if (!sel || !pool_counts || !idx || !seg_counts || V < 1 || S < 1 || P < 1 || T < 0 || n_segs < T + S)
+extern "C" int hvr_support_index(const int64_t* sel, const int* pool_counts, int64_t counts_rank_stride, int vpr,
+                                 int64_t rank_stride_rows, int V, int S, int P, int T, int* idx, int* seg_counts,
+                                 int n_segs, void* stream) {
+  if (!sel || !pool_counts || !idx || !seg_counts || V < 1 || S < 1 || P < 1 || T < 0 || n_segs < T + S || vpr < 1)
     return HVR_ERR_ARG;
   support_index_kernel<<<hvr_cdiv((long long)V * S * P, 256), 256, 0, ST(stream)>>>(
-      (const long long*)sel, pool_counts, V, S, P, T, idx, seg_counts, n_segs);
+      (const long long*)sel, pool_counts, counts_rank_stride, vpr, rank_stride_rows, V, S, P, T, idx, seg_counts,
+      n_segs);
   HVR_LAUNCHED();
   return HVR_OK;
 }

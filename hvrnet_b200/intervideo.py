@@ -8,10 +8,14 @@ chosen by ring order over the global list of key frames:  (g+1 .. g+n_support) m
 video descriptors (next row N4, hnmb_rcnn.py:76-101), the n_support most similar other videos.
 
 Sharding: each rank owns V key frames (global index g = rank*V + v), computes stages 1-3
-locally, and ONE all-gather of Z (split-bf16 pair = 4 bytes / element, bit-exact transport of
-what a single GPU would hold) gives every rank the pool [G*P, D]; stage 4 then runs locally.
-The functions below are device-agnostic torch.distributed code (NCCL on the GPUs; the gloo
-CPU tests drive the same code path with world_size 2).
+locally, and ONE all-gather (split-bf16 pair = 4 bytes / element, bit-exact transport of what a
+single GPU would hold) hands every rank the post-fc_new_4 key rows of all G key frames, their
+proposal counts (frames may yield fewer than max_num proposals: the receivers mask the support
+keys) and, for similarity selection, the video descriptors; stage 4 then runs locally
+(window.inter_stage_a/b/c; the support rows are gathered out of the receive buffer as it lies by
+hvr_support_index + hvr_gather_rows_split).  The functions below are device-agnostic
+torch.distributed plumbing - layout of the send buffer, the collective, ring rule, sharding -
+(NCCL on the GPUs; the gloo CPU tests drive the same code with world_size 2).
 """
 import torch
 import torch.distributed as dist
@@ -50,18 +54,45 @@ def shard_videos(seg_lens, world):
     return out
 
 
-def all_gather_rows(z, group=None):
-    """z: Split [V*P, D] (same V*P on every rank) -> Split [world*V*P, D], rank-major.
-    One collective: hi and lo travel as one [2, V*P, D] bf16 tensor."""
+def pack_exchange(z_key, key_counts, desc=None):
+    """Send buffer of the ONE all-gather: bf16 [2, rpr, D].  Block 0 (hi): the V*P post-fc_new_4 key rows' hi parts,
+    then one carrier row holding the V per-key-frame proposal counts (int32 bits; the receivers mask the support
+    keys with them), then - similarity selection only - r carrier rows per video holding its fp32 descriptor.
+    Block 1 (lo): the lo parts of the key rows; its carrier rows are zero.  Split-bf16 travels bit-exactly."""
+    VP, D = z_key.hi.shape
+    V = key_counts.shape[0]
+    assert V * 4 <= D * 2, 'counts carrier row too small'
+    n_desc = 0
+    carrier = None
+    if desc is not None:
+        carrier, r = _desc_rows(desc, D)
+        n_desc = V * r
+    rpr = VP + 1 + n_desc
+    send = torch.zeros((2, rpr, D), dtype=torch.bfloat16, device=z_key.hi.device)
+    send[0, :VP].copy_(z_key.hi)                # contiguous blocks: device-to-device memcpy nodes, no kernel
+    send[1, :VP].copy_(z_key.lo)
+    send[0, VP].view(torch.int32)[:V].copy_(key_counts)
+    if carrier is not None:
+        send[0, VP + 1:].copy_(carrier)
+    return send, rpr, n_desc
+
+
+def exchange(send, group=None, async_op=False):
+    """The one collective of the path: all_gather_into_tensor of the send buffer -> recv bf16 [world, 2, rpr, D]
+    (rank-major).  Returns (recv, work) - work is None unless async_op."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return z
+        return send.unsqueeze(0), None
     world = dist.get_world_size(group)
-    send = torch.stack([z.hi, z.lo]).contiguous()
-    rows = z.hi.shape[0]
-    recv = torch.empty((world * 2,) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
-    dist.all_gather_into_tensor(recv, send, group=group)       # rank-major: [hi_0, lo_0, hi_1, lo_1, ...]
-    recv = recv.view(world, 2, rows, -1)
-    return Split(recv[:, 0].reshape(world * rows, -1), recv[:, 1].reshape(world * rows, -1))
+    recv = torch.empty((world * send.shape[0],) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+    work = dist.all_gather_into_tensor(recv, send, group=group, async_op=async_op)   # dim-0 concatenation, rank-major
+    return recv.view((world,) + tuple(send.shape)), (work if async_op else None)
+
+
+def unpack_descriptors(recv, V, P, n_desc_rows, C):
+    """Descriptor carrier rows of every rank -> fp32 [world*V, C]."""
+    world, _, rpr, D = recv.shape
+    rows = recv[:, 0, V * P + 1:V * P + 1 + n_desc_rows].contiguous().view(world * n_desc_rows, D)
+    return _desc_from_rows(rows, world * V, n_desc_rows // V, C)
 
 
 def _desc_rows(desc, D):
@@ -77,49 +108,3 @@ def _desc_rows(desc, D):
 def _desc_from_rows(rows, V, r, C):
     """Inverse of _desc_rows: carrier rows [V*r, D] (bf16) -> fp32 [V, C]."""
     return rows.contiguous().view(torch.uint8).view(V, -1)[:, :C * 4].contiguous().view(torch.float32).view(V, C)
-
-
-def select_by_similarity(desc_all, g0, n_local, n_support):
-    """Product selector: hvr_support_select on the device, one small D2H read of the indices."""
-    from . import ops
-    idx = ops.support_select(desc_all, g0, n_local, n_support).cpu().tolist()
-    return [[i for i in row if i >= 0] for row in idx]
-
-
-def gather_support(z_local, rows_per_key, n_support, group=None, async_stream=None, desc_local=None,
-                   selector=select_by_similarity):
-    """Exchange + selection.  z_local: Split [V*P, D] of this rank's V key frames.
-    Returns a list of V Splits [n_sel*P, D]: the support rows of each local key frame.
-    desc_local None: ring order.  desc_local fp32 [V, C] (ops.video_descriptor of each local video): the
-    n_support most similar other videos; the descriptors ride in the same all-gather as extra rows and
-    `selector(desc_all [G,C], g0, V, n_support)` returns the chosen global indices per local key frame
-    (the gloo CPU tests pass a CPU selector; the default runs the CUDA kernel)."""
-    P = rows_per_key
-    V = z_local.hi.shape[0] // P
-    if dist.is_available() and dist.is_initialized():
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-    else:
-        world, rank = 1, 0
-    G = world * V
-    chosen = None
-    if desc_local is None:
-        pool = all_gather_rows(z_local, group)
-    else:
-        D, C = z_local.hi.shape[1], desc_local.shape[1]
-        carrier, r = _desc_rows(desc_local, D)
-        sent = Split(torch.cat([z_local.hi, carrier], 0), torch.cat([z_local.lo, torch.zeros_like(carrier)], 0))
-        got = all_gather_rows(sent, group)                     # still ONE collective
-        per = V * P + V * r
-        hi, lo = got.hi.view(world, per, D), got.lo.view(world, per, D)
-        pool = Split(hi[:, :V * P].reshape(G * P, D), lo[:, :V * P].reshape(G * P, D))
-        desc_all = _desc_from_rows(hi[:, V * P:].reshape(G * r, D), G, r, C)
-        chosen = selector(desc_all, rank * V, V, min(n_support, G - 1)) if G > 1 else [[] for _ in range(V)]
-    out = []
-    for v in range(V):
-        idx = support_indices(rank * V + v, G, n_support) if chosen is None else chosen[v]
-        if not idx:
-            out.append(Split(pool.hi[:0], pool.lo[:0]))
-            continue
-        out.append(Split(torch.cat([pool.hi[i * P:(i + 1) * P] for i in idx], 0),
-                         torch.cat([pool.lo[i * P:(i + 1) * P] for i in idx], 0)))
-    return out

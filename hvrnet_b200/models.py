@@ -602,25 +602,25 @@ class TwoStageDetector(nn.Module):
             return parts[0]
         return ops.Split(torch.cat([p.hi for p in parts], 0), torch.cat([p.lo for p in parts], 0))
 
-    def _rois_and_feats(self, c4, img_meta, proposals=None):
-        """C5 + RPN + RoIAlign of a window: returns (rois [N,5] with frame index, per-frame
-        counts (host ints), roi feature rows Split [N, h*w*C], aux)."""
-        T = c4.shape[0]
-        c5 = self.shared_head.forward_nhwc(c4) if self.feat_from_shared_head else ops.merge(c4)
-        if proposals is None:
-            props, counts = self.rpn_head.get_proposals(c4, img_meta[0]['img_shape'], self.test_cfg.rpn)
-            cnt = counts.cpu().tolist()                                  # the one host read of the window
-        else:
-            cnt = [int(p.shape[0]) for p in proposals]
-            props = None
-        frame_idx = torch.arange(T, device=c4.hi.device, dtype=torch.float32)
-        if props is not None and all(c == props.shape[1] for c in cnt):
-            rois = torch.cat([frame_idx.view(T, 1, 1).expand(T, props.shape[1], 1), props[..., :4]], -1).view(-1, 5)
-        else:
-            plist = [props[t, :cnt[t]] for t in range(T)] if props is not None else proposals
-            rois = torch.cat([torch.cat([p.new_full((p.shape[0], 1), t), p[:, :4]], -1) for t, p in enumerate(plist)], 0)
-        rows = self.bbox_roi_extractor.roi_layers[0].forward_nhwc_split(c5, rois.contiguous())
-        return rois, cnt, rows, dict(c5=c5, proposals=props)
+    def _detect(self, c4, img_meta, V, T, key_dim, rescale, proposals=None, return_aux=False):
+        """window.detect_windows + the one device->host read of the step -> per video the list (one entry per head
+        output) of bbox2result lists; optionally the intermediate tensors (tests / parity reports)."""
+        from . import window
+        result, fs, outs = window.detect_windows(self, c4, img_meta, V, T, key_dim, rescale, proposals=proposals)
+        counts, per_video = result.parse(result.buf.cpu())
+        nc = self.bbox_head.num_classes
+        res = [[bbox2result(d, l, nc) for d, l in pv] for pv in per_video]
+        if not return_aux:
+            return res
+        assert V == 1, 'return_aux is a single-window facility'
+        P = fs.P
+        n = counts[key_dim]
+        rois = torch.cat([fs.rois[t * P:t * P + counts[t]] for t in range(T)], 0)     # the reference's compact roi list
+        aux = dict(c5=fs.c5, proposals=fs.props, counts=counts, rois=rois, start=int(sum(counts[:key_dim])), length=n,
+                   cls=[self.bbox_head._split_out(o)[0][:n] for o in outs],
+                   reg=[self.bbox_head._split_out(o)[1][:n] for o in outs],
+                   dets=[(d[0], l[0], k[0:1]) for d, l, k in result.outs], frame_stages=fs)
+        return res, aux
 
 
 @DETECTORS.register_module
@@ -629,14 +629,7 @@ class FasterRCNN(TwoStageDetector):
 
     def simple_test(self, img, img_meta, proposals=None, rescale=False):
         c4 = self.extract_feat(img)[0]._hvr_split
-        rois, cnt, rows, _ = self._rois_and_feats(c4, img_meta, proposals)
-        cls, reg = self.bbox_head(rows)
-        m = img_meta[0]
-        rois0 = rois.clone()
-        rois0[:, 0] = 0
-        d, l, n = self.bbox_head.get_det_bboxes(rois0, cls, reg, m['img_shape'], m['scale_factor'], rescale=rescale,
-                                                cfg=self.test_cfg.rcnn)
-        return _result_from_device(d, l, n, self.bbox_head.num_classes)
+        return self._detect(c4, img_meta, 1, 1, 0, rescale, proposals=proposals)[0][0]
 
 
 class _WindowRCNN(TwoStageDetector):
@@ -654,44 +647,28 @@ class _WindowRCNN(TwoStageDetector):
         if (self._runner is not None and proposals is None and support is None and not return_aux
                 and not isinstance(x, torch.Tensor) and all(hasattr(t, '_hvr_split') for t in x)):
             out = self._runner.detect([[t._hvr_split for t in x]], img_meta, rescale)[0]
-            if out is not None:
-                return [bbox2result(d, l, self.bbox_head.num_classes) for d, l in out]
+            return [bbox2result(d, l, self.bbox_head.num_classes) for d, l in out]
+        if support is not None:
+            raise HvrError('forward_feat(support=...) was replaced by forward_feat_intervideo (fixed-size exchange)')
         c4 = self._window_split(x)
-        rois, cnt, rows, aux = self._rois_and_feats(c4, img_meta, proposals)
-        cur_range = self._key_range(cnt)
-        s, n = cur_range[0]['start'], cur_range[0]['length']
-        rois_key = rois[s:s + n].clone()
-        rois_key[:, 0] = 0                                               # bbox2roi([props_key]) -> batch idx 0
-        cls, reg = self._head(rows, cur_range, support)
-        m = img_meta[0]                                                  # frame 0's meta, hnmb_rcnn.py:603-604
-        outs = self.bbox_head.get_det_bboxes(rois_key, cls, reg, m['img_shape'], m['scale_factor'], rescale=rescale,
-                                             cfg=self.test_cfg.rcnn)
-        res = [_result_from_device(d, l, k, self.bbox_head.num_classes) for d, l, k in outs]
+        T = c4.shape[0]
+        out = self._detect(c4, img_meta, 1, T, self.key_dim, rescale, proposals=proposals, return_aux=return_aux)
         if return_aux:
-            aux.update(rois=rois, counts=cnt, cls=cls, reg=reg, dets=outs, start=s, length=n)
-            return res, aux
-        return res
+            return out[0][0], out[1]
+        return out[0]
 
     def forward_feat_batch(self, xs, img_meta, rescale=False):
         """Throughput extension (not in the reference, whose driver handles one video per
         process): V windows of V different videos in one call -> list of V forward_feat results.
         Each video's arithmetic is exactly forward_feat's; with CUDA graphs enabled the V*T frames
         share the C5 / RPN / RoIAlign launches."""
+        V, T = len(xs), len(xs[0])
+        assert all(len(x) == T for x in xs)
         if self._runner is not None and all(hasattr(t, '_hvr_split') for x in xs for t in x):
             outs = self._runner.detect([[t._hvr_split for t in x] for x in xs], img_meta, rescale)
-        else:
-            outs = [None] * len(xs)
-        res = []
-        for x, out in zip(xs, outs):
-            if out is None:
-                runner, self._runner = self._runner, None
-                try:
-                    res.append(self.forward_feat(x=x, img_meta=img_meta, rescale=rescale))
-                finally:
-                    self._runner = runner
-            else:
-                res.append([bbox2result(d, l, self.bbox_head.num_classes) for d, l in out])
-        return res
+            return [[bbox2result(d, l, self.bbox_head.num_classes) for d, l in out] for out in outs]
+        c4 = self._window_split([t for x in xs for t in x])
+        return self._detect(c4, img_meta, V, T, self.key_dim, rescale)
 
     def simple_test(self, img, img_meta, proposals=None, rescale=False):
         pass                                                             # hnmb_rcnn.py:615-616
@@ -723,71 +700,47 @@ class HNMBRCNN(_WindowRCNN):
         """BASELINE.json configs 4-5 (oracle-defined, parity unpinned by the
         reference): V local key frames, one window each; stage 4 of every key frame also attends
         to the post-fc_new_4 key rows of `n_support` other key frames (ring order over all ranks,
-        intervideo.support_indices) gathered with ONE all-gather.  Every frame must yield the same
-        number of proposals P (the all-gather is fixed-size); otherwise a ValueError is raised.
+        intervideo.support_indices) gathered with ONE all-gather.  Frames may yield fewer than max_num
+        proposals: every key frame travels as a fixed block of rows plus its count, and the receivers mask
+        the support keys with the counts (window.inter_stage_a/b/c).
         support_select='similarity' (next row N4): the supports of a key frame are the n_support videos
         whose descriptor - max over the window's frames of the spatially averaged C5 map, as
         get_triplet_patches builds it (hnmb_rcnn.py:76-101) - is most similar to its own; the descriptors
         travel inside the same all-gather."""
-        from . import intervideo
+        import torch.distributed as dist
+        from . import intervideo, window
         if support_select not in ('ring', 'similarity'):
             raise ValueError('support_select must be "ring" or "similarity", got %r' % (support_select,))
-        P = self.test_cfg.rpn['max_num']
-        head = self.bbox_head
-        per_video, z, desc = [], [], []
         V, T = len(xs), len(xs[0])
-        if proposals is None and V > 1 and all(len(x) == T for x in xs):
-            # all V windows at once: C5 / RPN / proposals / RoIAlign over the V*T frames, stages 1-3 with
-            # the row-wise GEMMs batched over the videos (engine.hrnmp_stage123_batched)
-            c4 = self._window_split([t for x in xs for t in x])
-            c5 = self.shared_head.forward_nhwc(c4) if self.feat_from_shared_head else ops.merge(c4)
-            props, counts = self.rpn_head.get_proposals(c4, img_meta[0]['img_shape'], self.test_cfg.rpn)
-            cnt = counts.cpu().tolist()
-            if any(c != P for c in cnt):
-                raise ValueError('inter-video exchange needs %d proposals per frame, got %s' % (P, cnt))
-            dev = c4.hi.device
-            N, s = T * P, self.key_dim * P
-            Npad = ops.round_up(N, 64)
-            fidx = torch.arange(V * T, device=dev, dtype=torch.float32).view(V * T, 1, 1).expand(V * T, P, 1)
-            rois = torch.cat([fidx, props[..., :4]], -1).view(V, N, 5)
-            rois_p = torch.zeros((V, Npad, 5), device=dev)
-            rois_p[:, :N] = rois
-            rows = self.bbox_roi_extractor.roi_layers[0].forward_nhwc_split(c5, rois_p.view(-1, 5))
-            if support_select == 'similarity':
-                desc.append(ops.video_descriptor(c5, V))
-            out1, f4, f4T = engine.hrnmp_stage123_batched(head.packed(dev), rows, V, N, Npad, s, P)
-            for v in range(V):
-                f4v = f4[v * Npad:v * Npad + N]
-                f4Tv = ops.Split(f4T.hi[:, v * Npad:(v + 1) * Npad], f4T.lo[:, v * Npad:(v + 1) * Npad])
-                per_video.append((rois[v, s:s + P].clone(), out1[v * P:(v + 1) * P], f4v, f4Tv, s))
-                z.append(f4v[s:s + P])
-            xs = []
-        for vi, x in enumerate(xs):
-            c4 = self._window_split(x)
-            rois, cnt, rows, a = self._rois_and_feats(c4, img_meta, None if proposals is None else proposals[vi])
-            if any(c != P for c in cnt):
-                raise ValueError('inter-video exchange needs %d proposals per frame, got %s' % (P, cnt))
-            if support_select == 'similarity':
-                desc.append(ops.video_descriptor(a['c5'], 1))
-            s = self.key_dim * P
-            packed = head.packed(rows.hi.device)
-            out1, f4, f4T = engine.hrnmp_stage123(packed, rows, s, P)
-            per_video.append((rois[s:s + P].clone(), out1, f4, f4T, s))
-            z.append(f4[s:s + P])
-        z_local = ops.Split(torch.cat([t.hi for t in z], 0), torch.cat([t.lo for t in z], 0))
-        supports = intervideo.gather_support(z_local, P, n_support, group,
-                                             desc_local=torch.cat(desc, 0) if desc else None)
-        m = img_meta[0]
-        results, aux = [], []
-        for (rois_key, out1, f4, f4T, s), sup in zip(per_video, supports):
-            out2 = engine.hrnmp_stage4(head.packed(f4.hi.device), f4, f4T, s, P, sup if sup.hi.shape[0] else None)
-            rois_key[:, 0] = 0
-            (c1, r1), (c2, r2) = head._split_out(out1), head._split_out(out2)
-            outs = head.get_det_bboxes(rois_key, [c1, c2], [r1, r2], m['img_shape'], m['scale_factor'],
-                                       rescale=rescale, cfg=self.test_cfg.rcnn)
-            results.append([_result_from_device(d, l, k, head.num_classes) for d, l, k in outs])
-            aux.append(dict(cls=[c1, c2], reg=[r1, r2], support=sup))
-        return (results, aux) if return_aux else results
+        assert all(len(x) == T for x in xs)
+        if (self._runner is not None and proposals is None and not return_aux and support_select == 'ring'
+                and all(hasattr(t, '_hvr_split') for x in xs for t in x)):
+            outs = self._runner.detect_inter([[t._hvr_split for t in x] for x in xs], img_meta, rescale, n_support, group)
+            return [[bbox2result(d, l, self.bbox_head.num_classes) for d, l in out] for out in outs]
+        on = dist.is_available() and dist.is_initialized()
+        world, rank = (dist.get_world_size(group), dist.get_rank(group)) if on else (1, 0)
+        c4 = self._window_split([t for x in xs for t in x])
+        flat = None if proposals is None else [p for pv in proposals for p in pv]
+        st = window.inter_stage_a(self, c4, img_meta, V, T, self.key_dim, n_support, support_select, proposals=flat)
+        recv, _ = intervideo.exchange(st.send, group)
+        window.inter_stage_b(self, st, img_meta, rescale)
+        window.inter_stage_c(self, st, recv, img_meta, rescale, world, rank)
+        counts, per_video = st.result.parse(st.result.buf.cpu())
+        nc = self.bbox_head.num_classes
+        results = [[bbox2result(d, l, nc) for d, l in pv] for pv in per_video]
+        if not return_aux:
+            return results
+        P, S = st.fs.P, n_support
+        kc = [counts[v * T + self.key_dim] for v in range(V)]
+        aux = []
+        for v in range(V):
+            n = kc[v]
+            c1, r1 = self.bbox_head._split_out(st.out1[v * P:v * P + n])
+            c2, r2 = self.bbox_head._split_out(st.out2[v * P:v * P + n])
+            sup = ops.Split(st.sup_rows.hi[v * S * P:(v + 1) * S * P], st.sup_rows.lo[v * S * P:(v + 1) * S * P])
+            aux.append(dict(cls=[c1, c2], reg=[r1, r2], support=sup, selected=st.sel[v].tolist(),
+                            support_counts=st.fs.seg[v, T:].tolist()))
+        return results, aux
 
 
 @DETECTORS.register_module

@@ -447,13 +447,14 @@ def gather_rows(src, dst, n_problems, n_rows, idx=None, src_rpp=0, src_row0=0, d
     return dst
 
 
-def support_index(sel, pool_counts, P, T, seg_counts):
-    """sel int64 [V,S], pool_counts int32 [G] -> idx int32 [V, S*P] (rows of the pool), and fills the support
+def support_index(sel, pool_counts, counts_rank_stride, vpr, rank_stride_rows, P, T, seg_counts):
+    """sel int64 [V,S] global key-frame indices -> idx int32 [V, S*P] (rows of the gathered pool); fills the support
     blocks [T, T+S) of seg_counts [V, n_segs] in place.  See hvr_support_index."""
     V, S = sel.shape
     idx = torch.empty((V, S * P), dtype=torch.int32, device=sel.device)
     assert sel.dtype == torch.int64 and sel.is_contiguous() and pool_counts.dtype == torch.int32
-    check(_lib.lib().hvr_support_index(_p(sel), _p(pool_counts), V, S, P, T, _p(idx), _p(seg_counts),
+    check(_lib.lib().hvr_support_index(_p(sel), _p(pool_counts), int(counts_rank_stride), int(vpr),
+                                       int(rank_stride_rows), V, S, P, T, _p(idx), _p(seg_counts),
                                        seg_counts.shape[1], _stream()), 'hvr_support_index')
     return idx
 

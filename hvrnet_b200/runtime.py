@@ -8,11 +8,10 @@ the same calls - unchanged kernels, unchanged order - into two CUDA graphs per i
   window graph   window of T C4 maps (static buffer) -> C5, RPN, proposals, RoIAlign,
                  relation head, decode + multiclass NMS -> one packed result buffer
 
-so a key frame costs two graph launches and ONE device->host read.  The window graph is
-captured for the common case "every frame yields max_num proposals" (row offsets are then
-static); the per-frame counts travel back with the result and, if any frame produced fewer
-proposals, the frame is recomputed on the eager path with the actual counts - results never
-depend on the speculation.
+so a key frame costs two graph launches and ONE device->host read.  Every frame keeps a fixed block of
+max_num rows and its proposal count stays on the device as a mask (window.py), so the SAME graph replays
+whether or not a frame yields fewer proposals than max_num - there is no speculation and no eager failover.
+The inter-video split (configs 4-5) is three graphs around the one all-gather (``detect_inter``).
 """
 import torch
 
@@ -20,7 +19,8 @@ from . import _lib, ops
 
 
 class _Captured:
-    __slots__ = ('graph', 'fn', 'inputs', 'outputs', 'launches', 'perm', 'perm_host', 'perm_pin', 'ring')
+    __slots__ = ('graph', 'fn', 'inputs', 'outputs', 'launches', 'perm', 'perm_host', 'perm_pin', 'ring', 'result',
+                 'host', 'side', 'comm', 'sel', 'graphs', 'state', 'group', 'world', 'recv_flat', 'ev')
 
 
 class WindowRing:
@@ -117,15 +117,16 @@ class GraphRunner:
         self._staged = (img, trunk, ev)             # holds the tensor: identity cannot be recycled while staged
 
     # ------------------------------------------------------------------ capture helper
-    def _capture(self, fn):
+    def _capture(self, fn, warm=True):
         """Warm up eagerly (lazy weight packing, func attributes, tensor-map cache), then capture."""
         torch.cuda.synchronize()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            fn()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
+        if warm:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
         c = _Captured()
         c.fn = fn
         if not getattr(self, 'capture', True):
@@ -185,157 +186,168 @@ class GraphRunner:
         return outs
 
     # ------------------------------------------------------------------ window(s)
+    def _window_key(self, kind, windows, img_meta, rescale, extra=()):
+        from .window import scale_of
+        meta = img_meta[0]
+        return (kind, len(windows), len(windows[0]), tuple(windows[0][0].shape), tuple(meta['img_shape'][:2]),
+                scale_of(meta), bool(rescale), self.m.key_dim) + tuple(extra)
+
+    def _new_window(self, windows, n_out):
+        """Static state of a window capture: the input ring, the slot permutation, the result buffer."""
+        from .window import ResultBuffer
+        m = self.m
+        V, T = len(windows), len(windows[0])
+        dev = windows[0][0].hi.device
+        _, h, w, C = windows[0][0].shape
+        c = _Captured()
+        c.inputs = ops.Split.zeros((V * T, h, w, C), dev)
+        c.perm = torch.arange(V * T, device=dev)            # window position -> ring slot (static graph input)
+        c.perm_host = list(range(V * T))
+        c.perm_pin = torch.empty(V * T, dtype=torch.int64).pin_memory()
+        c.ring = WindowRing(V, T)
+        c.result = ResultBuffer(V * T, V, n_out, m.test_cfg.rcnn['max_per_img'], dev)
+        c.host = torch.empty(c.result.nbytes, dtype=torch.uint8).pin_memory()
+        c.side = [torch.cuda.Stream(), torch.cuda.Stream()]
+        return c
+
+    @staticmethod
+    def _fill(c, windows):
+        """Bring the static window buffer up to date: only the frames WindowRing has not seen in the
+        previous calls are copied; `perm` (window position -> ring slot) is a graph input."""
+        copies, perm = c.ring.place(windows)
+        for slot, p in copies:
+            c.inputs.hi[slot].copy_(p.hi[0])
+            c.inputs.lo[slot].copy_(p.lo[0])
+        if perm != c.perm_host:
+            # pinned staging buffer: the previous step's copy has completed (every step ends with a
+            # device->host read), so it can be rewritten here
+            c.perm_pin.copy_(torch.tensor(perm, dtype=torch.int64))
+            c.perm.copy_(c.perm_pin, non_blocking=True)
+            c.perm_host = perm
+
+    @staticmethod
+    def _read(c):
+        """The one device->host read of the step (pinned buffer, then the stream is synchronised)."""
+        c.host.copy_(c.result.buf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return c.result.parse(c.host)[1]
+
     def detect(self, windows, img_meta, rescale):
-        """windows: list of V windows, each a list of T per-frame C4 Splits [1,h,w,C] (V key
-        frames of V different videos are batched through one graph: C5 / RPN / proposals /
-        RoIAlign run over all V*T frames at once, the relation head once per video).
-        Returns, per video, the list of per-output (dets, labels) host tensors, or None for
-        the videos whose speculation (every frame yields max_num proposals) failed."""
+        """windows: list of V windows, each a list of T per-frame C4 Splits [1,h,w,C] (V key frames of V different
+        videos are batched through one graph: C5 / RPN / proposals / RoIAlign run over all V*T frames at once, the
+        row-wise head GEMMs over all videos, the attention products one batched launch per stage).  Frames that
+        yield fewer than max_num proposals replay the same graph: the per-frame counts are device-side masks
+        (window.py).  Returns, per video, the list of per-output (dets, labels) host tensors."""
+        from . import window
         self._check_weights()
         m = self.m
         V, T = len(windows), len(windows[0])
-        meta = img_meta[0]
-        sf = meta['scale_factor']
-        sf = float(sf if not hasattr(sf, '__len__') else sf[0])
-        key = (V, T, tuple(windows[0][0].shape), tuple(meta['img_shape'][:2]), sf, bool(rescale), m.key_dim)
+        key = self._window_key('intra', windows, img_meta, rescale)
         c = self._window.get(key)
-        P = m.test_cfg.rpn['max_num']
-        M = m.test_cfg.rcnn['max_per_img']
-
-        def fill(c):
-            """Bring the static window buffer up to date: only the frames WindowRing has not seen in the
-            previous calls are copied; `perm` (window position -> ring slot) is a graph input."""
-            copies, perm = c.ring.place(windows)
-            for slot, p in copies:
-                c.inputs.hi[slot].copy_(p.hi[0])
-                c.inputs.lo[slot].copy_(p.lo[0])
-            if perm != c.perm_host:
-                # pinned staging buffer: the previous step's copy has completed (every step ends with a
-                # device->host read), so it can be rewritten here
-                c.perm_pin.copy_(torch.tensor(perm, dtype=torch.int64))
-                c.perm.copy_(c.perm_pin, non_blocking=True)
-                c.perm_host = perm
-
         if c is None:
-            dev = windows[0][0].hi.device
-            _, h, w, C = windows[0][0].shape
-            win = ops.Split.zeros((V * T, h, w, C), dev)
-            perm = torch.arange(V * T, device=dev)          # window position -> ring slot (static graph input)
-
-            side = [torch.cuda.Stream(), torch.cuda.Stream()]
+            c = self._new_window(windows, 2 if m.bbox_head.kind == 'hrnmp' else 1)
 
             def fn():
-                main = torch.cuda.current_stream()
-                # RPN maps first; proposal generation (sort + decode + greedy NMS: 15 busy CTAs, latency
-                # bound) then runs on a forked branch UNDER the C5 convolutions instead of after them
-                maps = m.rpn_head.forward_maps(win)
-                side[0].wait_stream(main)
-                with torch.cuda.stream(side[0]):
-                    props, counts = m.rpn_head.proposals_from_maps(maps, meta['img_shape'], m.test_cfg.rpn)
-                c5 = m.shared_head.forward_nhwc(win) if m.feat_from_shared_head else ops.merge(win)
-                main.wait_stream(side[0])
-                props, counts = props.index_select(0, perm), counts.index_select(0, perm)   # slot -> window order
-                fidx = perm.to(torch.float32).view(V * T, 1, 1).expand(V * T, P, 1)
-                rois = torch.cat([fidx, props[..., :4]], -1).view(-1, 5).contiguous()
-                flat = [counts.float()]
-                forked, per_video = set(), []
-                s = m.key_dim * P
-                N = T * P
-                head = m.bbox_head
-                if V > 1:
-                    # batched head: rows of video v live at [v*Npad, v*Npad + N) (Npad = N rounded up to 64);
-                    # the pad rows pool a dummy 1-pixel RoI and never reach a result
-                    from . import engine
-                    Npad = ops.round_up(N, 64)
-                    rois_p = torch.zeros((V, Npad, 5), device=dev)
-                    rois_p[:, :N] = rois.view(V, N, 5)
-                    rows = m.bbox_roi_extractor.roi_layers[0].forward_nhwc_split(c5, rois_p.view(-1, 5))
-                    packed = head.packed(dev)
-                    # key-frame rois of every video, batch index 0 as bbox2roi([props_key]) gives them
-                    rois_key = rois.view(V, N, 5)[:, s:s + P].reshape(V * P, 5).clone()
-                    rois_key[:, 0] = 0
-
-                    def post(j, h):
-                        """decode + multiclass NMS of head output j for all V key frames: one launch per
-                        stage (hvr_det_postprocess_batched), on a forked branch"""
-                        st = side[j % 2]
-                        st.wait_stream(main)
-                        forked.add(st)
-                        cls_, reg_ = head._split_out(h)
-                        with torch.cuda.stream(st):
-                            return head.get_det_bboxes_batched(rois_key, cls_, reg_, V, meta['img_shape'], sf,
-                                                               rescale=rescale, cfg=m.test_cfg.rcnn)
-                    if head.kind == 'hrnmp':
-                        # the branch output is post-processed under stages 3-4
-                        out1, f4, f4T = engine.hrnmp_stage123_batched(packed, rows, V, N, Npad, s, P)
-                        b1 = post(0, out1)
-                        a4 = engine.relation_batched(packed, 4, f4, f4T, V, N, Npad, q_range=(s, P),
-                                                     res=engine._key_rows(f4, V, Npad, s, P))
-                        _, out2, _ = engine.lin(a4, packed['out2'], want_split=False, want_f32=True)
-                        batched = [b1, post(1, out2)]
-                        keep = [maps, props, counts, c5, rois, rois_p, rows, out1, f4, f4T, a4, out2, rois_key, batched]
-                    else:
-                        out1 = engine.selsa_forward_batched(packed, rows, V, N, Npad, s, P)
-                        batched = [post(0, out1)]
-                        keep = [maps, props, counts, c5, rois, rois_p, rows, out1, rois_key, batched]
-                    for v in range(V):
-                        per_video.append([(d[v], l[v], k[v:v + 1]) for d, l, k in batched])
-                else:
-                    rows = m.bbox_roi_extractor.roi_layers[0].forward_nhwc_split(c5, rois)
-                    keep = [maps, props, counts, c5, rois, rows]
-                    cls, reg = m._head(rows[0:T * P], [dict(start=s, length=P)], None)
-                    rois_key = rois[s:s + P].clone()
-                    rois_key[:, 0] = 0
-                    # the head outputs are post-processed on parallel branches (tiny, latency-bound kernels)
-                    outs = []
-                    for j, (c_, r_) in enumerate(zip(cls, reg)):
-                        st = side[j % 2]
-                        st.wait_stream(main)
-                        forked.add(st)
-                        with torch.cuda.stream(st):
-                            outs.append(m.bbox_head.get_det_bboxes(rois_key, c_, r_, meta['img_shape'], sf,
-                                                                   rescale=rescale, cfg=m.test_cfg.rcnn))
-                    keep += [cls, reg, rois_key, outs]
-                    per_video.append(outs)
-                for st in forked:                       # join only the branches that were forked
-                    main.wait_stream(st)
-                for outs in per_video:
-                    for d, l, k in outs:
-                        flat += [k.float(), d.reshape(-1), l.float()]
-                return torch.cat(flat), keep
-            c = _Captured()
-            c.inputs, c.perm, c.perm_host = win, perm, list(range(V * T))
-            c.perm_pin = torch.empty(V * T, dtype=torch.int64).pin_memory()
-            c.ring = WindowRing(V, T)
-            fill(c)                                     # real data for the warm-up pass
+                keep = []
+                window.detect_windows(m, c.inputs, img_meta, V, T, m.key_dim, rescale, perm=c.perm, side=c.side,
+                                      result=c.result, keep=keep)
+                return keep
+            self._fill(c, windows)                          # real data for the warm-up pass
             cap = self._capture(fn)
             c.graph, c.fn, c.outputs, c.launches = cap.graph, cap.fn, cap.outputs, cap.launches
             self._window[key] = c
-        fill(c)
+        self._fill(c, windows)
         self._replay(c)
         self.replayed_launches += c.launches
-        host = c.outputs[0].cpu()                       # the one device->host read of the step
-        n_out = (host.numel() - V * T) // (V * (1 + 6 * M))
-        res, o = [], V * T
-        for v in range(V):
-            ok = bool((host[v * T:(v + 1) * T] == P).all())
-            outs = []
-            for _ in range(n_out):
-                k = int(host[o])
-                d = host[o + 1:o + 1 + 5 * M].view(M, 5)[:k]
-                l = host[o + 1 + 5 * M:o + 1 + 6 * M][:k].long()
-                outs.append((d, l))
-                o += 1 + 6 * M
-            res.append(outs if ok else None)
-        return res
+        return self._read(c)
+
+    def detect_inter(self, windows, img_meta, rescale, n_support, group=None):
+        """Inter-video split (BASELINE.json configs 4-5): three captured graphs around the ONE all-gather, which is
+        issued on a communication stream right after stage 3 / fc_new_4 (graph A) and runs under graph B - the
+        post-processing of the branch output and the k_4 projection of the window's own rows; graph C (support rows
+        out of the receive buffer, stage 4, post-processing) waits for it.  No host synchronisation before the final
+        device->host read."""
+        import torch.distributed as dist
+        from . import intervideo, window
+        self._check_weights()
+        m = self.m
+        V, T = len(windows), len(windows[0])
+        on = dist.is_available() and dist.is_initialized()
+        world, rank = (dist.get_world_size(group), dist.get_rank(group)) if on else (1, 0)
+        key = self._window_key('inter', windows, img_meta, rescale, (n_support, world, rank))
+        c = self._window.get(key)
+        main = torch.cuda.current_stream()
+        if c is None:
+            c = self._new_window(windows, 2)
+            c.comm = torch.cuda.Stream()
+            c.sel = window.ring_selection(rank, world, V, n_support, c.inputs.hi.device)
+            box = {}
+
+            def fn_a():
+                box['st'] = window.inter_stage_a(m, c.inputs, img_meta, V, T, m.key_dim, n_support, 'ring', perm=c.perm,
+                                                 side=c.side, result=c.result)
+                return box['st']
+
+            def fn_b():
+                return window.inter_stage_b(m, box['st'], img_meta, rescale, side=c.side)
+
+            def fn_c():
+                return window.inter_stage_c(m, box['st'], box['recv'], img_meta, rescale, world, rank, sel=c.sel)
+
+            self._fill(c, windows)
+            # warm-up pass of the whole chain (lazy packing, kernel attributes, NCCL communicator), then the captures
+            fn_a()
+            box['recv'], _ = intervideo.exchange(box['st'].send, group)
+            fn_b()
+            fn_c()
+            torch.cuda.synchronize()
+            ga = self._capture(fn_a, warm=False)
+            st = box['st']
+            if world > 1:
+                c.recv_flat = torch.empty((world * 2,) + tuple(st.send.shape[1:]), dtype=st.send.dtype,
+                                          device=st.send.device)
+                box['recv'] = c.recv_flat.view((world,) + tuple(st.send.shape))
+            else:
+                c.recv_flat = None
+                box['recv'] = st.send.unsqueeze(0)
+            gb = self._capture(fn_b, warm=False)
+            gc = self._capture(fn_c, warm=False)
+            c.graphs, c.state, c.group, c.world = (ga, gb, gc), box, group, world
+            c.launches = ga.launches + gb.launches + gc.launches
+            c.ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self._window[key] = c
+        self._fill(c, windows)
+        ga, gb, gc = c.graphs
+        self._replay(ga)
+        if c.world > 1:
+            c.comm.wait_stream(main)
+            with torch.cuda.stream(c.comm):
+                c.ev[0].record()
+                dist.all_gather_into_tensor(c.recv_flat, c.state['st'].send, group=c.group)
+                c.ev[1].record()
+        self._replay(gb)
+        if c.world > 1:
+            main.wait_stream(c.comm)
+        self._replay(gc)
+        self.replayed_launches += c.launches
+        self.last_inter = c
+        return self._read(c)
+
+    def last_all_gather_ms(self):
+        """Device time of the most recent all-gather (events on the communication stream), or None."""
+        c = getattr(self, 'last_inter', None)
+        if c is None or c.world == 1:
+            return None
+        return c.ev[0].elapsed_time(c.ev[1])
 
 
 class StreamGraphRunner:
     """CUDA-graph executor of the streaming scheduler (streaming.py) for V
     video streams advanced in lock-step.  Per step: ONE frame graph (trunk, C5, RPN, proposals,
     RoIAlign, fc_new_1 for the V new frames) and ONE head graph (relation stages, decode, NMS for
-    the V key frames on the cached rows), one device->host read.  Captured for the common case
-    of max_num proposals per frame; a short frame raises (use streaming.StreamingDetector then)."""
+    the V key frames on the cached rows), one device->host read.  Every cached frame carries its own proposal
+    count; the head graph masks the keys of all T frames of every window with them, so frames that yield fewer
+    than max_num proposals are handled inside the graphs (same arithmetic as forward_feat)."""
 
     def __init__(self, model, n_videos, window=None):
         from collections import deque
@@ -343,84 +355,88 @@ class StreamGraphRunner:
         self.V = n_videos
         self.T = int(window or model.bbox_head.t_dim)
         self.P = model.test_cfg.rpn['max_num']
-        self.cache = [deque(maxlen=self.T) for _ in range(n_videos)]      # per video: (props, f1, f1T)
+        self.cache = [deque(maxlen=self.T) for _ in range(n_videos)]   # per video: (props, count, f1 hi/lo, f1T hi/lo)
         self._frame = None
         self._head = None
         self.replayed_launches = 0
         self._cap = GraphRunner._capture
+        self.capture = True
+        self._version = model.weights_version()
 
     def _frame_graph(self, img, meta):
-        m, V, P = self.m, self.V, self.P
+        from . import engine, window
+        m, V = self.m, self.V
         buf = torch.zeros(img.shape, dtype=torch.float32, device='cuda:%d' % torch.cuda.current_device())
-        dev = buf.device
 
         def fn():
             c4 = m.backbone.forward_split(buf)
-            maps = m.rpn_head.forward_maps(c4)
-            props, counts = m.rpn_head.proposals_from_maps(maps, meta['img_shape'], m.test_cfg.rpn)
-            c5 = m.shared_head.forward_nhwc(c4)
-            fidx = torch.arange(V, device=dev, dtype=torch.float32).view(V, 1, 1).expand(V, P, 1)
-            rois = torch.cat([fidx, props[..., :4]], -1).view(-1, 5).contiguous()
-            rows = m.bbox_roi_extractor.roi_layers[0].forward_nhwc_split(c5, rois)
-            f1, f1T = engine_head_fc1(m, rows)
-            return props, counts, f1, f1T, (c4, maps, c5, rois, rows)
+            fs = window.frame_stages(m, c4, meta['img_shape'], V, 1, 0)
+            f1, f1T = engine.head_fc1(m.bbox_head.packed(buf.device), fs.rows)
+            return fs.props, fs.counts, f1, f1T, (c4, fs)
         c = self._cap(self, fn)
         c.inputs = buf
         return c
 
     def _head_graph(self, meta, rescale):
+        from . import engine, window
         m, V, T, P = self.m, self.V, self.T, self.P
         dev = self._frame.inputs.device
         D = self._frame.outputs[2].shape[1]
         N = T * P
-        f1w = [ops.Split.zeros((N, D), dev) for _ in range(V)]
-        f1Tw = [ops.Split.zeros((D, ops.round_up(N, 64)), dev) for _ in range(V)]
-        rk = [torch.zeros((P, 5), device=dev) for _ in range(V)]
-        counts = self._frame.outputs[1]
-        sf = meta['scale_factor']
-        sf = float(sf if not hasattr(sf, '__len__') else sf[0])
+        Npad = ops.round_up(N, 64)
         head = m.bbox_head
+        fs = window.FrameStages()                           # the inputs of the window-dependent stages, static buffers
+        fs.V, fs.T, fs.P, fs.N, fs.Npad = V, T, P, N, Npad
+        fs.rois_key = torch.zeros((V * P, 5), device=dev)
+        fs.seg = torch.zeros((V, T), dtype=torch.int32, device=dev)
+        fs.key_counts = torch.zeros(V, dtype=torch.int32, device=dev)
+        f1w = ops.Split.zeros((V * Npad, D), dev)
+        f1Tw = ops.Split.zeros((D, V * Npad), dev)
+        n_out = 2 if head.kind == 'hrnmp' else 1
+        result = window.ResultBuffer(V * T, V, n_out, m.test_cfg.rcnn['max_per_img'], dev)
         side = [torch.cuda.Stream(), torch.cuda.Stream()]
+        sf = window.scale_of(meta)
+        s = m.key_dim * P
 
         def fn():
             main = torch.cuda.current_stream()
             packed = head.packed(dev)
-            flat, keep = [counts.float()], []
-            forked, per_video = set(), []
-            s = m.key_dim * P
-            from . import engine
-            for v in range(V):
-                if head.kind == 'hrnmp':
-                    o1, o2, _ = engine.hrnmp_forward_test(packed, None, s, P, f1=f1w[v], f1T=f1Tw[v])
-                    outs = [o1, o2]
-                else:
-                    outs = [engine.selsa_forward(packed, None, s, P, f1=f1w[v], f1T=f1Tw[v])]
-                dets, used = [], []
-                for j, o in enumerate(outs):
-                    cls, reg = head._split_out(o)
-                    st = side[j % 2]
-                    st.wait_stream(main)
-                    used.append(st)
-                    with torch.cuda.stream(st):
-                        dets.append(head.get_det_bboxes(rk[v], cls, reg, meta['img_shape'], sf, rescale=rescale,
-                                                        cfg=m.test_cfg.rcnn))
-                forked.update(used)
-                keep += [outs, dets]
-                per_video.append(dets)
+            mask = engine.KeyMask(fs.seg, P)
+            forked = []
+
+            def post(j, o):
+                st = side[j % 2]
+                st.wait_stream(main)
+                forked.append(st)
+                with torch.cuda.stream(st):
+                    window.post_process(m, fs, o, V, meta['img_shape'], sf, rescale, out=result.outs[j])
+            if head.kind == 'hrnmp':
+                out1, f4, f4T = engine.hrnmp_stage123_batched(packed, None, V, N, Npad, s, P, mask=mask, f1=f1w, f1T=f1Tw)
+                post(0, out1)
+                out2 = engine.hrnmp_stage4_batched(packed, f4, f4T, V, N, Npad, s, P, mask=mask)
+                post(1, out2)
+                keep = [out1, out2, f4, f4T]
+            else:
+                out1 = engine.selsa_forward_batched(packed, None, V, N, Npad, s, P, mask=mask, f1=f1w, f1T=f1Tw)
+                post(0, out1)
+                keep = [out1]
             for st in forked:
                 main.wait_stream(st)
-            for dets in per_video:
-                for d, l, k in dets:
-                    flat += [k.float(), d.reshape(-1), l.float()]
-            return torch.cat(flat), keep
+            return keep
         c = self._cap(self, fn)
-        c.inputs = (f1w, f1Tw, rk)
+        c.inputs = (f1w, f1Tw, fs)
+        c.result = result
+        c.host = torch.empty(result.nbytes, dtype=torch.uint8).pin_memory()
         return c
 
     def push(self, img, meta, rescale=True):
         """img [V,3,H,W] (device or pinned host): the next frame of each of the V streams.
         Returns None while the windows fill, then a list of V forward_feat-style results."""
         V, T, P = self.V, self.T, self.P
+        if self.m.weights_version() != self._version:      # weights changed under the captured graphs: start over
+            torch.cuda.synchronize()
+            self._frame = self._head = None
+            self._version = self.m.weights_version()
         if self._frame is None:
             self._frame = self._frame_graph(img, meta)
         fr = self._frame
@@ -428,44 +444,33 @@ class StreamGraphRunner:
         fr.graph.replay()
         self.replayed_launches += fr.launches
         props, counts, f1, f1T = fr.outputs[:4]
+        B = f1.shape[0] // V                                 # rows per video in the frame graph (P rounded up to 64)
         for v in range(V):
-            self.cache[v].append((props[v].clone(), f1.hi[v * P:(v + 1) * P].clone(), f1.lo[v * P:(v + 1) * P].clone(),
-                                  f1T.hi[:, v * P:(v + 1) * P].clone(), f1T.lo[:, v * P:(v + 1) * P].clone()))
+            self.cache[v].append((props[v].clone(), counts[v:v + 1].clone(),
+                                  f1.hi[v * B:v * B + P].clone(), f1.lo[v * B:v * B + P].clone(),
+                                  f1T.hi[:, v * B:v * B + P].clone(), f1T.lo[:, v * B:v * B + P].clone()))
         if len(self.cache[0]) < T:
             return None
         if self._head is None:
             self._head = self._head_graph(meta, rescale)
         hd = self._head
-        f1w, f1Tw, rk = hd.inputs
-        N = T * P
+        f1w, f1Tw, fs = hd.inputs
+        N, Npad = fs.N, fs.Npad
+        key = self.m.key_dim
         for v in range(V):
             fl = list(self.cache[v])
-            torch.cat([f[1] for f in fl], 0, out=f1w[v].hi)
-            torch.cat([f[2] for f in fl], 0, out=f1w[v].lo)
-            torch.cat([f[3] for f in fl], 1, out=f1Tw[v].hi[:, :N])
-            torch.cat([f[4] for f in fl], 1, out=f1Tw[v].lo[:, :N])
-            rk[v][:, 1:] = fl[self.m.key_dim][0][:, :4]
+            torch.cat([f[2] for f in fl], 0, out=f1w.hi[v * Npad:v * Npad + N])
+            torch.cat([f[3] for f in fl], 0, out=f1w.lo[v * Npad:v * Npad + N])
+            torch.cat([f[4] for f in fl], 1, out=f1Tw.hi[:, v * Npad:v * Npad + N])
+            torch.cat([f[5] for f in fl], 1, out=f1Tw.lo[:, v * Npad:v * Npad + N])
+            torch.cat([f[1] for f in fl], 0, out=fs.seg[v])
+            fs.rois_key[v * P:(v + 1) * P, 1:] = fl[key][0][:, :4]
+            fs.key_counts[v:v + 1].copy_(fl[key][1])
         hd.graph.replay()
         self.replayed_launches += hd.launches
-        host = hd.outputs[0].cpu()
-        if not bool((host[:V] == P).all()):
-            raise RuntimeError('a frame produced fewer than %d proposals: use streaming.StreamingDetector' % P)
-        M = self.m.test_cfg.rcnn['max_per_img']
-        n_out = (host.numel() - V) // (V * (1 + 6 * M))
+        hd.host.copy_(hd.result.buf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        per_video = hd.result.parse(hd.host)[1]
         from .models import bbox2result
-        res, o = [], V
-        for v in range(V):
-            outs = []
-            for _ in range(n_out):
-                k = int(host[o])
-                d = host[o + 1:o + 1 + 5 * M].view(M, 5)[:k]
-                l = host[o + 1 + 5 * M:o + 1 + 6 * M][:k].long()
-                outs.append(bbox2result(d, l, self.m.bbox_head.num_classes))
-                o += 1 + 6 * M
-            res.append(outs)
-        return res
-
-
-def engine_head_fc1(model, rows):
-    from . import engine
-    return engine.head_fc1(model.bbox_head.packed(rows.hi.device), rows)
+        nc = self.m.bbox_head.num_classes
+        return [[bbox2result(d, l, nc) for d, l in pv] for pv in per_video]

@@ -297,11 +297,16 @@ int hvr_gather_rows_split(const hvr_bf16* src_hi, const hvr_bf16* src_lo, int64_
                           int64_t src_rows_per_problem, int src_row0, hvr_bf16* dst_hi, hvr_bf16* dst_lo,
                           int64_t ld_dst, int n_problems, int n_rows, int64_t dst_rows_per_problem,
                           int dst_row0, int cols, void* stream);
-/* Support selection -> row indices into the gathered pool [G*P, D] and the support blocks of the key mask:
- *   idx[v][s*P + j] = sel[v][s]*P + j (-1 when sel < 0), seg_counts[v][T + s] = pool_counts[sel[v][s]] (0 when
- *   absent).  sel [V, S] int64 (ring order or hvr_support_select), pool_counts [G] int32. */
-int hvr_support_index(const int64_t* sel, const int* pool_counts, int V, int S, int P, int T, int* idx,
-                      int* seg_counts, int n_segs, void* stream);
+/* Support selection -> row indices into the all-gathered pool and the support blocks of the key mask.  The pool
+ * is the receive buffer of the ONE all-gather as it lies: rank r's rows start at row r*rank_stride_rows, its vpr
+ * local key frames own P rows each; its per-key-frame proposal counts are int32 at
+ * pool_counts[r*counts_rank_stride + local].  sel [V, S] int64 = global key-frame indices (ring order or
+ * hvr_support_select; < 0 = absent):
+ *   idx[v][s*P + j] = (g/vpr)*rank_stride_rows + (g%vpr)*P + j  (-1 when absent -> zero rows in the gather)
+ *   seg_counts[v][T + s] = count of key frame g (0 when absent). */
+int hvr_support_index(const int64_t* sel, const int* pool_counts, int64_t counts_rank_stride, int vpr,
+                      int64_t rank_stride_rows, int V, int S, int P, int T, int* idx, int* seg_counts,
+                      int n_segs, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Test-time image pipeline (next row N2).  Replaces the CPU DataLoader path Resize(keep_ratio)

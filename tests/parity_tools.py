@@ -260,13 +260,10 @@ def window_parity(model, sd, frames, metas, key_dim, head='hrnmp', dev='cuda:0')
     def device_stage2(proposals):
         """-> (key rois [n,5] with batch index 0, [cls...], [reg...]) through the detector's own methods"""
         if frcnn:
-            rois, cnt, rows, _ = model._rois_and_feats(c4, metas, proposals)
-            c, r = model.bbox_head(rows)
-            rk = rois.clone()
-            rk[:, 0] = 0
-            return rk, [c], [r]
-        _, aux = model(x=c4s, img=None, img_meta=metas, forward_feat=True, return_loss=False, rescale=True,
-                       proposals=proposals, return_aux=True)
+            _, aux = model._detect(c4, metas, 1, 1, 0, False, proposals=proposals, return_aux=True)
+        else:
+            _, aux = model(x=c4s, img=None, img_meta=metas, forward_feat=True, return_loss=False, rescale=True,
+                           proposals=proposals, return_aux=True)
         s_, n_ = aux['start'], aux['length']
         rk = aux['rois'][s_:s_ + n_].clone()
         rk[:, 0] = 0

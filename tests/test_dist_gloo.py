@@ -17,89 +17,59 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, V, P, D, n_support, q):
+def _worker(rank, world, port, V, P, D, C, n_support, q):
+    """One rank of the inter-video exchange on the CPU: intervideo.pack_exchange -> ONE all-gather
+    (intervideo.exchange) -> the receive buffer every rank addresses with hvr_support_index's formula."""
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
-        from hvrnet_b200 import intervideo
+        from hvrnet_b200 import intervideo, window
         from hvrnet_b200.ops import Split
-        # row r of global key frame g carries the value g*16 + r (exact in bf16) in hi and its negative in lo
-        rows = []
-        for v in range(V):
-            g = rank * V + v
-            rows.append(torch.arange(P, dtype=torch.float32).view(P, 1).expand(P, D) + 16.0 * g)
-        z = torch.cat(rows, 0)
-        zl = Split(z.to(torch.bfloat16), (-z).to(torch.bfloat16))
-        sup = intervideo.gather_support(zl, P, n_support)
-        ok = len(sup) == V
-        for v in range(V):
-            g = rank * V + v
-            idx = intervideo.support_indices(g, world * V, n_support)
-            exp = torch.cat([(torch.arange(P, dtype=torch.float32) + 16.0 * i).view(P, 1).expand(P, D) for i in idx], 0)
-            ok = ok and torch.equal(sup[v].hi, exp.to(torch.bfloat16)) and torch.equal(sup[v].lo, (-exp).to(torch.bfloat16))
-        pool = intervideo.all_gather_rows(zl)
-        ok = ok and pool.hi.shape == (world * V * P, D) and float(pool.hi[(world * V - 1) * P, 0]) == 16.0 * (world * V - 1)
-        q.put((rank, bool(ok)))
-    finally:
-        dist.destroy_process_group()
-
-
-@pytest.mark.parametrize('V,n_support', [(3, 4), (1, 4), (2, 1)])
-def test_support_exchange_world2(V, n_support):
-    world, port = 2, _free_port()
-    ctx = mp.get_context('spawn')
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, V, 4, 8, n_support, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(timeout=150)
-    assert [p.exitcode for p in procs] == [0] * world
-    res = dict(q.get(timeout=10) for _ in range(world))
-    assert res == {0: True, 1: True}
-
-
-def _worker_similarity(rank, world, port, V, P, D, C, n_support, q):
-    os.environ['MASTER_ADDR'] = '127.0.0.1'
-    os.environ['MASTER_PORT'] = str(port)
-    dist.init_process_group('gloo', rank=rank, world_size=world)
-    try:
-        from hvrnet_b200 import intervideo
-        from hvrnet_b200.ops import Split
-        from oracle import ref_torch as R
         G = world * V
         gen = torch.Generator().manual_seed(7)
-        desc_all = torch.randn(G, C, generator=gen) * 3          # every rank can rebuild the global truth
+        desc_all = torch.randn(G, C, generator=gen) * 3 if C else None   # every rank can rebuild the global truth
+        counts_all = torch.randint(1, P + 1, (G,), generator=gen, dtype=torch.int32)
+        # row j of global key frame g carries the value g*16 + j (exact in bf16) in hi and its negative in lo
         z_all = torch.cat([(torch.arange(P, dtype=torch.float32) + 16.0 * g).view(P, 1).expand(P, D) for g in range(G)], 0)
         lo_, hi_ = rank * V * P, (rank + 1) * V * P
-        zl = Split(z_all[lo_:hi_].to(torch.bfloat16), (-z_all[lo_:hi_]).to(torch.bfloat16))
-        calls = []
-
-        def selector(d, g0, n_local, k):                          # CPU stand-in for hvr_support_select
-            calls.append((tuple(d.shape), g0, n_local, k, bool(torch.equal(d, desc_all))))
-            return [R.select_support_by_similarity(d, g0 + i, k)[0] for i in range(n_local)]
-        sup = intervideo.gather_support(zl, P, n_support, desc_local=desc_all[rank * V:(rank + 1) * V], selector=selector)
-        ok = len(sup) == V and calls == [((G, C), rank * V, V, min(n_support, G - 1), True)]
+        z = Split(z_all[lo_:hi_].to(torch.bfloat16).contiguous(), (-z_all[lo_:hi_]).to(torch.bfloat16).contiguous())
+        send, rpr, n_desc = intervideo.pack_exchange(z, counts_all[rank * V:(rank + 1) * V].contiguous(),
+                                                     desc_all[rank * V:(rank + 1) * V] if C else None)
+        recv, work = intervideo.exchange(send)
+        ok = work is None and tuple(recv.shape) == (world, 2, rpr, D) and rpr == V * P + 1 + n_desc
+        flat = recv.view(world * 2 * rpr, D)
+        # the addressing hvr_support_index uses: key frame g, row j -> hi row (g // V) * 2*rpr + (g % V) * P + j, lo row + rpr
+        sel = window.ring_selection(rank, world, V, n_support, 'cpu')
         for v in range(V):
-            idx = R.select_support_by_similarity(desc_all, rank * V + v, n_support)[0]
-            exp = torch.cat([z_all[i * P:(i + 1) * P] for i in idx], 0)
-            ok = ok and torch.equal(sup[v].hi, exp.to(torch.bfloat16)) and torch.equal(sup[v].lo, (-exp).to(torch.bfloat16))
+            want = intervideo.support_indices(rank * V + v, G, n_support)
+            ok = ok and sel[v].tolist() == want + [-1] * (n_support - len(want))
+            for g in want:
+                r0 = (g // V) * 2 * rpr + (g % V) * P
+                ok = ok and torch.equal(flat[r0:r0 + P], z_all[g * P:(g + 1) * P].to(torch.bfloat16))
+                ok = ok and torch.equal(flat[r0 + rpr:r0 + rpr + P], (-z_all[g * P:(g + 1) * P]).to(torch.bfloat16))
+        # counts carrier: pool_counts[(g // V) * counts_rank_stride + g % V] with the int32 view starting at row V*P
+        ci = flat.view(torch.int32)[V * P:].reshape(-1)
+        stride = 2 * rpr * (D // 2)
+        ok = ok and [int(ci[(g // V) * stride + g % V]) for g in range(G)] == counts_all.tolist()
+        if C:
+            ok = ok and torch.equal(intervideo.unpack_descriptors(recv, V, P, n_desc, C), desc_all)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('V,C,n_support', [(3, 256, 2), (2, 1500, 4)])
-def test_similarity_support_exchange_world2(V, C, n_support):
-    """Next row N4 at world_size 2: the fp32 descriptors ride in the one all-gather as carrier rows (C = 1500
-    needs two rows of D = 1024 bf16 per video), every rank sees the same [G, C] table bit for bit, and the
-    selected rows are those of the oracle's selection."""
+@pytest.mark.parametrize('V,C,n_support', [(3, 0, 4), (1, 0, 4), (2, 0, 1), (3, 256, 2), (2, 1500, 4)])
+def test_support_exchange_world2(V, C, n_support):
+    """The single collective of the path at world_size 2 (gloo): key rows (split pair, bit-exact), per-key-frame
+    proposal counts and - C > 0 - fp32 video descriptors (C = 1500 needs two carrier rows of D = 1024 bf16 per
+    video) travel in ONE all_gather_into_tensor; every rank finds every other rank's rows, counts and descriptors
+    at the addresses the device-side index kernel computes; ring selection = intervideo.support_indices."""
     world, port = 2, _free_port()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker_similarity, args=(r, world, port, V, 4, 1024, C, n_support, q))
-             for r in range(world)]
+    D = 1024 if C else 8
+    procs = [ctx.Process(target=_worker, args=(r, world, port, V, 4, D, C, n_support, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
@@ -124,13 +94,16 @@ def test_ring_rule_and_sharding():
 
 
 def test_single_process_is_identity():
-    from hvrnet_b200 import intervideo as iv
+    """Without a process group the exchange is the send buffer itself (world 1: configs[3], one GPU)."""
+    from hvrnet_b200 import intervideo as iv, window
     from hvrnet_b200.ops import Split
-    z = Split(torch.randn(6, 4).to(torch.bfloat16), torch.randn(6, 4).to(torch.bfloat16))
-    assert iv.all_gather_rows(z) is z
-    sup = iv.gather_support(z, 2, 4)
-    assert [tuple(s.hi.shape) for s in sup] == [(4, 4)] * 3
-    assert torch.equal(sup[2].hi, torch.cat([z.hi[0:2], z.hi[2:4]]))
+    z = Split(torch.randn(6, 8).to(torch.bfloat16), torch.randn(6, 8).to(torch.bfloat16))
+    send, rpr, n_desc = iv.pack_exchange(z, torch.tensor([2, 1, 2], dtype=torch.int32))
+    recv, work = iv.exchange(send)
+    assert work is None and recv.shape == (1, 2, 7, 8) and recv.data_ptr() == send.data_ptr() and n_desc == 0
+    assert torch.equal(recv[0, 0, :6], z.hi) and torch.equal(recv[0, 1, :6], z.lo)
+    assert recv[0, 0, 6].view(torch.int32)[:3].tolist() == [2, 1, 2]
+    assert window.ring_selection(0, 1, 3, 4, 'cpu').tolist() == [[1, 2, -1, -1], [2, 0, -1, -1], [0, 1, -1, -1]]
 
 
 def test_shard_videos_matches_reference_get_indices():

@@ -829,3 +829,125 @@ def test_support_select(cuda, G, C, n):
     # exact ties: identical descriptors -> the lower indices
     same = torch.ones(6, C).to(cuda)
     assert ops.support_select(same, 2, 2, 3).cpu().tolist() == [[0, 1, 3], [0, 1, 2]]
+
+
+# ---------------------------------------------------------------------------------------
+# window bookkeeping kernels (csrc/window.cu), masked softmax, counted post-processing
+# ---------------------------------------------------------------------------------------
+def test_softmax_rows_masked(cuda):
+    """hvr_softmax_rows_split_masked: blocks of `slot` keys of which only the first seg_counts[problem][block] take
+    part == the softmax over the compacted key set (per row: same values at the live keys, exactly 0 elsewhere);
+    with every count == slot the unmasked kernel's bits; a fully masked row gives zeros, not NaN."""
+    from hvrnet_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    V, nq, slot, segs = 3, 37, 300, 5
+    cols = slot * segs
+    S = (torch.randn(V * nq, cols + 44, generator=g) * 3).to(cuda)
+    cnt = torch.tensor([[300, 17, 0, 299, 1], [300] * 5, [0, 0, 0, 0, 0]], dtype=torch.int32)
+    Pm = ops.merge(ops.softmax_rows_split(S, cols, ld_p=cols + 44, seg_counts=cnt.to(cuda), slot=slot, rows_per_problem=nq)).cpu()
+    Sc = S.cpu().double()
+    for v in range(V):
+        live = torch.cat([torch.arange(slot) < int(cnt[v, b]) for b in range(segs)])
+        rows = slice(v * nq, (v + 1) * nq)
+        assert not bool(Pm[rows, :cols][:, ~live].any()) and not bool(Pm[rows, cols:].any())
+        if live.any():
+            ref = torch.softmax(Sc[rows, :cols][:, live], 1)
+            assert float((Pm[rows, :cols][:, live].double() - ref).abs().max()) < 1e-6
+        else:
+            assert not bool(Pm[rows].any()) and bool(torch.isfinite(Pm[rows]).all())
+    full = ops.softmax_rows_split(S, cols, ld_p=cols + 44)
+    allc = torch.full((V, segs), slot, dtype=torch.int32, device=cuda)
+    msk = ops.softmax_rows_split(S, cols, ld_p=cols + 44, seg_counts=allc, slot=slot, rows_per_problem=nq)
+    assert torch.equal(full.hi.view(torch.int16), msk.hi.view(torch.int16))
+    assert torch.equal(full.lo.view(torch.int16), msk.lo.view(torch.int16))
+    # slot not a multiple of 4: the scalar path
+    cnt2 = torch.tensor([[5, 0, 7]], dtype=torch.int32)
+    S2 = torch.randn(4, 21, generator=g).to(cuda)
+    P2 = ops.merge(ops.softmax_rows_split(S2, 21, ld_p=64, seg_counts=cnt2.to(cuda), slot=7, rows_per_problem=4)).cpu()
+    live = torch.cat([torch.arange(7) < int(c) for c in cnt2[0]])
+    assert float((P2[:, :21][:, live].double() - torch.softmax(S2.cpu().double()[:, live], 1)).abs().max()) < 1e-6
+    assert not bool(P2[:, :21][:, ~live].any())
+
+
+def test_window_rois_and_gathers(cuda):
+    """hvr_window_rois / hvr_gather_rows_split / hvr_support_index against their definitions (index arithmetic only)."""
+    from hvrnet_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    V, T, P, key = 3, 4, 8, 2
+    F = V * T
+    props = torch.rand(F, P, 5, generator=g) * 100
+    counts = torch.randint(0, P + 1, (F,), generator=g, dtype=torch.int32)
+    perm = torch.randperm(F, generator=g)
+    rois, rk, seg, kc = ops.window_rois(props.to(cuda), counts.to(cuda), perm.to(cuda), V, T, key, n_segs=T + 2)
+    Npad = ops.round_up(T * P, 64)
+    rois, rk, seg, kc = rois.cpu().view(V, Npad, 5), rk.cpu().view(V, P, 5), seg.cpu(), kc.cpu()
+    for v in range(V):
+        for t in range(T):
+            slot = int(perm[v * T + t])
+            blk = rois[v, t * P:(t + 1) * P]
+            assert torch.equal(blk[:, 1:], props[slot, :, :4]) and bool((blk[:, 0] == slot).all())
+            assert int(seg[v, t]) == int(counts[slot])
+        assert not bool(rois[v, T * P:].any()) and not bool(seg[v, T:].any())
+        ks = int(perm[v * T + key])
+        assert torch.equal(rk[v, :, 1:], props[ks, :, :4]) and not bool(rk[v, :, 0].any()) and int(kc[v]) == int(counts[ks])
+    # identity perm
+    r2 = ops.window_rois(props.to(cuda), counts.to(cuda), None, V, T, key)[0].cpu().view(V, Npad, 5)
+    assert bool((r2[1, P:2 * P, 0] == T + 1).all())
+    # gathers
+    src = ops.split(torch.randn(40, 16, generator=g).to(cuda))
+    dst = ops.Split.zeros((3 * 20, 16), cuda)
+    ops.gather_rows(src, dst, 3, 5, src_rpp=10, src_row0=2, dst_rpp=20, dst_row0=7)
+    for p in range(3):
+        assert torch.equal(dst.hi[p * 20 + 7:p * 20 + 12], src.hi[p * 10 + 2:p * 10 + 7])
+        assert torch.equal(dst.lo[p * 20 + 7:p * 20 + 12], src.lo[p * 10 + 2:p * 10 + 7])
+    assert not bool(dst.hi[:7].any())
+    idx = torch.tensor([3, -1, 39, 0, 0, 17], dtype=torch.int32, device=cuda)
+    d2 = ops.Split.empty((6, 16), cuda)
+    ops.gather_rows(src, d2, 1, 6, idx=idx)
+    for j, i in enumerate(idx.tolist()):
+        assert torch.equal(d2.hi[j], src.hi[i]) if i >= 0 else not bool(d2.hi[j].any())
+    # support index: global key frame g of rank g // vpr
+    sel = torch.tensor([[4, 1, -1], [0, 5, 2]], dtype=torch.int64, device=cuda)
+    vpr, Pk, rank_stride, cstride = 2, 3, 50, 64
+    pool_counts = torch.arange(3 * cstride, dtype=torch.int32, device=cuda)
+    segc = torch.zeros((2, 7), dtype=torch.int32, device=cuda)
+    ix = ops.support_index(sel, pool_counts, cstride, vpr, rank_stride, Pk, 4, segc).cpu()
+    for v in range(2):
+        for s_ in range(3):
+            gk = int(sel[v, s_])
+            want = [-1] * Pk if gk < 0 else [(gk // vpr) * rank_stride + (gk % vpr) * Pk + j for j in range(Pk)]
+            assert ix[v, s_ * Pk:(s_ + 1) * Pk].tolist() == want
+            assert int(segc[v, 4 + s_]) == (0 if gk < 0 else (gk // vpr) * cstride + gk % vpr)
+
+
+@pytest.mark.parametrize('n_valid', [[300, 117, 1], [0, 300, 299]])
+def test_det_postprocess_counted(cuda, n_valid):
+    """hvr_det_postprocess_batched_ex: problem g with n_valid[g] proposals inside a block of n rows == the same call on
+    exactly those n_valid[g] rows (labels, counts, boxes, scores identical); roi_idx = the row every detection came from
+    (checked against the oracle's multiclass_nms rows)."""
+    from hvrnet_b200 import ops
+    from tests import parity_tools as PT
+    g = torch.Generator().manual_seed(4)
+    G, n = 3, 300
+    x1, y1 = torch.rand(G * n, generator=g) * 700, torch.rand(G * n, generator=g) * 400
+    rois = torch.stack([torch.zeros(G * n), x1, y1, x1 + 30 + torch.rand(G * n, generator=g) * 200,
+                        y1 + 30 + torch.rand(G * n, generator=g) * 150], 1)
+    cls = torch.randn(G * n, 31, generator=g) * 2
+    reg = torch.randn(G * n, 4, generator=g) * 0.5
+    nv = torch.tensor(n_valid, dtype=torch.int32)
+    d, l, k, ridx = ops.det_postprocess_batched(rois.to(cuda), cls.to(cuda), reg.to(cuda), G, (600, 1000), 1.0, True,
+                                                n_valid=nv.to(cuda), want_idx=True)
+    for p in range(G):
+        m = int(nv[p])
+        kk = int(k[p])
+        if m == 0:
+            assert kk == 0
+            continue
+        sl = slice(p * n, p * n + m)
+        t = PT.det_trace(rois[sl], cls[sl], reg[sl], (600, 1000), 1.0, True)
+        assert kk == t['dets'].shape[0]
+        assert l[p, :kk].cpu().tolist() == t['labels'].tolist() and ridx[p, :kk].cpu().tolist() == t['rows'].tolist()
+        assert float((d[p, :kk, :4].cpu() - t['dets'][:, :4]).abs().max()) < 1e-3
+        assert float((d[p, :kk, 4].cpu() - t['dets'][:, 4]).abs().max()) < 1e-6
+        d1, l1, k1 = ops.det_postprocess(rois[sl].to(cuda), cls[sl].to(cuda), reg[sl].to(cuda), (600, 1000), 1.0, True)
+        assert int(k1) == kk and torch.equal(d1[:kk], d[p, :kk]) and torch.equal(l1[:kk], l[p, :kk])

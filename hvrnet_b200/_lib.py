@@ -36,6 +36,14 @@ class HvrIGemm(ctypes.Structure):
     ]
 
 
+class HvrRelationWeights(ctypes.Structure):
+    """Mirror of struct HvrRelationWeights (include/hvr_b200.h)."""
+    _fields_ = [('dim', c_int),
+                ('q_hi', c_vp), ('q_lo', c_vp), ('q_bias', c_vp),
+                ('k_hi', c_vp), ('k_lo', c_vp), ('k_bias', c_vp),
+                ('o_hi', c_vp), ('o_lo', c_vp), ('o_bias', c_vp)]
+
+
 # name -> (restype, argtypes); every symbol include/hvr_b200.h declares
 SIGNATURES = {
     'hvr_strerror': (ctypes.c_char_p, [c_int]),
@@ -58,8 +66,9 @@ SIGNATURES = {
     'hvr_maxpool3x3s2_split': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp]),
     'hvr_roi_align_fwd': (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_int,
                                   c_vp, c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    'hvr_roi_align_fast_workspace_bytes': (c_sz, [c_int, c_int]),
     'hvr_roi_align_fwd_fast': (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_int,
-                                       c_vp, c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),
+                                       c_vp, c_int, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
     'hvr_nms_workspace_bytes': (c_sz, [c_int]),
     'hvr_nms': (c_int, [c_vp, c_int, c_f32, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'hvr_rpn_workspace_bytes': (c_sz, [c_int, c_int, c_int]),
@@ -80,6 +89,14 @@ SIGNATURES = {
     'hvr_softmax_rows_split': (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_i64, c_vp]),
     'hvr_softmax_rows_split_masked': (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_int,
                                               c_vp]),
+    'hvr_packed_rows': (c_sz, [c_int]),
+    'hvr_packed_cols': (c_sz, [c_int]),
+    'hvr_pack_conv_bn': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
+                                 c_vp]),
+    'hvr_pack_linear': (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'hvr_relation_workspace_bytes': (c_sz, [c_int, c_int, c_int]),
+    'hvr_relation_fwd': (c_int, [ctypes.POINTER(HvrRelationWeights), c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_int,
+                                 c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
     'hvr_window_rois': (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     'hvr_gather_rows_split': (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_int, c_int, c_i64,
                                       c_int, c_int, c_vp]),

@@ -26,6 +26,7 @@ SOURCES = {
     'preprocess.cu': ['-fmad=false'],
     'intervideo.cu': ['-fmad=false'],
     'window.cu': ['-fmad=false'],
+    'relation.cu': ['-fmad=false'],
 }
 
 

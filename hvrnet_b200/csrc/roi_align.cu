@@ -222,6 +222,102 @@ __global__ void __launch_bounds__(448, MINB) roi_align_sep_kernel(
                      nullptr);
 }
 
+// Slab variant of the fast path.  ncu of the RoI-per-CTA kernels above (profiles/r01q_*, r02a_*): every variant
+// sits at ~7.3 TB/s of L2 -> SM traffic (lts__t_sectors_srcunit_tex_op_read: 7.3 GB per 105-frame launch, the chip's
+// L2 throughput cap) - each RoI drags its own patch of the map (~200 KB on the bench distribution) out of L2,
+// although the 300 RoIs of a frame overlap 26-fold.  Here the MAP is what a CTA owns: CTA = (frame, 16-channel
+// slab); the slab of the whole map (H*W pixels x 64 B = 153 KB for 38 x 63) is copied into shared memory ONCE
+// (cp.async) and every RoI of the frame is evaluated from it, so the L2 -> SM traffic of a launch drops to one
+// pass over the maps (257 MB) and all taps are LDS.128.  One warp per RoI: lane = (output column q, 4-channel
+// group) for 7 x 4 = 28 lanes, lanes 0..2*ph-1 compute the RoI's y samples into a per-warp table first; the
+// separable evaluation of roi_align_sep.cuh then walks the rows.  RoIs are claimed dynamically (one shared
+// counter per CTA).  Needs the RoIs bucketed by frame: roi_bucket_kernel (one small launch) writes `order` / `start`.
+constexpr int SLAB_C = 16;           // channels per slab: 64-byte pixels, 32-byte output sectors per (RoI, bin)
+constexpr int SLAB_THREADS = 512;
+
+__global__ void roi_bucket_kernel(const float* __restrict__ rois, int n, int n_imgs, int* __restrict__ start,
+                                  int* __restrict__ order) {
+  extern __shared__ int sb[];        // [n_imgs] counts, [n_imgs] cursors
+  int* cnt = sb;
+  int* cur = sb + n_imgs;
+  for (int i = threadIdx.x; i < n_imgs; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  auto img_of = [&](int i) {
+    const int b = (int)rois[(size_t)i * 5];
+    return b < 0 ? 0 : (b >= n_imgs ? n_imgs - 1 : b);
+  };
+  for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&cnt[img_of(i)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = 0; b < n_imgs; ++b) {
+      start[b] = acc;
+      cur[b] = acc;
+      acc += cnt[b];
+    }
+    start[n_imgs] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) order[atomicAdd(&cur[img_of(i)], 1)] = i;
+}
+
+struct SlabLoad {
+  const char* base;   // slab + 4-channel group
+  __device__ __forceinline__ float4 operator()(uint32_t off) const {
+    return *reinterpret_cast<const float4*>(base + off);
+  }
+};
+
+__global__ void __launch_bounds__(SLAB_THREADS, 1) roi_align_slab_kernel(
+    const float* __restrict__ feat, const float* __restrict__ rois, const int* __restrict__ start,
+    const int* __restrict__ order, int n_imgs, int C, int H, int W, int ph, int pw, float scale,
+    float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+    long long ld_split) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int HW = H * W;
+  uint8_t* slab = smem;                                                      // [HW][16] fp32
+  RowTap* rtab = reinterpret_cast<RowTap*>(smem + (size_t)HW * SLAB_C * 4);  // [warps][32]
+  __shared__ int next;
+  const int img = blockIdx.y, c0 = blockIdx.x * SLAB_C;
+  const int first = start[img], last = start[img + 1];
+  if (first == last) return;
+  // slab of the whole map: 4 x 16 B per pixel
+  const float* src = feat + (size_t)img * HW * C + c0;
+  for (int i = threadIdx.x; i < HW * 4; i += SLAB_THREADS) {
+    const float* g = src + (size_t)(i >> 2) * C + (i & 3) * 4;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(slab + (size_t)i * 16)), "l"(g) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (threadIdx.x == 0) next = first;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = lane >> 2, cg = lane & 3;
+  RowTap* rows = rtab + warp * 32;
+  const SlabLoad ld{reinterpret_cast<const char*>(slab) + cg * 16};
+  const uint32_t row_pitch = (uint32_t)W * SLAB_C * 4u;
+  const size_t step = (size_t)pw * C;
+  for (;;) {
+    int r = 0;
+    if (lane == 0) r = atomicAdd(&next, 1);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    if (r >= last) break;
+    const int roi = order[r];
+    const RoiGeom g = roi_geom(rois + (size_t)roi * 5, scale, ph, pw, n_imgs);
+    __syncwarp();                                   // the previous RoI's table reads are done
+    if (lane < 2 * ph) rows[lane] = row_tap_sn2(g.sh, g.bh, lane, H, row_pitch);
+    __syncwarp();
+    if (q < pw) {
+      const ColTaps ct = col_taps_sn2(g.sw, g.bw, q, W, (uint32_t)SLAB_C * 4u);
+      const size_t o_f32 = ((size_t)roi * ph * pw + q) * C + c0 + cg * 4;
+      const size_t o_split = (size_t)roi * ld_split + (size_t)q * C + c0 + cg * 4;
+      roi_column_sep_sn2(rows, ph, ct, ld,
+                         [&](int p, const float4& v) { store_bin(v, out, out_hi, out_lo, o_f32 + p * step, o_split + p * step); },
+                         nullptr);
+    }
+  }
+}
+
 // Generic path (adaptive sample_num == 0, or very large sampling grids): reference-style, one
 // thread per output element, NHWC or NCHW output.
 __global__ void roi_align_generic_kernel(const float* __restrict__ feat, const float* __restrict__ rois, int n_rois,
@@ -261,6 +357,7 @@ __global__ void roi_align_generic_kernel(const float* __restrict__ feat, const f
 
 int g_roi_variant = 0;   // test hook (hvr_debug_roi_variant): 0 = heuristic, 1 = always the per-bin kernel
 int g_sep_minb = 2;      // test hook (hvr_debug_roi_variant 2 / 3): resident CTAs per SM the fast kernel is built for
+int g_slab = 0;          // test hook (hvr_debug_roi_variant 4 / 5 / 6): 0 = heuristic, 1 = slab kernel whenever it applies, 2 = never
 
 }  // namespace
 
@@ -269,22 +366,44 @@ extern "C" int hvr_debug_roi_variant(int v) {
     g_sep_minb = v;
     return HVR_OK;
   }
+  if (v >= 4 && v <= 6) {          // 4 = heuristic, 5 = slab kernel whenever it applies, 6 = never the slab kernel
+    g_slab = v - 4;
+    return HVR_OK;
+  }
   if (v != 0 && v != 1) return HVR_ERR_ARG;
   g_roi_variant = v;
   return HVR_OK;
 }
 
-// Fast arithmetic (roi_align_sep.cuh) where it applies - NHWC rows out, sample_num == 2, one CTA of
-// pw * C/4 <= 448 threads per RoI - else the strict kernels of hvr_roi_align_fwd.
+extern "C" size_t hvr_roi_align_fast_workspace_bytes(int n_rois, int n_imgs) {
+  return ((size_t)(n_rois > 0 ? n_rois : 0) + (size_t)(n_imgs > 0 ? n_imgs : 0) + 1) * sizeof(int) + 256;
+}
+
+// Fast arithmetic (roi_align_sep.cuh) where it applies - NHWC rows out, sample_num == 2 - else the strict kernels
+// of hvr_roi_align_fwd.  Two launch shapes: the slab kernel (CTA = frame x 16-channel slab, map slab in shared
+// memory) when the map slab fits and the launch has at least one CTA per SM; otherwise one CTA of pw * C/4 <= 448
+// threads per RoI.
 extern "C" int hvr_roi_align_fwd_fast(const float* feat, int feat_nhwc, const float* rois, int n_rois, int n_imgs,
                                       int C, int H, int W, int ph, int pw, float spatial_scale, int sample_num,
                                       float* out, int out_layout, hvr_bf16* out_hi, hvr_bf16* out_lo,
-                                      int64_t ld_split, float* ws, void* stream) {
-  const bool sep = feat_nhwc && out_layout == 1 && sample_num == 2 && C >= 4 && C % 4 == 0 && pw * (C >> 2) <= 448 &&
-                   2 * ph <= 32 && g_roi_variant == 0;
-  if (!sep)
+                                      int64_t ld_split, void* ws, size_t ws_bytes, void* stream) {
+  const bool fast_ok = feat_nhwc && out_layout == 1 && sample_num == 2 && C >= 4 && C % 4 == 0 && 2 * ph <= 32 &&
+                       g_roi_variant == 0;
+  const bool sep = fast_ok && pw * (C >> 2) <= 448;
+  const size_t slab_smem = (size_t)H * W * SLAB_C * 4 + (SLAB_THREADS / 32) * 32 * sizeof(RowTap);
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    HVR_CUDA(cudaGetDevice(&dev));
+    HVR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const bool slab = fast_ok && g_slab != 2 && C % SLAB_C == 0 && pw * 4 <= 32 && slab_smem <= 220 * 1024 && n_imgs <= 65535 &&
+                    (size_t)n_imgs * 8 <= 96 * 1024 && ws != nullptr &&
+                    ws_bytes >= hvr_roi_align_fast_workspace_bytes(n_rois, n_imgs) &&
+                    (g_slab == 1 || (long long)n_imgs * (C / SLAB_C) >= num_sms);
+  if (!sep && !slab)
     return hvr_roi_align_fwd(feat, feat_nhwc, rois, n_rois, n_imgs, C, H, W, ph, pw, spatial_scale, sample_num, out,
-                             out_layout, out_hi, out_lo, ld_split, ws, stream);
+                             out_layout, out_hi, out_lo, ld_split, feat_nhwc ? nullptr : (float*)ws, stream);
   if (n_rois == 0) return HVR_OK;
   if (!feat || !rois || n_rois < 0 || n_imgs < 1 || H < 1 || W < 1 || ph < 1 || pw < 1) return HVR_ERR_ARG;
   if (!out && !out_hi) return HVR_ERR_ARG;
@@ -292,6 +411,23 @@ extern "C" int hvr_roi_align_fwd_fast(const float* feat, int feat_nhwc, const fl
   if (out_hi && (ld_split < (int64_t)ph * pw * C || ld_split % 4 != 0)) return HVR_ERR_ARG;
   if ((size_t)H * W * C >= (1u << 30)) return HVR_ERR_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (slab) {
+    int* start = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(ws) + 15) & ~(uintptr_t)15);
+    int* order = start + n_imgs + 1;
+    static bool attr = false;
+    if (!attr) {
+      HVR_CUDA(cudaFuncSetAttribute(roi_align_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      HVR_CUDA(cudaFuncSetAttribute(roi_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr = true;
+    }
+    roi_bucket_kernel<<<1, 1024, (size_t)n_imgs * 8, st>>>(rois, n_rois, n_imgs, start, order);
+    HVR_LAUNCHED();
+    roi_align_slab_kernel<<<dim3(C / SLAB_C, n_imgs), SLAB_THREADS, slab_smem, st>>>(
+        feat, rois, start, order, n_imgs, C, H, W, ph, pw, spatial_scale, out, (__nv_bfloat16*)out_hi,
+        (__nv_bfloat16*)out_lo, ld_split);
+    HVR_LAUNCHED();
+    return HVR_OK;
+  }
   const int threads = pw * (C >> 2);
   if (g_sep_minb == 3)
     roi_align_sep_kernel<3><<<n_rois, threads, 0, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out,
@@ -302,7 +438,6 @@ extern "C" int hvr_roi_align_fwd_fast(const float* feat, int feat_nhwc, const fl
   HVR_LAUNCHED();
   return HVR_OK;
 }
-
 extern "C" int hvr_roi_align_fwd(const float* feat, int feat_nhwc, const float* rois, int n_rois, int n_imgs, int C,
                                  int H, int W, int ph, int pw, float spatial_scale, int sample_num, float* out,
                                  int out_layout, hvr_bf16* out_hi, hvr_bf16* out_lo, int64_t ld_split, float* ws,

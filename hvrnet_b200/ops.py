@@ -292,11 +292,18 @@ def roi_align(feat, rois, out_size=7, spatial_scale=1 / 16., sample_num=2, feat_
         ld_split = ld_split or ph * pw * C
         sp = Split.empty((n, ld_split), dev)
     ws = None if feat_nhwc else torch.empty(feat.numel(), dtype=torch.float32, device=dev)
-    fn = _lib.lib().hvr_roi_align_fwd_fast if arithmetic == 'fast' else _lib.lib().hvr_roi_align_fwd
-    check(fn(_p(feat), int(feat_nhwc), _p(rois), n, B, C, H, W, ph, pw, float(spatial_scale),
-             int(sample_num), _p(out), 1 if out_nhwc else 0,
-             _p(sp.hi) if sp else None, _p(sp.lo) if sp else None,
-             ld_split or 0, _p(ws), _stream()), 'hvr_roi_align_fwd')
+    if arithmetic == 'fast' and feat_nhwc:
+        wsb = _lib.lib().hvr_roi_align_fast_workspace_bytes(n, B)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        check(_lib.lib().hvr_roi_align_fwd_fast(_p(feat), 1, _p(rois), n, B, C, H, W, ph, pw, float(spatial_scale),
+                                                int(sample_num), _p(out), 1 if out_nhwc else 0,
+                                                _p(sp.hi) if sp else None, _p(sp.lo) if sp else None,
+                                                ld_split or 0, _p(ws), wsb, _stream()), 'hvr_roi_align_fwd_fast')
+    else:
+        check(_lib.lib().hvr_roi_align_fwd(_p(feat), int(feat_nhwc), _p(rois), n, B, C, H, W, ph, pw, float(spatial_scale),
+                                           int(sample_num), _p(out), 1 if out_nhwc else 0,
+                                           _p(sp.hi) if sp else None, _p(sp.lo) if sp else None,
+                                           ld_split or 0, _p(ws), _stream()), 'hvr_roi_align_fwd')
     return (out, sp) if want_split else out
 
 

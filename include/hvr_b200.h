@@ -168,7 +168,8 @@ int hvr_roi_align_fwd(const float* feat, int feat_nhwc, const float* rois, int n
                       int64_t ld_split, float* ws, void* stream);
 /* Test hook: 1 = always the generic per-bin kernel (16 loads per output vector, as the reference),
  * 0 = heuristic (sample_num 2 + out_layout 1 run roi_align_sn2_kernel, which reuses taps held in registers);
- * 2 / 3 = resident CTAs per SM the fast kernel below is compiled for (experiments). */
+ * 2 / 3 = resident CTAs per SM the fast RoI-per-CTA kernel below is compiled for (experiments);
+ * 4 / 5 / 6 = fast path launch shape: heuristic / slab kernel whenever it applies / never the slab kernel. */
 int hvr_debug_roi_variant(int v);
 /* Fast arithmetic for the pipeline (feat_nhwc = 1, out_layout = 1, sample_num = 2): the same average of
  * bilinear samples evaluated separably - every map row of the RoI is interpolated once along x with the
@@ -176,11 +177,17 @@ int hvr_debug_roi_variant(int v);
  * (csrc/roi_align_sep.cuh).  Same sample positions, validity and clamping rules as the strict kernels; the
  * summation order differs, so values agree with hvr_roi_align_fwd to a few ulp of the largest term (1e-5
  * relative, the agreement between the reference's own default build, which nvcc contracts into FMAs, and its
- * -fmad=false build), not bit for bit.  Other argument combinations run the strict kernels. */
+ * -fmad=false build), not bit for bit.  Other argument combinations run the strict kernels.
+ * Launch shapes: when a 16-channel slab of the whole map fits in shared memory (H*W*64 B <= 220 KB) and the launch
+ * has at least one (frame, slab) pair per SM, CTA = (frame, slab): the slab is staged in shared memory once and all
+ * RoIs of the frame are pooled from it (the L2 -> SM traffic falls from one patch per RoI to one pass over the
+ * maps); otherwise one CTA per RoI.  ws: hvr_roi_align_fast_workspace_bytes(n_rois, n_imgs) bytes (the RoIs
+ * bucketed by frame); with ws == NULL only the CTA-per-RoI shape is used. */
+size_t hvr_roi_align_fast_workspace_bytes(int n_rois, int n_imgs);
 int hvr_roi_align_fwd_fast(const float* feat, int feat_nhwc, const float* rois, int n_rois, int n_imgs,
                            int C, int H, int W, int ph, int pw, float spatial_scale, int sample_num,
                            float* out, int out_layout, hvr_bf16* out_hi, hvr_bf16* out_lo,
-                           int64_t ld_split, float* ws, void* stream);
+                           int64_t ld_split, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * NMS.  Replaces nms_cuda.nms (nms_kernel.cu:71-136, strict `>`; strict_gt=0 gives
@@ -271,6 +278,50 @@ int hvr_softmax_rows_split(const float* S, int rows, int cols, int64_t ld_s, hvr
 int hvr_softmax_rows_split_masked(const float* S, int rows, int cols, int64_t ld_s, hvr_bf16* p_hi,
                                   hvr_bf16* p_lo, int64_t ld_p, const int* seg_counts, int n_segs, int slot,
                                   int rows_per_problem, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Composites for non-Python hosts (csrc/relation.cu).  The Python engine (hvrnet_b200/engine.py)
+ * packs weights and sequences the launches itself; a C / C++ host binds these instead and gets the same bits.
+ *
+ * Weight packing (host pointers in, device buffers out; the calls synchronise `stream` - one-time setup):
+ *   hvr_pack_conv_bn : conv weight [cout, cin, kh, kw] (+ frozen BatchNorm: weight / bias / running_mean /
+ *       running_var [cout], eps; all four NULL = no BN) (+ conv bias [cout] or NULL) -> folded in fp64, re-laid-out
+ *       K-major [cout, (r*kw + s)*cin + c], zero-padded to [hvr_packed_rows(cout), hvr_packed_cols(kh*kw*cin)] and
+ *       split (resnet.py:222-257 conv + norm; conv_module.py).  bias: fp32 [hvr_packed_rows(cout)] (NULL allowed
+ *       when there is neither BN nor conv bias).
+ *   hvr_pack_linear  : nn.Linear weight [n, k] (+ bias or NULL) -> split [hvr_packed_rows(n), hvr_packed_cols(k)],
+ *       bias fp32 [hvr_packed_rows(n)]; col_perm (optional, host int32 [k]): packed column c = source column
+ *       col_perm[c] (fc_new_1 reads RoI rows in (h, w, C) order: hrnmp_bbox_head.py:827-828).
+ * ---------------------------------------------------------------------------------- */
+size_t hvr_packed_rows(int n);
+size_t hvr_packed_cols(int k);
+int hvr_pack_conv_bn(const float* w_host, const float* bn_weight_host, const float* bn_bias_host,
+                     const float* bn_mean_host, const float* bn_var_host, float bn_eps,
+                     const float* conv_bias_host, int cout, int cin, int kh, int kw, hvr_bf16* w_hi,
+                     hvr_bf16* w_lo, float* bias, void* stream);
+int hvr_pack_linear(const float* w_host, const float* bias_host, int n, int k, const int* col_perm_host,
+                    hvr_bf16* w_hi, hvr_bf16* w_lo, float* bias, void* stream);
+
+/* One relation block behind one call.  Replaces forward_single_selsa (hrnmp_bbox_head.py:216-355; SelsaBBoxHead:
+ * selsa_bbox_head.py:108-201) with conv_g False / conv_z True (the configs' setting):
+ *     Q = xq Wq^T + bq;  K = x Wk^T + bk;  P = softmax_keys(Q K^T / sqrt(D));  O = P x;
+ *     out = [relu](res + O Wo^T + bo)
+ * x  [n_k, D] split (row pitch ld_x): the key / value rows;  xq [n_q, D] (NULL = x: every row is a query);
+ * res [n_q, D] or NULL;  out [n_q, D] (row pitch ld_out).  Weights as packed by hvr_pack_linear with n = k = D
+ * (linear_out_k is a 1x1 conv over a [N, D, 1, 1] tensor = a linear layer).  Six hvr_igemm / softmax / transpose
+ * launches on `stream`, no host synchronisation; ws: hvr_relation_workspace_bytes(n_q, n_k, D) bytes. */
+typedef struct HvrRelationWeights {
+  int dim;                                   /* D (1024 in both configs; multiple of 8) */
+  const hvr_bf16 *q_hi, *q_lo; const float* q_bias;   /* q_data_fc_k  */
+  const hvr_bf16 *k_hi, *k_lo; const float* k_bias;   /* k_data_fc_k  */
+  const hvr_bf16 *o_hi, *o_lo; const float* o_bias;   /* linear_out_k */
+} HvrRelationWeights;
+size_t hvr_relation_workspace_bytes(int n_q, int n_k, int D);
+int hvr_relation_fwd(const HvrRelationWeights* w, const hvr_bf16* x_hi, const hvr_bf16* x_lo, int64_t ld_x,
+                     int n_k, const hvr_bf16* xq_hi, const hvr_bf16* xq_lo, int64_t ld_xq, int n_q,
+                     const hvr_bf16* res_hi, const hvr_bf16* res_lo, int64_t ld_res, int relu,
+                     hvr_bf16* out_hi, hvr_bf16* out_lo, int64_t ld_out, void* ws, size_t ws_bytes,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Window bookkeeping on the device (csrc/window.cu).  Replaces the host-side assembly of a window in

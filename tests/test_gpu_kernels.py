@@ -529,11 +529,10 @@ def test_roi_align_sn2_kernel_equals_generic_per_bin_kernel(cuda, C, out_size):
 
 @pytest.mark.parametrize('C,out_size', [(256, 7), (128, 7), (256, 3), (16, 7), (40, 3), (512, 7)])
 def test_roi_align_fast_variant_vs_strict(cuda, C, out_size):
-    """hvr_roi_align_fwd_fast (roi_align_sep_kernel: separable, fused multiply-add) against the strict kernel and
-    the C oracle.  Tolerance (the contract in include/hvr_b200.h): every element within 1e-5 of the largest
-    |reference| value of its RoI; bins the oracle evaluates to exactly 0 are exactly 0; the split rows are the
-    split of the fp32 rows.  C = 512 has no fast launch shape (7 * 128 threads > 448) and must fall back to the
-    strict kernel bit for bit."""
+    """hvr_roi_align_fwd_fast (roi_align_sep_kernel / roi_align_slab_kernel: separable, fused multiply-add) against
+    the strict kernel and the C oracle.  Tolerance (the contract in include/hvr_b200.h): every element within 1e-5
+    of the largest |reference| value of its RoI; bins the oracle evaluates to exactly 0 are exactly 0; the split
+    rows are the split of the fp32 rows; both launch shapes give the same bits."""
     from hvrnet_b200 import ops
     from oracle import cref
     g = torch.Generator().manual_seed(31 + C)
@@ -547,11 +546,25 @@ def test_roi_align_fast_variant_vs_strict(cuda, C, out_size):
     rois[44, 1:] = torch.tensor([100., -500., 200., -100.])
     ref = cref.roi_align(feat, rois, out_size=out_size, feat_nhwc=True, out_nhwc=True)
     f, r = feat.to(cuda), rois.to(cuda)
-    o, sp = ops.roi_align(f, r, out_size=out_size, feat_nhwc=True, out_nhwc=True, want_split=True, arithmetic='fast')
-    o = o.cpu()
+    from hvrnet_b200 import _lib
+    assert _lib.lib().hvr_debug_roi_variant(6) == 0                               # the RoI-per-CTA launch shape
+    try:
+        o, sp = ops.roi_align(f, r, out_size=out_size, feat_nhwc=True, out_nhwc=True, want_split=True, arithmetic='fast')
+        # the slab launch shape (CTA = frame x 16-channel slab, map slab in shared memory): the same separable core,
+        # so identical bits wherever it applies (C % 16 == 0, out_size <= 8)
+        _lib.lib().hvr_debug_roi_variant(5)
+        o_s, sp_s = ops.roi_align(f, r, out_size=out_size, feat_nhwc=True, out_nhwc=True, want_split=True, arithmetic='fast')
+    finally:
+        _lib.lib().hvr_debug_roi_variant(4)
     if C == 512:
-        assert torch.equal(o.view(torch.int32), ref.view(torch.int32))
-        return
+        # no RoI-per-CTA launch shape (7 * 128 threads > 448): with the slab shape disabled this is the strict kernel;
+        # the slab shape still applies and is held to the tolerance below
+        assert torch.equal(o.cpu().view(torch.int32), ref.view(torch.int32))
+        o, sp = o_s, sp_s
+    elif C % 16 == 0:
+        assert torch.equal(o_s.view(torch.int32), o.view(torch.int32))
+        assert torch.equal(sp_s.hi.view(torch.int16), sp.hi.view(torch.int16)) and torch.equal(sp_s.lo.view(torch.int16), sp.lo.view(torch.int16))
+    o = o.cpu()
     scale = ref.abs().flatten(1).amax(1).clamp_min(1e-30).view(-1, 1, 1, 1)
     assert float(((o.double() - ref.double()).abs() / scale).max()) < 1e-5
     dead = ref.abs().flatten(1).amax(1) == 0
@@ -851,8 +864,8 @@ def test_softmax_rows_masked(cuda):
         rows = slice(v * nq, (v + 1) * nq)
         assert not bool(Pm[rows, :cols][:, ~live].any()) and not bool(Pm[rows, cols:].any())
         if live.any():
-            ref = torch.softmax(Sc[rows, :cols][:, live], 1)
-            assert float((Pm[rows, :cols][:, live].double() - ref).abs().max()) < 1e-6
+            ref = torch.softmax(Sc[rows, :cols][:, live], 1)          # P is stored split-bf16: 2^-16 relative
+            assert float(((Pm[rows, :cols][:, live].double() - ref).abs() / (ref + 1e-6)).max()) < 2e-5
         else:
             assert not bool(Pm[rows].any()) and bool(torch.isfinite(Pm[rows]).all())
     full = ops.softmax_rows_split(S, cols, ld_p=cols + 44)
@@ -865,7 +878,8 @@ def test_softmax_rows_masked(cuda):
     S2 = torch.randn(4, 21, generator=g).to(cuda)
     P2 = ops.merge(ops.softmax_rows_split(S2, 21, ld_p=64, seg_counts=cnt2.to(cuda), slot=7, rows_per_problem=4)).cpu()
     live = torch.cat([torch.arange(7) < int(c) for c in cnt2[0]])
-    assert float((P2[:, :21][:, live].double() - torch.softmax(S2.cpu().double()[:, live], 1)).abs().max()) < 1e-6
+    ref2 = torch.softmax(S2.cpu().double()[:, live], 1)
+    assert float(((P2[:, :21][:, live].double() - ref2).abs() / (ref2 + 1e-6)).max()) < 2e-5
     assert not bool(P2[:, :21][:, ~live].any())
 
 

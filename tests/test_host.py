@@ -493,7 +493,7 @@ def test_abi_argument_checks_without_a_gpu():
     assert L.hvr_roi_align_fwd(one, 1, one, 4, 1, 256, 38, 63, 7, 7, 0.0625, 2, null, 1, null, null, 0, null, null) == ARG
     assert L.hvr_roi_align_fwd(one, 1, one, 4, 1, 256, 38, 63, 7, 7, 0.0625, 2, one, 2, null, null, 0, null, null) == ARG
     assert L.hvr_roi_align_fwd(one, 0, one, 4, 1, 256, 38, 63, 7, 7, 0.0625, 2, one, 0, null, null, 0, null, null) == WS
-    assert L.hvr_debug_roi_variant(5) == ARG and L.hvr_debug_roi_variant(0) == 0
+    assert L.hvr_debug_roi_variant(9) == ARG and L.hvr_debug_roi_variant(0) == 0
     # video descriptor / support selection (next row N4)
     nb = L.hvr_video_descriptor_workspace_bytes(7, 15, 256)
     assert nb == 7 * 15 * 16 * 256 * 4

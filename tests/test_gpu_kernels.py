@@ -965,3 +965,83 @@ def test_det_postprocess_counted(cuda, n_valid):
         assert float((d[p, :kk, 4].cpu() - t['dets'][:, 4]).abs().max()) < 1e-6
         d1, l1, k1 = ops.det_postprocess(rois[sl].to(cuda), cls[sl].to(cuda), reg[sl].to(cuda), (600, 1000), 1.0, True)
         assert int(k1) == kk and torch.equal(d1[:kk], d[p, :kk]) and torch.equal(l1[:kk], l[p, :kk])
+
+
+# ---------------------------------------------------------------------------------------
+# C-ABI composites for non-Python hosts (csrc/relation.cu)
+# ---------------------------------------------------------------------------------------
+def test_c_host_relation_block(cuda, tmp_path):
+    """tests/host/relation_host.c - a plain-C host: hvr_pack_linear + hvr_relation_fwd against its own double-precision
+    restatement of forward_single_selsa (1e-3 relative), built with gcc and run here."""
+    import subprocess
+    from tests.test_host import _build_c_host
+    exe = _build_c_host(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and 'OK' in r.stdout, (r.stdout, r.stderr)
+
+
+def test_abi_packing_and_relation_equal_the_python_engine(cuda):
+    """hvr_pack_conv_bn / hvr_pack_linear produce the bits engine.pack_* produce (fp64 BN fold, K-major re-layout,
+    padding, split), and hvr_relation_fwd returns the bits engine.relation returns (the same six launches)."""
+    import ctypes
+    from hvrnet_b200 import _lib, engine, ops
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(6)
+    fp = lambda t: ctypes.c_void_p(t.data_ptr())
+    # conv + BN (+ bias)
+    for (co, ci, k, with_bn, with_bias) in ((96, 40, 3, True, False), (70, 64, 1, False, True), (64, 24, 3, True, True)):
+        w = torch.randn(co, ci, k, k, generator=g)
+        sd = {'c.weight': w}
+        bn = [torch.rand(co, generator=g) + 0.5, torch.randn(co, generator=g), torch.randn(co, generator=g), torch.rand(co, generator=g) + 0.5]
+        if with_bn:
+            sd.update({'b.weight': bn[0], 'b.bias': bn[1], 'b.running_mean': bn[2], 'b.running_var': bn[3]})
+        bias = torch.randn(co, generator=g) if with_bias else None
+        if with_bias:
+            sd['c.bias'] = bias
+        ref = engine._pack_conv_bn(sd, 'c', 'b' if with_bn else None, cuda, bias_name='c.bias' if with_bias else None)
+        R, C = L.hvr_packed_rows(co), L.hvr_packed_cols(k * k * ci)
+        assert (R, C) == tuple(ref.w.shape)
+        hi = torch.empty((R, C), dtype=torch.bfloat16, device=cuda)
+        lo = torch.empty_like(hi)
+        b = torch.empty(R, dtype=torch.float32, device=cuda)
+        null = ctypes.c_void_p(0)
+        rc = L.hvr_pack_conv_bn(fp(w), *( [fp(t) for t in bn] if with_bn else [null] * 4), 1e-5,
+                                fp(bias) if with_bias else null, co, ci, k, k, fp(hi), fp(lo), fp(b), null)
+        assert rc == 0
+        assert torch.equal(hi.view(torch.int16), ref.w.hi.view(torch.int16)) and torch.equal(lo.view(torch.int16), ref.w.lo.view(torch.int16))
+        assert torch.equal(b, ref.bias)
+    # linear with a column permutation (fc_new_1's NHWC order)
+    n, kk = 100, 4 * 3 * 3
+    wl, bl = torch.randn(n, kk, generator=g), torch.randn(n, generator=g)
+    perm = engine.nhwc_perm(4, 3)
+    ref = engine.pack_linear(wl, bl, cuda, col_perm=perm)
+    hi = torch.empty(tuple(ref.w.shape), dtype=torch.bfloat16, device=cuda)
+    lo = torch.empty_like(hi)
+    b = torch.empty(ref.w.shape[0], dtype=torch.float32, device=cuda)
+    pi = perm.to(torch.int32).contiguous()
+    assert L.hvr_pack_linear(fp(wl), fp(bl), n, kk, fp(pi), fp(hi), fp(lo), fp(b), ctypes.c_void_p(0)) == 0
+    assert torch.equal(hi.view(torch.int16), ref.w.hi.view(torch.int16)) and torch.equal(lo.view(torch.int16), ref.w.lo.view(torch.int16))
+    assert torch.equal(b, ref.bias)
+    # one relation block: all-row queries and key-only queries
+    D, N = 256, 450
+    P = {}
+    for name in ('q1', 'k1', 'o1'):
+        P[name] = engine.pack_linear(torch.randn(D, D, generator=g) * 0.2, torch.randn(D, generator=g) * 0.1, cuda)
+    X = ops.split(torch.randn(N, D, generator=g).to(cuda))
+    XT = ops.transpose_split(X, D)
+    W = _lib.HvrRelationWeights(D, *[x for nm in ('q1', 'k1', 'o1') for x in (P[nm].w.hi.data_ptr(), P[nm].w.lo.data_ptr(), P[nm].bias.data_ptr())])
+    for (s0, nq) in ((0, N), (128, 100)):
+        q_range = None if nq == N else (s0, nq)
+        want = engine.relation(P, 1, X, XT, q_range=q_range, res=X[s0:s0 + nq])
+        out = ops.Split.empty((nq, D), cuda)
+        wsb = L.hvr_relation_workspace_bytes(nq, N, D)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=cuda)
+        xq = X[s0:s0 + nq]
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        rc = L.hvr_relation_fwd(ctypes.byref(W), fp(X.hi), fp(X.lo), D, N, fp(xq.hi) if q_range else None,
+                                fp(xq.lo) if q_range else None, D, nq, fp(xq.hi), fp(xq.lo), D, 1, fp(out.hi), fp(out.lo), D,
+                                fp(ws), wsb, st)
+        assert rc == 0
+        assert torch.equal(out.hi.view(torch.int16), want.hi.view(torch.int16))
+        assert torch.equal(out.lo.view(torch.int16), want.lo.view(torch.int16))

@@ -504,3 +504,24 @@ def test_abi_argument_checks_without_a_gpu():
     assert L.hvr_support_select(one, 8, 256, 7, 2, 4, one, null, null) == ARG            # g0 + n_local > G
     assert L.hvr_support_select(one, 8, 256, 0, 0, 4, one, null, null) == 0              # nothing to select
     assert L.hvr_strerror(ARG) not in (b'', b'ok')
+
+
+def _build_c_host(tmp_path):
+    """gcc build of tests/host/relation_host.c against include/hvr_b200.h and libhvr_b200.so."""
+    import subprocess
+    from hvrnet_b200 import _lib
+    exe = str(tmp_path / 'relation_host')
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(['gcc', '-std=c11', '-O2', '-Wall', '-Werror', os.path.join(ROOT, 'tests', 'host', 'relation_host.c'),
+                           '-I', os.path.join(ROOT, 'include'), '-I', '/usr/local/cuda/include', '-L', libdir,
+                           '-lhvr_b200', '-L', '/usr/local/cuda/lib64', '-lcudart', '-lm', '-Wl,-rpath,' + libdir,
+                           '-Wl,-rpath,/usr/local/cuda/lib64', '-o', exe])
+    return exe
+
+
+def test_c_host_compiles_against_the_header(tmp_path):
+    """The boundary is a C ABI: a plain-C translation unit (gcc -std=c11 -Werror) includes include/hvr_b200.h, calls the
+    packing / relation / igemm entry points and links against libhvr_b200.so.  (Run on the GPU box by
+    tests/test_gpu_kernels.py::test_c_host_relation_block.)"""
+    exe = _build_c_host(tmp_path)
+    assert os.path.exists(exe)

@@ -406,7 +406,7 @@ def main():
             c4 = model(img=img, img_meta=[metas[0]] * V, backbone_feat=True)[0]
             # next step's H2D + trunk overlap this step's window graph (side stream); not in the roofline leg,
             # whose per-launch event timings must not see a second stream's kernels
-            if model._runner is not None and model._runner.capture:
+            if model._runner is not None and model._runner.capture and os.environ.get('HVR_NO_PREFETCH') != '1':
                 model._runner.prefetch((hostV if from_host else devV)[T + (i + 1) % pool])
             for v, t in enumerate(GraphRunner.per_frame(c4)):
                 dqs[v].append(t)
@@ -585,31 +585,59 @@ def main():
     # NOT the headline: `value` / `e2e` above time the path as the reference executes it.
     streaming = None
     if args.workload in ('hrnmp', 'selsa') and not args.no_streaming and not args.eager:
-        from hvrnet_b200.runtime import StreamGraphRunner
         model.enable_cuda_graphs(False)
-        run = StreamGraphRunner(model, V, window=T)
-        src = hostV if V > 1 else host
-        for i in range(T + W):                                     # fill the windows + warm-up (captures both graphs)
-            run.push(src[i % (T + pool)], metas[0])
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for i in range(K):
-            run.push(src[(T + W + i) % (T + pool)], metas[0])
-        s1.record()
-        torch.cuda.synchronize()
-        sms = s0.elapsed_time(s1)
-        if world > 1:
-            t = torch.tensor([sms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            sms = float(t.item())
-        streaming = {'value': world * V * K / (sms / 1e3), 'unit': 'frames/s', 'ms_per_step': sms / K,
-                     'input': 'pinned host frames (H2D inside the timed region)',
+        src_h, src_d = (hostV, devV) if V > 1 else (host, devf)
+        n_src = T + pool
+
+        def stream_pass(src, capture=True, profile=False):
+            """K timed steps of the streaming scheduler through the detector's call surface (stream=True)."""
+            model.enable_streaming(V, window=T, capture=capture)
+            for i in range(T + W):                                 # fill the windows + warm-up (captures both graphs)
+                model(img=src[i % n_src], img_meta=[metas[0]], stream=True, rescale=True)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            if profile:
+                ops.PROFILE = []
+            l0 = _lib.launch_count() + model._streamer.replayed_launches
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for i in range(K):
+                res = model(img=src[(T + W + i) % n_src], img_meta=[metas[0]], stream=True, rescale=True)
+            s1.record()
+            torch.cuda.synchronize()
+            sms = s0.elapsed_time(s1)
+            n_launch = _lib.launch_count() + model._streamer.replayed_launches - l0
+            prof, ops.PROFILE = ops.PROFILE, None
+            if world > 1:
+                t = torch.tensor([sms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                sms = float(t.item())
+            model.enable_streaming(flag=False)
+            return sms, prof, n_launch, res
+        sms_dev, _, s_launch, s_res = stream_pass(src_d)
+        sms_e2e, _, _, _ = stream_pass(src_h)
+        sms_prof, sprof, _, _ = stream_pass(src_d, capture=False, profile=True)
+        s_gemm_ms = sum(p_[0].elapsed_time(p_[1]) for p_ in sprof)
+        s_gemm_flops = sum(p_[2] for p_ in sprof)
+        s_ach = s_gemm_flops / (s_gemm_ms / 1e3) / 1e12 if s_gemm_ms > 0 else 0.0
+
+        def nbytes_(r):
+            return int(r.nbytes) if hasattr(r, 'nbytes') else sum(nbytes_(x) for x in r)
+        streaming = {'value': world * V * K / (sms_dev / 1e3), 'unit': 'frames/s', 'ms_per_step': sms_dev / K,
+                     'e2e': {'value': world * V * K / (sms_e2e / 1e3), 'unit': 'frames/s', 'ms_per_step': sms_e2e / K,
+                             'h2d_bytes_per_step': frame_bytes, 'd2h_bytes_per_step': nbytes_(s_res)},
+                     'gpu_launches': int(s_launch),
+                     'executed_gflop_per_key_frame': s_gemm_flops / K / V / 1e9,
+                     'roofline': {'bound': 'tensor', 'kernel': 'igemm_tc_kernel (tcgen05 split-bf16 implicit GEMM)',
+                                  'achieved': s_ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': s_ach / peak,
+                                  'tensor_work_frac': 3.0 * s_ach / peak, 'peak_source': peak_src,
+                                  'kernel_ms_per_step': s_gemm_ms / K, 'share_of_step': s_gemm_ms / sms_prof,
+                                  'launches_per_step': len(sprof) / K},
+                     'call': 'model.enable_streaming(V, window=T); model(img=frames, img_meta=[meta], stream=True)',
                      'note': 'streaming scheduler with per-frame caches (SURVEY 8f N1): same detections bit for '
-                             'bit, less work per key frame than the reference executes; reported for information, '
-                             'not the headline'}
+                             'bit (ragged frames included), less work per key frame than the reference executes; '
+                             'reported for information, not the headline'}
     line = {
         'metric': 'VID key frames/sec (1000x600, 300 proposals)', 'value': fps, 'unit': 'frames/s', 'n_gpus': world,
         'steps': K, 'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak',

@@ -357,7 +357,7 @@ __global__ void roi_align_generic_kernel(const float* __restrict__ feat, const f
 
 int g_roi_variant = 0;   // test hook (hvr_debug_roi_variant): 0 = heuristic, 1 = always the per-bin kernel
 int g_sep_minb = 2;      // test hook (hvr_debug_roi_variant 2 / 3): resident CTAs per SM the fast kernel is built for
-int g_slab = 0;          // test hook (hvr_debug_roi_variant 4 / 5 / 6): 0 = heuristic, 1 = slab kernel whenever it applies, 2 = never
+int g_slab = 0;          // test hook (hvr_debug_roi_variant 4 / 5 / 6): 0 = heuristic (= never), 1 = slab kernel whenever it applies, 2 = never
 
 }  // namespace
 
@@ -400,7 +400,8 @@ extern "C" int hvr_roi_align_fwd_fast(const float* feat, int feat_nhwc, const fl
   const bool slab = fast_ok && g_slab != 2 && C % SLAB_C == 0 && pw * 4 <= 32 && slab_smem <= 220 * 1024 && n_imgs <= 65535 &&
                     (size_t)n_imgs * 8 <= 96 * 1024 && ws != nullptr &&
                     ws_bytes >= hvr_roi_align_fast_workspace_bytes(n_rois, n_imgs) &&
-                    (g_slab == 1 || (long long)n_imgs * (C / SLAB_C) >= num_sms);
+                    g_slab == 1;   // measured (profiles/r02c_roi_align_variants.txt): instruction-bound, 1.4x slower than the
+                                   // RoI-per-CTA shape at 105 frames -> never chosen by the heuristic, kept behind the hook
   if (!sep && !slab)
     return hvr_roi_align_fwd(feat, feat_nhwc, rois, n_rois, n_imgs, C, H, W, ph, pw, spatial_scale, sample_num, out,
                              out_layout, out_hi, out_lo, ld_split, feat_nhwc ? nullptr : (float*)ws, stream);

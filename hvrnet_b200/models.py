@@ -550,6 +550,19 @@ class TwoStageDetector(nn.Module):
         self._runner = GraphRunner(self, capture=capture) if flag else None
         return self
 
+    _streamer = None
+
+    def enable_streaming(self, n_videos=1, window=None, flag=True, capture=True):
+        """Streaming scheduler behind the detector's own call surface: afterwards
+        ``model(img=frames [V,3,H,W], img_meta=[meta], stream=True, rescale=...)`` advances V video streams by one
+        frame each and returns None while the windows fill, then the V forward_feat results of the windows' key
+        frames - the same detections, bit for bit, as backbone_feat=True + forward_feat=True on the same windows,
+        with the per-frame stages (trunk, C5, RPN, proposals, RoIAlign, fc_new_1) computed once per frame instead of
+        once per window (runtime.StreamGraphRunner: two CUDA graphs and one device->host read per step)."""
+        from .runtime import StreamGraphRunner
+        self._streamer = StreamGraphRunner(self, n_videos, window=window, capture=capture) if flag else None
+        return self
+
     def extract_feat(self, img):
         """two_stage.py:91-97 -> (C4,).  `img` may live in pinned host memory when CUDA graphs
         are enabled (it is copied straight into the trunk graph's input buffer)."""
@@ -574,8 +587,14 @@ class TwoStageDetector(nn.Module):
         return self.simple_test(imgs[0], img_metas[0], **kwargs)
 
     @torch.no_grad()
-    def forward(self, img=None, img_meta=None, return_loss=True, backbone_feat=False, forward_feat=False, **kwargs):
-        """base.py:106-132."""
+    def forward(self, img=None, img_meta=None, return_loss=True, backbone_feat=False, forward_feat=False, stream=False,
+                **kwargs):
+        """base.py:106-132 (+ stream=True: enable_streaming's per-frame entry)."""
+        if stream:
+            if self._streamer is None:
+                raise HvrError('call enable_streaming(n_videos, window) first')
+            meta = img_meta[0] if isinstance(img_meta, (list, tuple)) else img_meta
+            return self._streamer.push(img, meta, rescale=kwargs.get('rescale', True))
         if backbone_feat:
             if isinstance(img, list):
                 assert len(img) == len(img_meta), 'img and img_meta should have same number!'

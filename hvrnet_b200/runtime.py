@@ -349,7 +349,9 @@ class StreamGraphRunner:
     count; the head graph masks the keys of all T frames of every window with them, so frames that yield fewer
     than max_num proposals are handled inside the graphs (same arithmetic as forward_feat)."""
 
-    def __init__(self, model, n_videos, window=None):
+    def __init__(self, model, n_videos, window=None, capture=True):
+        """capture=False: the two closures are re-issued eagerly every step (identical launches) so that bench.py's
+        roofline leg can bracket each hvr_igemm launch with CUDA events."""
         from collections import deque
         self.m = model
         self.V = n_videos
@@ -360,7 +362,7 @@ class StreamGraphRunner:
         self._head = None
         self.replayed_launches = 0
         self._cap = GraphRunner._capture
-        self.capture = True
+        self.capture = capture
         self._version = model.weights_version()
 
     def _frame_graph(self, img, meta):
@@ -441,7 +443,7 @@ class StreamGraphRunner:
             self._frame = self._frame_graph(img, meta)
         fr = self._frame
         fr.inputs.copy_(img, non_blocking=True)
-        fr.graph.replay()
+        GraphRunner._replay(fr)
         self.replayed_launches += fr.launches
         props, counts, f1, f1T = fr.outputs[:4]
         B = f1.shape[0] // V                                 # rows per video in the frame graph (P rounded up to 64)
@@ -466,7 +468,7 @@ class StreamGraphRunner:
             torch.cat([f[1] for f in fl], 0, out=fs.seg[v])
             fs.rois_key[v * P:(v + 1) * P, 1:] = fl[key][0][:, :4]
             fs.key_counts[v:v + 1].copy_(fl[key][1])
-        hd.graph.replay()
+        GraphRunner._replay(hd)
         self.replayed_launches += hd.launches
         hd.host.copy_(hd.result.buf, non_blocking=True)
         torch.cuda.current_stream().synchronize()

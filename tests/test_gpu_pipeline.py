@@ -345,6 +345,20 @@ def test_stream_graph_runner_bit_identical(world):
     got = [run.push(torch.cat([frames[orders[0][t]][None], frames[orders[1][t]][None]]), world['metas'][0])
            for t in range(4)]
     assert got[0] is None and got[1] is None
+    # the same through the registered detector's call surface (enable_streaming + stream=True), graphs and eager
+    for capture in (True, False):
+        m.enable_streaming(2, window=3, capture=capture)
+        try:
+            via = [m(img=torch.cat([frames[orders[0][t]][None], frames[orders[1][t]][None]]), img_meta=[world['metas'][0]],
+                     stream=True, rescale=True) for t in range(4)]
+        finally:
+            m.enable_streaming(flag=False)
+        assert via[0] is None and via[1] is None
+        for w_ in (2, 3):
+            for v in range(2):
+                for o in range(2):
+                    for c in range(30):
+                        assert np.array_equal(via[w_][v][o][c], got[w_][v][o][c])
     for w in range(2):
         for v in range(2):
             ref = m(x=c4[v][w:w + 3], img=None, img_meta=world['metas'], forward_feat=True, return_loss=False,

@@ -309,39 +309,69 @@ def inter_video_block(args, dev, world, rank, dist, steps=4, warm=2):
         for v, t in enumerate(GraphRunner.per_frame(c4)):
             dqs[v].append(t)
         return model.forward_feat_intervideo([list(d) for d in dqs], metas, n_support=4, rescale=True)
-    for i in range(warm):
-        step(i)
+    def timed(fn):
+        for i in range(warm):
+            fn(i)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        extra = []
+        e0.record()
+        for i in range(steps):
+            fn(warm + i)
+            extra.append(model._runner.last_all_gather_ms())   # events on the communication stream; the step has ended
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        return e0.elapsed_time(e1), extra
+    ms, ag = timed(step)
+
+    # the same batch WITHOUT the inter-video stage (plain forward_feat_batch on the same windows): what the exchange
+    # and the longer stage-4 key set cost at this batch size
+    def step_intra(i):
+        c4 = model(img=devV[T + i % pool], img_meta=[metas[0]] * V, backbone_feat=True)[0]
+        for v, t in enumerate(GraphRunner.per_frame(c4)):
+            dqs[v].append(t)
+        return model.forward_feat_batch([list(d) for d in dqs], metas, rescale=True)
+    ms_intra, _ = timed(step_intra)
+    # the collective alone: back-to-back replays of the same all_gather_into_tensor after a barrier (no rank skew)
+    c = model._runner.last_inter
+    reps = 10
     torch.cuda.synchronize()
     dist.barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.all_gather_into_tensor(c.recv_flat, c.state['st'].send)
+    a0.record()
+    for _ in range(reps):
+        dist.all_gather_into_tensor(c.recv_flat, c.state['st'].send)
+    a1.record()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ag = []
-    e0.record()
-    for i in range(steps):
-        step(warm + i)
-        ag.append(model._runner.last_all_gather_ms())     # events on the communication stream; the step has ended
-    e1.record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms, max(ag), sum(ag) / len(ag)], device=dev, dtype=torch.float64)
+    ag_iso = a0.elapsed_time(a1) / reps
+    t = torch.tensor([ms, max(ag), sum(ag) / len(ag), ms_intra, ag_iso], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ag_max, ag_mean = [float(x) for x in t.tolist()]
-    st = model._runner.last_inter.state['st']
+    ms, ag_max, ag_mean, ms_intra, ag_iso = [float(x) for x in t.tolist()]
+    st = c.state['st']
     send_bytes = st.send.numel() * 2
     recv_bytes = send_bytes * (world - 1)
     model.enable_cuda_graphs(False)
     del model
     torch.cuda.empty_cache()
+    fps, fps_intra = world * V * steps / (ms / 1e3), world * V * steps / (ms_intra / 1e3)
     return {'workload': 'HVRNet hrnmp batched inference, %d key-frames/GPU, NCCL all-gather of inter-video proposal features' % V,
-            'value': world * V * steps / (ms / 1e3), 'unit': 'frames/s', 'ms_per_step': ms / steps, 'steps': steps,
+            'value': fps, 'unit': 'frames/s', 'ms_per_step': ms / steps, 'steps': steps,
             'key_frames_per_gpu': V, 'n_support': 4, 'launch': 'cuda graphs: trunk + three window graphs around the all-gather',
-            'all_gather': {'ms_mean': ag_mean, 'ms_max': ag_max, 'bytes_sent_per_rank': send_bytes,
-                           'bytes_received_per_rank': recv_bytes,
-                           'achieved_GBs_per_rank': recv_bytes / (ag_mean / 1e3) / 1e9 if ag_mean > 0 else None,
-                           'nvlink_reference_GBs': 770.0, 'share_of_step': ag_mean / (ms / steps),
-                           'note': 'device time between events on the communication stream around the ONE collective of a '
-                                   'step; it runs under the branch post-processing and the k_4 projection (graph B)'},
+            'intra_same_batch': {'value': fps_intra, 'unit': 'frames/s', 'ms_per_step': ms_intra / steps,
+                                 'note': 'forward_feat_batch on the same %d windows per rank (no inter-video stage)' % V},
+            'loss_vs_intra_same_batch': 1.0 - fps / fps_intra,
+            'all_gather': {'ms_isolated': ag_iso, 'achieved_GBs_per_rank': recv_bytes / (ag_iso / 1e3) / 1e9,
+                           'nvlink_reference_GBs': 770.0, 'bytes_sent_per_rank': send_bytes,
+                           'bytes_received_per_rank': recv_bytes, 'share_of_step_isolated': ag_iso / (ms / steps),
+                           'ms_in_step_mean': ag_mean, 'ms_in_step_max': ag_max,
+                           'note': 'ms_isolated: the same all_gather_into_tensor replayed back to back after a barrier. '
+                                   'ms_in_step: device time between events on the communication stream around the ONE collective '
+                                   'of a step - it includes waiting for the slowest rank to reach it (rank skew) and runs under '
+                                   'graph B (branch post-processing, k_4 projection)'},
             'input': 'device-resident frames (%dx3x608x1008 fp32 per step per rank)' % V}
 
 

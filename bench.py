@@ -306,6 +306,9 @@ def inter_video_block(args, dev, world, rank, dist, steps=4, warm=2):
 
     def step(i):
         c4 = model(img=devV[T + i % pool], img_meta=[metas[0]] * V, backbone_feat=True)[0]
+        # the next step's trunk runs on the side stream under this step's window graphs (as in the headline loop): it also
+        # keeps the GPU busy while graph C waits for the slowest rank to reach the all-gather
+        model._runner.prefetch(devV[T + (i + 1) % pool])
         for v, t in enumerate(GraphRunner.per_frame(c4)):
             dqs[v].append(t)
         return model.forward_feat_intervideo([list(d) for d in dqs], metas, n_support=4, rescale=True)
@@ -331,6 +334,7 @@ def inter_video_block(args, dev, world, rank, dist, steps=4, warm=2):
     # and the longer stage-4 key set cost at this batch size
     def step_intra(i):
         c4 = model(img=devV[T + i % pool], img_meta=[metas[0]] * V, backbone_feat=True)[0]
+        model._runner.prefetch(devV[T + (i + 1) % pool])
         for v, t in enumerate(GraphRunner.per_frame(c4)):
             dqs[v].append(t)
         return model.forward_feat_batch([list(d) for d in dqs], metas, rescale=True)

@@ -18,7 +18,7 @@ extern "C" const char* hvr_strerror(int code) {
   }
 }
 extern "C" int hvr_last_cuda_error(void) { return g_hvr_last_cuda_error; }
-extern "C" int hvr_abi_version(void) { return 2; }
+extern "C" int hvr_abi_version(void) { return 3; }   // 3: round-2 entry points (fast RoIAlign, masks, window kernels, composites)
 extern "C" uint64_t hvr_launch_count(void) { return g_hvr_launches.load(); }
 
 namespace {
@@ -276,9 +276,15 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* red, 
 struct SegMask {
   const int* counts;
   int n_segs, slot, rows_per_problem;
+  float inv_slot;
 };
-__device__ __forceinline__ int seg_limit(const SegMask& m, int row, int c) {
-  const int seg = c / m.slot;
+constexpr int SM_MAX_SEGS = 64;   // blocks whose limits are staged in shared memory (more: read from global)
+// first column past the live keys of the block that holds column c.  lim: the row's per-block limits
+// (seg * slot + count) staged in shared memory.  The block index comes from a float multiply instead of an integer
+// division: (c + 0.5) / slot is never within 1e-3 of an integer, far outside fp32 rounding for c < 2^20.
+__device__ __forceinline__ int seg_limit(const SegMask& m, const int* lim, int row, int c) {
+  const int seg = (int)(((float)c + 0.5f) * m.inv_slot);
+  if (lim) return lim[seg];
   return seg * m.slot + m.counts[(size_t)(row / m.rows_per_problem) * m.n_segs + seg];
 }
 __global__ void __launch_bounds__(SM_THREADS) softmax_rows_kernel(const float* __restrict__ S, int cols, long long ld_s,
@@ -287,7 +293,14 @@ __global__ void __launch_bounds__(SM_THREADS) softmax_rows_kernel(const float* _
                                                                   int vec_ok, const SegMask mask) {
   __shared__ float red[SM_THREADS / 32];
   __shared__ float bcast;
+  __shared__ int s_lim[SM_MAX_SEGS];
   const int row = blockIdx.x, tid = threadIdx.x;
+  const int* lim = nullptr;
+  if (mask.counts && mask.n_segs <= SM_MAX_SEGS) {
+    if (tid < mask.n_segs) s_lim[tid] = tid * mask.slot + mask.counts[(size_t)(row / mask.rows_per_problem) * mask.n_segs + tid];
+    __syncthreads();
+    lim = s_lim;
+  }
   const float* s = S + (size_t)row * ld_s;
   __nv_bfloat16* ph = phi + (size_t)row * ld_p;
   __nv_bfloat16* pl = plo + (size_t)row * ld_p;
@@ -305,11 +318,13 @@ __global__ void __launch_bounds__(SM_THREADS) softmax_rows_kernel(const float* _
         if (c + 2 >= cols) v[j].z = -INFINITY;
         if (c + 3 >= cols) v[j].w = -INFINITY;
         if (mask.counts) {                   // slot % 4 == 0 on this path: the group lies inside one block
-          const int lim = seg_limit(mask, row, c);
-          if (c >= lim) v[j].x = -INFINITY;
-          if (c + 1 >= lim) v[j].y = -INFINITY;
-          if (c + 2 >= lim) v[j].z = -INFINITY;
-          if (c + 3 >= lim) v[j].w = -INFINITY;
+          const int end = seg_limit(mask, lim, row, c);
+          if (c + 3 >= end) {                // only the groups that straddle / lie behind a block's count
+            if (c >= end) v[j].x = -INFINITY;
+            if (c + 1 >= end) v[j].y = -INFINITY;
+            if (c + 2 >= end) v[j].z = -INFINITY;
+            v[j].w = -INFINITY;
+          }
         }
         mx = fmaxf(mx, fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w)));
       } else {
@@ -353,7 +368,7 @@ __global__ void __launch_bounds__(SM_THREADS) softmax_rows_kernel(const float* _
     return;
   }
   // scalar path: any alignment, any length (re-reads the row)
-  auto live = [&](int c) { return mask.counts == nullptr || c < seg_limit(mask, row, c); };
+  auto live = [&](int c) { return mask.counts == nullptr || c < seg_limit(mask, lim, row, c); };
   float mx = -INFINITY;
   for (int c = tid; c < cols; c += SM_THREADS)
     if (live(c)) mx = fmaxf(mx, __ldg(s + c));
@@ -472,7 +487,7 @@ extern "C" int hvr_softmax_rows_split(const float* S, int rows, int cols, int64_
   const int vec_ok = (ld_s % 4 == 0) && (ld_p % 4 == 0) && ((reinterpret_cast<uintptr_t>(S) & 15u) == 0) &&
                      ((reinterpret_cast<uintptr_t>(p_hi) & 7u) == 0) && ((reinterpret_cast<uintptr_t>(p_lo) & 7u) == 0);
   softmax_rows_kernel<<<rows, SM_THREADS, 0, ST(stream)>>>(S, cols, ld_s, (__nv_bfloat16*)p_hi,
-                                                           (__nv_bfloat16*)p_lo, ld_p, vec_ok, SegMask{nullptr, 0, 1, 1});
+                                                           (__nv_bfloat16*)p_lo, ld_p, vec_ok, SegMask{nullptr, 0, 1, 1, 1.0f});
   HVR_LAUNCHED();
   return HVR_OK;
 }
@@ -486,7 +501,8 @@ extern "C" int hvr_softmax_rows_split_masked(const float* S, int rows, int cols,
                      ((reinterpret_cast<uintptr_t>(S) & 15u) == 0) &&
                      ((reinterpret_cast<uintptr_t>(p_hi) & 7u) == 0) && ((reinterpret_cast<uintptr_t>(p_lo) & 7u) == 0);
   softmax_rows_kernel<<<rows, SM_THREADS, 0, ST(stream)>>>(S, cols, ld_s, (__nv_bfloat16*)p_hi, (__nv_bfloat16*)p_lo,
-                                                           ld_p, vec_ok, SegMask{seg_counts, n_segs, slot, rows_per_problem});
+                                                           ld_p, vec_ok,
+                                                           SegMask{seg_counts, n_segs, slot, rows_per_problem, 1.0f / (float)slot});
   HVR_LAUNCHED();
   return HVR_OK;
 }

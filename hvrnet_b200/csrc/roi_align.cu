@@ -200,6 +200,83 @@ __global__ void __launch_bounds__(256, SN2_MIN_CTAS) roi_align_sn2_kernel(
 // RoI are computed once into shared memory, the <= 4 merged column taps of q live in registers; every thread
 // walks the RoI's rows top to bottom and writes its ph outputs.  All branches depend on the RoI only (rows)
 // or on q only (warp-uniform when C % 128 == 0).  Explicit fmaf: independent of this file's -fmad=false.
+// The walk of roi_align_sep.cuh::roi_column_sep_sn2 specialised for the device: the number of merged column taps NC
+// (1..4, uniform per warp) and the output height PH are compile-time, so a row interpolation is NC loads + 4*NC
+// multiply-adds of straight-line code on pre-added 64-bit column pointers and the sample loop is unrolled (row taps
+// at immediate shared-memory offsets).  ncu of the first version (profiles/r02e_roi_align_ncu_summary.txt): the
+// kernel is instruction-issue bound - 1867 warp instructions per warp and RoI of which 289 are the multiply-adds -
+// not memory bound, so the instruction count is what this version attacks.  Same operations in the same order as
+// the generic core (the slab kernel, which still runs the core, is its bit-for-bit twin in the tests).
+template <int NC>
+__device__ __forceinline__ float4 row_interp_nc(const char* const (&pc)[4], const float (&w)[4], uint32_t row_off) {
+  float4 v[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) v[k] = __ldg(reinterpret_cast<const float4*>(pc[k] + row_off));
+  float4 t;
+  if (NC == 4) {
+    t.x = w[3] * v[3].x; t.y = w[3] * v[3].y; t.z = w[3] * v[3].z; t.w = w[3] * v[3].w;
+  } else {
+    t = make_float4(fmaf(w[NC - 1], v[NC - 1].x, 0.f), fmaf(w[NC - 1], v[NC - 1].y, 0.f),
+                    fmaf(w[NC - 1], v[NC - 1].z, 0.f), fmaf(w[NC - 1], v[NC - 1].w, 0.f));
+  }
+#pragma unroll
+  for (int k = NC - 2; k >= 0; --k) {
+    t.x = fmaf(w[k], v[k].x, t.x); t.y = fmaf(w[k], v[k].y, t.y);
+    t.z = fmaf(w[k], v[k].z, t.z); t.w = fmaf(w[k], v[k].w, t.w);
+  }
+  return t;
+}
+
+// split + store of one output vector: packed conversions (the same round-to-nearest-even as split2)
+__device__ __forceinline__ void store_bin_packed(const float4& a, float* __restrict__ o_f32,
+                                                 __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_lo) {
+  if (o_f32) *reinterpret_cast<float4*>(o_f32) = a;
+  if (o_hi) {
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(a.x, a.y), h23 = __floats2bfloat162_rn(a.z, a.w);
+    const uint32_t b01 = *reinterpret_cast<const uint32_t*>(&h01), b23 = *reinterpret_cast<const uint32_t*>(&h23);
+    const __nv_bfloat162 l01 = __floats2bfloat162_rn(__fsub_rn(a.x, __uint_as_float(b01 << 16)),
+                                                     __fsub_rn(a.y, __uint_as_float(b01 & 0xFFFF0000u)));
+    const __nv_bfloat162 l23 = __floats2bfloat162_rn(__fsub_rn(a.z, __uint_as_float(b23 << 16)),
+                                                     __fsub_rn(a.w, __uint_as_float(b23 & 0xFFFF0000u)));
+    *reinterpret_cast<uint2*>(o_hi) = make_uint2(b01, b23);
+    *reinterpret_cast<uint2*>(o_lo) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+  }
+}
+
+template <int NC, int PH>
+__device__ __forceinline__ void roi_column_walk(const RowTap* __restrict__ rows, const char* const (&pc)[4],
+                                                const float (&w)[4], float* o_f32, __nv_bfloat16* o_hi,
+                                                __nv_bfloat16* o_lo, size_t step) {
+  uint32_t ca = kRowInvalid, cb = kRowInvalid;
+  float4 ta = make_float4(0.f, 0.f, 0.f, 0.f), tb = ta;
+#pragma unroll
+  for (int p = 0; p < PH; ++p) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int iy = 0; iy < 2; ++iy) {
+      const RowTap r = rows[p * 2 + iy];
+      if (r.o0 != kRowInvalid) {
+        if (r.o0 == cb) { ta = tb; ca = cb; }
+        else if (r.o0 != ca) { ta = row_interp_nc<NC>(pc, w, r.o0); ca = r.o0; }
+        acc.x = fmaf(r.w0, ta.x, acc.x); acc.y = fmaf(r.w0, ta.y, acc.y);
+        acc.z = fmaf(r.w0, ta.z, acc.z); acc.w = fmaf(r.w0, ta.w, acc.w);
+        if (r.w1 != 0.f) {
+          if (r.o1 != ca) {
+            if (r.o1 != cb) { tb = row_interp_nc<NC>(pc, w, r.o1); cb = r.o1; }
+            acc.x = fmaf(r.w1, tb.x, acc.x); acc.y = fmaf(r.w1, tb.y, acc.y);
+            acc.z = fmaf(r.w1, tb.z, acc.z); acc.w = fmaf(r.w1, tb.w, acc.w);
+          } else {
+            acc.x = fmaf(r.w1, ta.x, acc.x); acc.y = fmaf(r.w1, ta.y, acc.y);
+            acc.z = fmaf(r.w1, ta.z, acc.z); acc.w = fmaf(r.w1, ta.w, acc.w);
+          }
+        }
+      }
+    }
+    store_bin_packed(acc, o_f32 ? o_f32 + p * step : nullptr, o_hi ? o_hi + p * step : nullptr,
+                     o_hi ? o_lo + p * step : nullptr);
+  }
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(448, MINB) roi_align_sep_kernel(
     const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
@@ -213,10 +290,25 @@ __global__ void __launch_bounds__(448, MINB) roi_align_sep_kernel(
   const int q = threadIdx.x / cg, c4 = threadIdx.x - q * cg;
   const ColTaps ct = col_taps_sn2(g.sw, g.bw, q, W, (uint32_t)C * 4u);
   __syncthreads();
-  const TapLoad ld{reinterpret_cast<const char*>(feat + (size_t)g.b * H * W * C + c4 * 4)};
+  const char* base = reinterpret_cast<const char*>(feat + (size_t)g.b * H * W * C + c4 * 4);
   const size_t o_f32 = ((size_t)roi * ph * pw + q) * C + c4 * 4;
   const size_t o_split = (size_t)roi * ld_split + (size_t)q * C + c4 * 4;
   const size_t step = (size_t)pw * C;
+  if (ph == 7 && ct.n >= 1) {
+    const char* const pc[4] = {base + ct.off[0], base + ct.off[1], base + ct.off[2], base + ct.off[3]};
+    const float w[4] = {ct.w[0], ct.w[1], ct.w[2], ct.w[3]};
+    float* of = out ? out + o_f32 : nullptr;
+    __nv_bfloat16* oh = out_hi ? out_hi + o_split : nullptr;
+    __nv_bfloat16* ol = out_hi ? out_lo + o_split : nullptr;
+    switch (ct.n) {
+      case 1: roi_column_walk<1, 7>(rows, pc, w, of, oh, ol, step); break;
+      case 2: roi_column_walk<2, 7>(rows, pc, w, of, oh, ol, step); break;
+      case 3: roi_column_walk<3, 7>(rows, pc, w, of, oh, ol, step); break;
+      default: roi_column_walk<4, 7>(rows, pc, w, of, oh, ol, step); break;
+    }
+    return;
+  }
+  const TapLoad ld{base};
   roi_column_sep_sn2(rows, ph, ct, ld,
                      [&](int p, const float4& v) { store_bin(v, out, out_hi, out_lo, o_f32 + p * step, o_split + p * step); },
                      nullptr);

@@ -43,6 +43,10 @@ __global__ void window_rois_kernel(const float* __restrict__ props, const int* _
     seg_counts[(size_t)v * n_segs + t] = c;
     if (t == key_dim) key_counts[v] = c;
   }
+  if (i < V * (n_segs - T)) {                    // support blocks: empty until hvr_support_index fills them
+    const int v = i / (n_segs - T), k = i - v * (n_segs - T);
+    seg_counts[(size_t)v * n_segs + T + k] = 0;
+  }
 }
 
 // dst[p * dst_rpp + dst_row0 + j, :cols] = src[row(p, j), :cols] for j < n_rows, 16-byte vectors.

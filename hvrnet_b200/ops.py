@@ -435,7 +435,7 @@ def window_rois(props, counts, perm, V, T, key_dim, n_segs=None):
     dev = props.device
     rois = torch.empty((V * Npad, 5), dtype=torch.float32, device=dev)
     rois_key = torch.empty((V * P, 5), dtype=torch.float32, device=dev)
-    seg = torch.zeros((V, n_segs), dtype=torch.int32, device=dev)
+    seg = torch.empty((V, n_segs), dtype=torch.int32, device=dev)      # entries >= T are zeroed by the kernel
     kc = torch.empty(V, dtype=torch.int32, device=dev)
     assert props.is_contiguous() and counts.dtype == torch.int32 and (perm is None or perm.dtype == torch.int64)
     check(_lib.lib().hvr_window_rois(_p(props), _p(counts), _p(perm), V, T, P, key_dim, Npad, _p(rois), _p(rois_key),

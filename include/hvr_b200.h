@@ -333,7 +333,7 @@ int hvr_relation_fwd(const HvrRelationWeights* w, const hvr_bf16* x_hi, const hv
  *   rois       [V, Npad, 5]  (slot, x1, y1, x2, y2) for RoIAlign, rows t*P + j; rows >= T*P are zero
  *   rois_key   [V*P, 5]      (0, x1, y1, x2, y2) of the key frames (bbox2roi([props_key]))
  *   seg_counts [V, n_segs] int32: entries [0, T) = proposal count of every window frame (the key mask of the
- *                            relation stages); entries >= T (support blocks) are left to hvr_support_index
+ *                            relation stages); entries >= T (support blocks) are set to 0 (hvr_support_index fills them)
  *   key_counts [V] int32     proposal count of the key frames (n_valid of the post-processing)
  * ---------------------------------------------------------------------------------- */
 int hvr_window_rois(const float* props, const int* counts, const int64_t* perm, int V, int T, int P,

@@ -17,7 +17,14 @@ for row in csv.DictReader(lines):
     name = re.sub(r'<unnamed>::|void |at::native::|cub::', '', name)[:44]
     seq.append((name, row['Grid Size'], v))
 starts = [i for i, s in enumerate(seq) if 'im2col' in s[0]]
-a, b = (starts[-2], starts[-1]) if len(starts) >= 2 else (0, len(seq))
+# a full step = trunk + window graph: the widest gap between consecutive stem launches (the window prefill of a
+# timed() call launches trunk graphs only)
+gaps = [(starts[i + 1] - starts[i], i) for i in range(len(starts) - 1)]
+if gaps:
+    _, i = max(gaps, key=lambda g: (g[0], g[1]))
+    a, b = starts[i], starts[i + 1]
+else:
+    a, b = 0, len(seq)
 step = seq[a:b]
 tot = sum(s[2] for s in step)
 print('one step: %d launches, %.1f us summed kernel time' % (len(step), tot))

@@ -146,7 +146,7 @@ def test_abi_library_exports_every_declared_symbol():
     raw = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert getattr(raw, name) is not None
-    assert L.hvr_abi_version() == 2
+    assert L.hvr_abi_version() == 3
     assert L.hvr_strerror(0) == b'ok' and L.hvr_strerror(-3) == b'workspace too small'
     assert L.hvr_nms_workspace_bytes(6000) > 6000 * 94 * 8
     assert ctypes.sizeof(_lib.HvrIGemm) % 8 == 0

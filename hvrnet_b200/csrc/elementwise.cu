@@ -287,7 +287,8 @@ __device__ __forceinline__ int seg_limit(const SegMask& m, const int* lim, int r
   if (lim) return lim[seg];
   return seg * m.slot + m.counts[(size_t)(row / m.rows_per_problem) * m.n_segs + seg];
 }
-__global__ void __launch_bounds__(SM_THREADS) softmax_rows_kernel(const float* __restrict__ S, int cols, long long ld_s,
+template <bool MASKED>
+__global__ void __launch_bounds__(SM_THREADS, 5) softmax_rows_kernel(const float* __restrict__ S, int cols, long long ld_s,
                                                                   __nv_bfloat16* __restrict__ phi,
                                                                   __nv_bfloat16* __restrict__ plo, long long ld_p,
                                                                   int vec_ok, const SegMask mask) {
@@ -296,11 +297,12 @@ __global__ void __launch_bounds__(SM_THREADS) softmax_rows_kernel(const float* _
   __shared__ int s_lim[SM_MAX_SEGS];
   const int row = blockIdx.x, tid = threadIdx.x;
   const int* lim = nullptr;
-  if (mask.counts && mask.n_segs <= SM_MAX_SEGS) {
+  const bool staged = MASKED && mask.n_segs <= SM_MAX_SEGS;
+  auto stage_limits = [&]() {               // per-block limits of this row's window -> shared memory
     if (tid < mask.n_segs) s_lim[tid] = tid * mask.slot + mask.counts[(size_t)(row / mask.rows_per_problem) * mask.n_segs + tid];
     __syncthreads();
     lim = s_lim;
-  }
+  };
   const float* s = S + (size_t)row * ld_s;
   __nv_bfloat16* ph = phi + (size_t)row * ld_p;
   __nv_bfloat16* pl = plo + (size_t)row * ld_p;
@@ -317,7 +319,17 @@ __global__ void __launch_bounds__(SM_THREADS) softmax_rows_kernel(const float* _
         if (c + 1 >= cols) v[j].y = -INFINITY;
         if (c + 2 >= cols) v[j].z = -INFINITY;
         if (c + 3 >= cols) v[j].w = -INFINITY;
-        if (mask.counts) {                   // slot % 4 == 0 on this path: the group lies inside one block
+      } else {
+        v[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
+    }
+    if (MASKED) {
+      // the counts are fetched while the logits above are in flight (the mask does not delay the row's loads)
+      if (staged) stage_limits();
+#pragma unroll
+      for (int j = 0; j < SM_VEC; ++j) {
+        const int c = (tid + j * SM_THREADS) << 2;   // slot % 4 == 0 on this path: the group lies inside one block
+        if (c < cols) {
           const int end = seg_limit(mask, lim, row, c);
           if (c + 3 >= end) {                // only the groups that straddle / lie behind a block's count
             if (c >= end) v[j].x = -INFINITY;
@@ -326,11 +338,10 @@ __global__ void __launch_bounds__(SM_THREADS) softmax_rows_kernel(const float* _
             v[j].w = -INFINITY;
           }
         }
-        mx = fmaxf(mx, fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w)));
-      } else {
-        v[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
       }
     }
+#pragma unroll
+    for (int j = 0; j < SM_VEC; ++j) mx = fmaxf(mx, fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w)));
     mx = block_reduce(mx, true, red, &bcast);
     if (mx == -INFINITY) mx = 0.f;           // every key masked: probabilities 0 (exp(-inf) = 0, inv = 0 below)
     float sum = 0.f;
@@ -368,7 +379,8 @@ __global__ void __launch_bounds__(SM_THREADS) softmax_rows_kernel(const float* _
     return;
   }
   // scalar path: any alignment, any length (re-reads the row)
-  auto live = [&](int c) { return mask.counts == nullptr || c < seg_limit(mask, lim, row, c); };
+  if (staged) stage_limits();
+  auto live = [&](int c) { return !MASKED || c < seg_limit(mask, lim, row, c); };
   float mx = -INFINITY;
   for (int c = tid; c < cols; c += SM_THREADS)
     if (live(c)) mx = fmaxf(mx, __ldg(s + c));
@@ -486,8 +498,9 @@ extern "C" int hvr_softmax_rows_split(const float* S, int rows, int cols, int64_
   if (rows == 0) return HVR_OK;
   const int vec_ok = (ld_s % 4 == 0) && (ld_p % 4 == 0) && ((reinterpret_cast<uintptr_t>(S) & 15u) == 0) &&
                      ((reinterpret_cast<uintptr_t>(p_hi) & 7u) == 0) && ((reinterpret_cast<uintptr_t>(p_lo) & 7u) == 0);
-  softmax_rows_kernel<<<rows, SM_THREADS, 0, ST(stream)>>>(S, cols, ld_s, (__nv_bfloat16*)p_hi,
-                                                           (__nv_bfloat16*)p_lo, ld_p, vec_ok, SegMask{nullptr, 0, 1, 1, 1.0f});
+  softmax_rows_kernel<false><<<rows, SM_THREADS, 0, ST(stream)>>>(S, cols, ld_s, (__nv_bfloat16*)p_hi,
+                                                                  (__nv_bfloat16*)p_lo, ld_p, vec_ok,
+                                                                  SegMask{nullptr, 0, 1, 1, 1.0f});
   HVR_LAUNCHED();
   return HVR_OK;
 }
@@ -500,9 +513,9 @@ extern "C" int hvr_softmax_rows_split_masked(const float* S, int rows, int cols,
   const int vec_ok = (ld_s % 4 == 0) && (ld_p % 4 == 0) && (slot % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(S) & 15u) == 0) &&
                      ((reinterpret_cast<uintptr_t>(p_hi) & 7u) == 0) && ((reinterpret_cast<uintptr_t>(p_lo) & 7u) == 0);
-  softmax_rows_kernel<<<rows, SM_THREADS, 0, ST(stream)>>>(S, cols, ld_s, (__nv_bfloat16*)p_hi, (__nv_bfloat16*)p_lo,
-                                                           ld_p, vec_ok,
-                                                           SegMask{seg_counts, n_segs, slot, rows_per_problem, 1.0f / (float)slot});
+  softmax_rows_kernel<true><<<rows, SM_THREADS, 0, ST(stream)>>>(
+      S, cols, ld_s, (__nv_bfloat16*)p_hi, (__nv_bfloat16*)p_lo, ld_p, vec_ok,
+      SegMask{seg_counts, n_segs, slot, rows_per_problem, 1.0f / (float)slot});
   HVR_LAUNCHED();
   return HVR_OK;
 }

@@ -201,9 +201,8 @@ __global__ void __launch_bounds__(256, SN2_MIN_CTAS) roi_align_sn2_kernel(
 // walks the RoI's rows top to bottom and writes its ph outputs.  All branches depend on the RoI only (rows)
 // or on q only (warp-uniform when C % 128 == 0).  Explicit fmaf: independent of this file's -fmad=false.
 // The walk of roi_align_sep.cuh::roi_column_sep_sn2 specialised for the device: the number of merged column taps NC
-// (1..4, uniform per warp) and the output height PH are compile-time, so a row interpolation is NC loads + 4*NC
-// multiply-adds of straight-line code on pre-added 64-bit column pointers and the sample loop is unrolled (row taps
-// at immediate shared-memory offsets).  ncu of the first version (profiles/r02e_roi_align_ncu_summary.txt): the
+// (1..4, uniform per warp) is compile-time, so a row interpolation is NC loads + 4*NC multiply-adds of straight-line
+// code on pre-added 64-bit column pointers; split stores are packed.  ncu of the first version (profiles/r02e_roi_align_ncu_summary.txt): the
 // kernel is instruction-issue bound - 1867 warp instructions per warp and RoI of which 289 are the multiply-adds -
 // not memory bound, so the instruction count is what this version attacks.  Same operations in the same order as
 // the generic core (the slab kernel, which still runs the core, is its bit-for-bit twin in the tests).
@@ -243,42 +242,44 @@ __device__ __forceinline__ void store_bin_packed(const float4& a, float* __restr
   }
 }
 
-template <int NC, int PH>
-__device__ __forceinline__ void roi_column_walk(const RowTap* __restrict__ rows, const char* const (&pc)[4],
+template <int NC>
+__device__ __forceinline__ void roi_column_walk(const RowTap* __restrict__ rows, int ph, const char* const (&pc)[4],
                                                 const float (&w)[4], float* o_f32, __nv_bfloat16* o_hi,
                                                 __nv_bfloat16* o_lo, size_t step) {
   uint32_t ca = kRowInvalid, cb = kRowInvalid;
   float4 ta = make_float4(0.f, 0.f, 0.f, 0.f), tb = ta;
-#pragma unroll
-  for (int p = 0; p < PH; ++p) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int iy = 0; iy < 2; ++iy) {
-      const RowTap r = rows[p * 2 + iy];
-      if (r.o0 != kRowInvalid) {
-        if (r.o0 == cb) { ta = tb; ca = cb; }
-        else if (r.o0 != ca) { ta = row_interp_nc<NC>(pc, w, r.o0); ca = r.o0; }
-        acc.x = fmaf(r.w0, ta.x, acc.x); acc.y = fmaf(r.w0, ta.y, acc.y);
-        acc.z = fmaf(r.w0, ta.z, acc.z); acc.w = fmaf(r.w0, ta.w, acc.w);
-        if (r.w1 != 0.f) {
-          if (r.o1 != ca) {
-            if (r.o1 != cb) { tb = row_interp_nc<NC>(pc, w, r.o1); cb = r.o1; }
-            acc.x = fmaf(r.w1, tb.x, acc.x); acc.y = fmaf(r.w1, tb.y, acc.y);
-            acc.z = fmaf(r.w1, tb.z, acc.z); acc.w = fmaf(r.w1, tb.w, acc.w);
-          } else {
-            acc.x = fmaf(r.w1, ta.x, acc.x); acc.y = fmaf(r.w1, ta.y, acc.y);
-            acc.z = fmaf(r.w1, ta.z, acc.z); acc.w = fmaf(r.w1, ta.w, acc.w);
-          }
+  float4 acc = ta;
+  // NOT unrolled: four NC variants of a fully unrolled 14-sample walk are ~100 KB of code, and the warps of a CTA run
+  // different variants - the instruction cache (32 KB) thrashed (measured: -33 % instructions gave only -11 % time)
+#pragma unroll 1
+  for (int s = 0; s < 2 * ph; ++s) {
+    const RowTap r = rows[s];
+    if (r.o0 != kRowInvalid) {
+      if (r.o0 == cb) { ta = tb; ca = cb; }
+      else if (r.o0 != ca) { ta = row_interp_nc<NC>(pc, w, r.o0); ca = r.o0; }
+      acc.x = fmaf(r.w0, ta.x, acc.x); acc.y = fmaf(r.w0, ta.y, acc.y);
+      acc.z = fmaf(r.w0, ta.z, acc.z); acc.w = fmaf(r.w0, ta.w, acc.w);
+      if (r.w1 != 0.f) {
+        if (r.o1 != ca) {
+          if (r.o1 != cb) { tb = row_interp_nc<NC>(pc, w, r.o1); cb = r.o1; }
+          acc.x = fmaf(r.w1, tb.x, acc.x); acc.y = fmaf(r.w1, tb.y, acc.y);
+          acc.z = fmaf(r.w1, tb.z, acc.z); acc.w = fmaf(r.w1, tb.w, acc.w);
+        } else {
+          acc.x = fmaf(r.w1, ta.x, acc.x); acc.y = fmaf(r.w1, ta.y, acc.y);
+          acc.z = fmaf(r.w1, ta.z, acc.z); acc.w = fmaf(r.w1, ta.w, acc.w);
         }
       }
     }
-    store_bin_packed(acc, o_f32 ? o_f32 + p * step : nullptr, o_hi ? o_hi + p * step : nullptr,
-                     o_hi ? o_lo + p * step : nullptr);
+    if (s & 1) {                                     // second sample of the bin: emit, next bin
+      store_bin_packed(acc, o_f32, o_hi, o_lo);
+      if (o_f32) o_f32 += step;
+      if (o_hi) { o_hi += step; o_lo += step; }
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(448, MINB) roi_align_sep_kernel(
+__device__ __forceinline__ void roi_align_sep_body(
     const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
     float scale, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
     long long ld_split) {
@@ -294,17 +295,17 @@ __global__ void __launch_bounds__(448, MINB) roi_align_sep_kernel(
   const size_t o_f32 = ((size_t)roi * ph * pw + q) * C + c4 * 4;
   const size_t o_split = (size_t)roi * ld_split + (size_t)q * C + c4 * 4;
   const size_t step = (size_t)pw * C;
-  if (ph == 7 && ct.n >= 1) {
+  if (ct.n >= 1) {
     const char* const pc[4] = {base + ct.off[0], base + ct.off[1], base + ct.off[2], base + ct.off[3]};
     const float w[4] = {ct.w[0], ct.w[1], ct.w[2], ct.w[3]};
     float* of = out ? out + o_f32 : nullptr;
     __nv_bfloat16* oh = out_hi ? out_hi + o_split : nullptr;
     __nv_bfloat16* ol = out_hi ? out_lo + o_split : nullptr;
     switch (ct.n) {
-      case 1: roi_column_walk<1, 7>(rows, pc, w, of, oh, ol, step); break;
-      case 2: roi_column_walk<2, 7>(rows, pc, w, of, oh, ol, step); break;
-      case 3: roi_column_walk<3, 7>(rows, pc, w, of, oh, ol, step); break;
-      default: roi_column_walk<4, 7>(rows, pc, w, of, oh, ol, step); break;
+      case 1: roi_column_walk<1>(rows, ph, pc, w, of, oh, ol, step); break;
+      case 2: roi_column_walk<2>(rows, ph, pc, w, of, oh, ol, step); break;
+      case 3: roi_column_walk<3>(rows, ph, pc, w, of, oh, ol, step); break;
+      default: roi_column_walk<4>(rows, ph, pc, w, of, oh, ol, step); break;
     }
     return;
   }
@@ -312,6 +313,21 @@ __global__ void __launch_bounds__(448, MINB) roi_align_sep_kernel(
   roi_column_sep_sn2(rows, ph, ct, ld,
                      [&](int p, const float4& v) { store_bin(v, out, out_hi, out_lo, o_f32 + p * step, o_split + p * step); },
                      nullptr);
+}
+
+// MINB = 2: 63 registers, two CTAs (28 warps) per SM.  MINB = 3: capped at 48 registers for three CTAs (42 warps) per SM
+// (test hook hvr_debug_roi_variant(3); the kernel is bound by exposed L2 latency once the instruction count is down).
+__global__ void __launch_bounds__(448, 2) roi_align_sep_kernel(
+    const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
+    float scale, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+    long long ld_split) {
+  roi_align_sep_body(feat, rois, n_imgs, C, H, W, ph, pw, scale, out, out_hi, out_lo, ld_split);
+}
+__global__ void __maxnreg__(48) roi_align_sep48_kernel(
+    const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
+    float scale, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+    long long ld_split) {
+  roi_align_sep_body(feat, rois, n_imgs, C, H, W, ph, pw, scale, out, out_hi, out_lo, ld_split);
 }
 
 // Slab variant of the fast path.  ncu of the RoI-per-CTA kernels above (profiles/r01q_*, r02a_*): every variant
@@ -523,11 +539,11 @@ extern "C" int hvr_roi_align_fwd_fast(const float* feat, int feat_nhwc, const fl
   }
   const int threads = pw * (C >> 2);
   if (g_sep_minb == 3)
-    roi_align_sep_kernel<3><<<n_rois, threads, 0, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out,
-                                                        (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_split);
+    roi_align_sep48_kernel<<<n_rois, threads, 0, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out,
+                                                       (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_split);
   else
-    roi_align_sep_kernel<2><<<n_rois, threads, 0, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out,
-                                                        (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_split);
+    roi_align_sep_kernel<<<n_rois, threads, 0, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out,
+                                                     (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_split);
   HVR_LAUNCHED();
   return HVR_OK;
 }

@@ -85,6 +85,8 @@ def stage(kind):
     _, S = bmm_s()
     sm = lambda: ops.softmax_rows_split(S, N, ld_p=Npad, seg_counts=seg, slot=P, rows_per_problem=nq)
     tot['sm'] = row('row softmax -> split probabilities', best_us(sm), 0.0, Mq * N * 4.0 + Mq * Npad * sp)
+    row('  (the same without the key mask)', best_us(lambda: ops.softmax_rows_split(S, N, ld_p=Npad)), 0.0,
+        Mq * N * 4.0 + Mq * Npad * sp)
     Pm = sm()
     tot['pv'] = row('O = P X (values = un-projected rows)', best_us(lambda: ops.bmm(Pm, XT, V, D, Npad)), 2.0 * Mq * Npad * D,
                     Mq * Npad * sp + V * Npad * D * sp + Mq * D * sp)

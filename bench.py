@@ -712,29 +712,43 @@ def main():
             model, _, w2 = configs.build_workload(wl, dev)
             T2 = w2['t_dim']
             metas2 = [synth.make_img_meta() for _ in range(T2)]
-            model.enable_cuda_graphs(wl != 'faster_rcnn')
+            model.enable_cuda_graphs(True)
             from collections import deque
-            dq = deque(maxlen=T2)
 
-            def one(i):
-                img = devf[i % len(devf)]
-                if wl == 'faster_rcnn':
-                    return model(img=[img], img_meta=[[metas2[0]]], return_loss=False, rescale=True)
-                dq.append(model(img=img, img_meta=[metas2[0]], backbone_feat=True)[0])
-                if len(dq) < T2:
-                    return None
-                return model(x=list(dq), img=None, img_meta=metas2, forward_feat=True, return_loss=False, rescale=True)
-            for i in range(T2 + 3):
-                one(i)
-            torch.cuda.synchronize()
-            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a_.record()
-            for i in range(10):
-                one(T2 + 3 + i)
-            b_.record()
-            torch.cuda.synchronize()
-            others[wl] = {'value': 10 / (a_.elapsed_time(b_) / 1e3), 'unit': 'frames/s', 'videos_per_gpu': 1,
-                          'workload': workload_name(wl, T2)}
+            def run(Vb):
+                """Vb videos per step through the public call surface, device-resident frames; -> key frames / s"""
+                src = devV if Vb > 1 else devf
+                dqs2 = [deque(maxlen=T2) for _ in range(Vb)]
+
+                def one(i):
+                    img = src[i % len(src)]
+                    if wl == 'faster_rcnn':
+                        if Vb == 1:
+                            return model(img=[img], img_meta=[[metas2[0]]], return_loss=False, rescale=True)
+                        return model.simple_test_batch(img, [metas2[0]], rescale=True)
+                    c4 = model(img=img, img_meta=[metas2[0]] * Vb, backbone_feat=True)[0]
+                    for v_, t_ in enumerate(GraphRunner.per_frame(c4)):
+                        dqs2[v_].append(t_)
+                    if len(dqs2[0]) < T2:
+                        return None
+                    if Vb == 1:
+                        return model(x=list(dqs2[0]), img=None, img_meta=metas2, forward_feat=True, return_loss=False,
+                                     rescale=True)
+                    return model.forward_feat_batch([list(d) for d in dqs2], metas2, rescale=True)
+                for i in range(T2 + 3):
+                    one(i)
+                torch.cuda.synchronize()
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record()
+                for i in range(10):
+                    one(T2 + 3 + i)
+                b_.record()
+                torch.cuda.synchronize()
+                return Vb * 10 / (a_.elapsed_time(b_) / 1e3)
+            one_v, batched = run(1), run(V)
+            others[wl] = {'value': one_v, 'unit': 'frames/s', 'videos_per_gpu': 1, 'workload': workload_name(wl, T2),
+                          'batched': {'value': batched, 'unit': 'frames/s', 'videos_per_gpu': V,
+                                      'call': 'simple_test_batch' if wl == 'faster_rcnn' else 'forward_feat_batch'}}
         line['other_workloads'] = others
         model = None
     if streaming is not None:

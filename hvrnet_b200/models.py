@@ -646,9 +646,26 @@ class TwoStageDetector(nn.Module):
 class FasterRCNN(TwoStageDetector):
     """detectors/faster_rcnn.py + two_stage.py:280-299 + test_mixins.py:9-13,40-69 (config 1)."""
 
+    key_dim = 0          # a "window" of one frame whose key frame is itself (runtime.GraphRunner.detect)
+
     def simple_test(self, img, img_meta, proposals=None, rescale=False):
         c4 = self.extract_feat(img)[0]._hvr_split
+        if self._runner is not None and proposals is None:
+            d, l = self._runner.detect([[c4]], img_meta, rescale)[0][0]
+            return bbox2result(d, l, self.bbox_head.num_classes)
         return self._detect(c4, img_meta, 1, 1, 0, rescale, proposals=proposals)[0][0]
+
+    def simple_test_batch(self, img, img_meta, rescale=False):
+        """Throughput extension (the reference's test loop feeds one image per call, two_stage.py:280-299): V images
+        [V,3,H,W] of the same shape in one call -> list of V simple_test results (per image the same arithmetic);
+        with CUDA graphs enabled: one trunk graph + one graph for everything after it."""
+        c4 = self.extract_feat(img)[0]
+        V = c4.shape[0]
+        if self._runner is not None:
+            from .runtime import GraphRunner
+            outs = self._runner.detect([[t._hvr_split] for t in GraphRunner.per_frame(c4)], img_meta, rescale)
+            return [bbox2result(out[0][0], out[0][1], self.bbox_head.num_classes) for out in outs]
+        return [r[0] for r in self._detect(c4._hvr_split, img_meta, V, 1, 0, rescale)]
 
 
 class _WindowRCNN(TwoStageDetector):

@@ -21,7 +21,9 @@ starts = [i for i, s in enumerate(seq) if 'im2col' in s[0]]
 # timed() call launches trunk graphs only)
 gaps = [(starts[i + 1] - starts[i], i) for i in range(len(starts) - 1)]
 if gaps:
-    _, i = max(gaps, key=lambda g: (g[0], g[1]))
+    big = [g for g in gaps if g[0] > 0.75 * max(gaps)[0]]
+    common = collections.Counter(g[0] for g in big).most_common(1)[0][0]     # a steady-state step, not a leg boundary
+    i = [g[1] for g in big if g[0] == common][-1]
     a, b = starts[i], starts[i + 1]
 else:
     a, b = 0, len(seq)

@@ -198,6 +198,22 @@ def test_faster_rcnn_simple_test(cuda):
     assert len(res) == 30
     hit, tot = _match(res, ref, iou_thr=0.99, score_tol=1e-3)
     assert tot == 0 or hit / tot >= 0.96, (hit, tot)
+    # the same image through the CUDA-graph runner, and batched with a second image: identical bits per image
+    import numpy as np
+    img2 = synth.make_frames(1, seed=4)
+    res2 = m(img=[img2.to(cuda)], img_meta=[[meta]], return_loss=False, rescale=False)
+    both = torch.cat([img, img2]).to(cuda)
+    outs = [m.simple_test_batch(both, [meta], rescale=False)]
+    m.enable_cuda_graphs(True)
+    try:
+        g1 = m(img=[img.to(cuda)], img_meta=[[meta]], return_loss=False, rescale=False)
+        outs.append(m.simple_test_batch(both, [meta], rescale=False))
+    finally:
+        m.enable_cuda_graphs(False)
+    for c in range(30):
+        assert np.array_equal(g1[c], res[c])
+        for o in outs:
+            assert np.array_equal(o[0][c], res[c]) and np.array_equal(o[1][c], res2[c])
 
 
 def test_cuda_graph_runner_matches_eager(world):

@@ -185,6 +185,15 @@ class GraphRunner:
             outs.append(t)
         return outs
 
+    def reset_rings(self):
+        """Forget which frames the window buffers hold: every frame of the next call is copied again.  WindowRing
+        recognises a frame by tensor identity + torch's version counter, which in-place torch ops bump; a caller that
+        rewrites a C4 tensor's memory behind torch's back (a raw-pointer kernel, cudaMemcpy through data_ptr) must call
+        this (or hand in a new tensor), otherwise the stale copy in the ring would be used."""
+        for c in self._window.values():
+            c.ring = WindowRing(c.ring.V, c.ring.T)
+            c.perm_host = None
+
     # ------------------------------------------------------------------ window(s)
     def _window_key(self, kind, windows, img_meta, rescale, extra=()):
         from .window import scale_of

@@ -710,3 +710,48 @@ def test_intervideo_graphs_equal_eager_world1(world):
                 m.enable_cuda_graphs(False)
         finally:
             m.test_cfg = old
+
+
+def test_graphs_follow_weight_changes_and_raw_writes(cuda):
+    """Captured graphs hold raw pointers into the packed weights and into the ring copy of the window.
+    (1) load_state_dict after enable_cuda_graphs(): the runner notices (models._Packed bumps a version), drops its
+        captures and the next call equals the eager path on the NEW weights (round-1 advisor finding: stale replay);
+    (2) a C4 tensor rewritten behind torch's back (raw-pointer write, version counter untouched) is the documented limit
+        of the ring's identity check: after GraphRunner.reset_rings() the new contents are used."""
+    import numpy as np
+    from hvrnet_b200 import _lib, configs, synth
+    m, sd, w = configs.build_workload('selsa', cuda)
+    frames = synth.make_frames(3, seed=8).to(cuda)
+    metas = [synth.make_img_meta() for _ in range(3)]
+
+    def run():
+        c4 = [m(img=frames[i:i + 1], img_meta=[metas[i]], backbone_feat=True)[0] for i in range(3)]
+        return c4, m(x=c4, img=None, img_meta=metas, forward_feat=True, return_loss=False, rescale=True)
+    m.enable_cuda_graphs(True)
+    try:
+        _, a = run()
+        sd2 = synth.make_state_dict('selsa', seed=1)
+        m.load_state_dict(sd2, strict=False)
+        c4g, b = run()
+        r0 = m._runner.replayed_launches
+        # (2) overwrite frame 0's C4 split through its raw pointer with frame 2's (no version bump)
+        src, dst = c4g[2]._hvr_split, c4g[0]._hvr_split
+        v0 = dst.hi._version
+        dst.hi.data.copy_(src.hi)           # `.data` has its own version counter: the ring cannot see this write
+        dst.lo.data.copy_(src.lo)
+        assert dst.hi._version == v0
+        m._runner.reset_rings()
+        c = m(x=c4g, img=None, img_meta=metas, forward_feat=True, return_loss=False, rescale=True)
+        assert m._runner.replayed_launches > r0
+    finally:
+        m.enable_cuda_graphs(False)
+    _, b_eager = run()
+    c4e = [m(img=frames[i:i + 1], img_meta=[metas[i]], backbone_feat=True)[0] for i in (2, 1, 2)]
+    c_eager = m(x=c4e, img=None, img_meta=metas, forward_feat=True, return_loss=False, rescale=True)
+    differs = False
+    for cl in range(30):
+        assert np.array_equal(b[0][cl], b_eager[0][cl])                # new weights, not the captured old ones
+        assert np.array_equal(c[0][cl], c_eager[0][cl])                # the rewritten frame, not the ring's stale copy
+        differs = differs or not np.array_equal(a[0][cl], b[0][cl])
+    assert differs                                                      # the weight change does change the result
+    del _lib

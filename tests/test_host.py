@@ -441,7 +441,13 @@ def test_window_schedule_matches_trace_of_reference_loop():
     forward_feat call (which frames, in which order) and where each result is filed, across consecutive
     videos sharing one np.random stream: video_shuffle=True (the config's mode), windows 3 / 5 / 15 / 21, videos
     shorter than the window; and the call sequence in temporal order (video_shuffle=False, for which the
-    reference's loop files nothing)."""
+    reference's loop files nothing).
+    Known deviation of the DRIVER built on this schedule (video.detect_video, documented there): windows whose centre
+    is a padding frame (offset -1) or that are shorter than the window are skipped, whereas the reference still calls
+    forward_feat for them and files the result under offset -1, where later frames overwrite it and the evaluation
+    never reads it (tools/hnl_test.py:421-433) - so detect_video makes fewer forward_feat calls than this trace lists,
+    with identical results for every real frame.  The `executed` assertion below pins that the entries detect_video keeps
+    still cover every frame of every video at least as long as the window."""
     import numpy as np
     from hvrnet_b200 import video
     from oracle import window_loop
@@ -452,10 +458,15 @@ def test_window_schedule_matches_trace_of_reference_loop():
             np.random.seed(c['seed'])
             calls, filed, start = [], [None] * sum(c['seg_lens']), 1
             for L in c['seg_lens']:
+                executed = set()
                 for idxs, offs, key in impl(L, c['window'], np.random, c['video_shuffle']):
                     calls.append(idxs)
                     filed[start + key - 1] = idxs                      # hnl_test.py:399-409
                     assert [o for o in offs if o >= 0] == [i for i, o in zip(idxs, offs) if o >= 0]
+                    if key >= 0 and len(idxs) == c['window']:          # what video.detect_video runs
+                        executed.add(key)
+                if L >= c['window']:
+                    assert executed == set(range(L))
                 start += L
             assert calls == c['calls'] and len(calls) == c['n_calls']
             if c['video_shuffle']:

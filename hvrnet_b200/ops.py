@@ -425,12 +425,13 @@ def softmax_rows_split(S, cols, ld_p=None, seg_counts=None, slot=0, rows_per_pro
     return P
 
 
-def window_rois(props, counts, perm, V, T, key_dim, n_segs=None):
+def window_rois(props, counts, perm, V, T, key_dim, n_segs=None, pad=True):
     """props [F,P,5], counts [F] int32 (hvr_rpn_proposals outputs), perm int64 [V*T] or None -> (rois [V*Npad,5],
-    rois_key [V*P,5], seg_counts int32 [V,n_segs], key_counts int32 [V]); see hvr_window_rois."""
+    rois_key [V*P,5], seg_counts int32 [V,n_segs], key_counts int32 [V]); see hvr_window_rois.  pad=False: Npad = T*P
+    (heads without attention need no 64-row alignment of a video's block)."""
     _need_cuda(props, counts)
     P = props.shape[1]
-    Npad = round_up(T * P, 64)
+    Npad = round_up(T * P, 64) if pad else T * P
     n_segs = n_segs or T
     dev = props.device
     rois = torch.empty((V * Npad, 5), dtype=torch.float32, device=dev)

@@ -17,6 +17,14 @@ import torch
 from . import engine, ops
 
 
+import os
+
+# experiment switches (bench): HVR_FORK_POST=0 runs the detection post-processing on the main stream instead of a forked
+# branch under stages 3-4; HVR_FORK_PROPOSALS=0 does the same for proposal generation (under the C5 convolutions)
+FORK_POST = os.environ.get('HVR_FORK_POST', '1') != '0'
+FORK_PROPOSALS = os.environ.get('HVR_FORK_PROPOSALS', '1') != '0'
+
+
 class FrameStages:
     """Outputs of the per-frame stages of V*T frames (C5, RPN, proposals, RoIAlign)."""
     __slots__ = ('maps', 'props', 'counts', 'c5', 'rois', 'rois_key', 'seg', 'key_counts', 'rows', 'P', 'N', 'Npad',
@@ -57,8 +65,12 @@ def frame_stages(m, c4, img_shape, V, T, key_dim, perm=None, proposals=None, n_s
         main.wait_stream(side)
     fs.P = fs.props.shape[1]
     fs.N = T * fs.P
-    fs.Npad = ops.round_up(fs.N, 64)
-    fs.rois, fs.rois_key, fs.seg, fs.key_counts = ops.window_rois(fs.props, fs.counts, perm, V, T, key_dim, n_segs)
+    # relation heads want every video's block 64-row aligned (X^T operands); the plain fc head (Faster-RCNN, T = 1) reads
+    # its output rows back as V blocks of P rows, so its blocks are not padded
+    pad = m.bbox_head.kind != 'shared_fc'
+    fs.Npad = ops.round_up(fs.N, 64) if pad else fs.N
+    fs.rois, fs.rois_key, fs.seg, fs.key_counts = ops.window_rois(fs.props, fs.counts, perm, V, T, key_dim, n_segs,
+                                                                  pad=pad)
     fs.rows = m.bbox_roi_extractor.roi_layers[0].forward_nhwc_split(fs.c5, fs.rois)
     return fs
 
@@ -122,6 +134,7 @@ def head_outputs(m, fs, key_dim):
     V, P, N, Npad = fs.V, fs.P, fs.N, fs.Npad
     s = key_dim * P
     if head.kind == 'shared_fc':
+        assert fs.T == 1 and fs.Npad == P, 'the fc head post-processes V blocks of P rows'
         return [engine.shared_fc_forward(packed, fs.rows)]
     assert head.nongt_dim >= N, 'window rows exceed sampler_num * t_dim (hrnmp_bbox_head.py:249)'
     mask = engine.KeyMask(fs.seg, P)
@@ -143,7 +156,7 @@ def detect_windows(m, c4, img_meta, V, T, key_dim, rescale, perm=None, proposals
     sf = scale_of(meta)
     main = torch.cuda.current_stream()
     fs = frame_stages(m, c4, meta['img_shape'], V, T, key_dim, perm=perm, proposals=proposals,
-                      side=side[0] if side else None)
+                      side=side[0] if (side and FORK_PROPOSALS) else None)
     head = m.bbox_head
     n_out = 2 if head.kind == 'hrnmp' else 1
     if result is None:
@@ -151,7 +164,7 @@ def detect_windows(m, c4, img_meta, V, T, key_dim, rescale, perm=None, proposals
     forked = []
 
     def post(j, o):
-        st = side[j % 2] if side else None
+        st = side[j % 2] if (side and FORK_POST) else None
         if st is None:
             return post_process(m, fs, o, V, meta['img_shape'], sf, rescale, out=result.outs[j])
         st.wait_stream(main)

@@ -580,7 +580,7 @@ def main():
         if k_:
             hbm_peak, src = v_, 'MEASURED_PEAKS.json ' + k_
         gbs = nbytes / us / 1e3
-        out = {'bound': 'hbm', 'kernel': 'roi_align_sep_kernel (one CTA per RoI, thread = output column x 4 channels, rows of the RoI '
+        out = {'bound': 'hbm', 'kernel': 'roi_align_sep8_kernel (one CTA per RoI, thread = output column x 8 channels, rows of the RoI '
                                          'interpolated once along x with merged column taps, LDG.128 along C, FMA)', 'frames': Tn,
                'rois': Tn * 300, 'us_per_launch': us, 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                'frac': gbs / hbm_peak, 'peak_source': src, 'algorithmic_bytes': nbytes,

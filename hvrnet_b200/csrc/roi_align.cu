@@ -206,24 +206,50 @@ __global__ void __launch_bounds__(256, SN2_MIN_CTAS) roi_align_sn2_kernel(
 // kernel is instruction-issue bound - 1867 warp instructions per warp and RoI of which 289 are the multiply-adds -
 // not memory bound, so the instruction count is what this version attacks.  Same operations in the same order as
 // the generic core (the slab kernel, which still runs the core, is its bit-for-bit twin in the tests).
-template <int NC>
-__device__ __forceinline__ float4 row_interp_nc(const char* const (&pc)[4], const float (&w)[4], uint32_t row_off) {
-  float4 v[NC];
+// VEC = float4 vectors (4 channels each) a thread owns: 1, or 2 (8 adjacent channels - the address arithmetic, the row
+// walk's control flow and the table reads are then paid once per 8 channels instead of once per 4).
+template <int VEC>
+struct Vec { float4 v[VEC]; };
+
+template <int NC, int VEC>
+__device__ __forceinline__ Vec<VEC> row_interp_nc(const char* const (&pc)[4], const float (&w)[4], uint32_t row_off) {
+  float4 v[NC][VEC];
 #pragma unroll
-  for (int k = 0; k < NC; ++k) v[k] = __ldg(reinterpret_cast<const float4*>(pc[k] + row_off));
-  float4 t;
-  if (NC == 4) {
-    t.x = w[3] * v[3].x; t.y = w[3] * v[3].y; t.z = w[3] * v[3].z; t.w = w[3] * v[3].w;
-  } else {
-    t = make_float4(fmaf(w[NC - 1], v[NC - 1].x, 0.f), fmaf(w[NC - 1], v[NC - 1].y, 0.f),
-                    fmaf(w[NC - 1], v[NC - 1].z, 0.f), fmaf(w[NC - 1], v[NC - 1].w, 0.f));
-  }
+  for (int k = 0; k < NC; ++k)
 #pragma unroll
-  for (int k = NC - 2; k >= 0; --k) {
-    t.x = fmaf(w[k], v[k].x, t.x); t.y = fmaf(w[k], v[k].y, t.y);
-    t.z = fmaf(w[k], v[k].z, t.z); t.w = fmaf(w[k], v[k].w, t.w);
+    for (int e = 0; e < VEC; ++e) v[k][e] = __ldg(reinterpret_cast<const float4*>(pc[k] + row_off) + e);
+  Vec<VEC> t;
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    if (NC == 4) {
+      t.v[e].x = w[3] * v[3][e].x; t.v[e].y = w[3] * v[3][e].y; t.v[e].z = w[3] * v[3][e].z; t.v[e].w = w[3] * v[3][e].w;
+    } else {
+      t.v[e] = make_float4(fmaf(w[NC - 1], v[NC - 1][e].x, 0.f), fmaf(w[NC - 1], v[NC - 1][e].y, 0.f),
+                           fmaf(w[NC - 1], v[NC - 1][e].z, 0.f), fmaf(w[NC - 1], v[NC - 1][e].w, 0.f));
+    }
+#pragma unroll
+    for (int k = NC - 2; k >= 0; --k) {
+      t.v[e].x = fmaf(w[k], v[k][e].x, t.v[e].x); t.v[e].y = fmaf(w[k], v[k][e].y, t.v[e].y);
+      t.v[e].z = fmaf(w[k], v[k][e].z, t.v[e].z); t.v[e].w = fmaf(w[k], v[k][e].w, t.v[e].w);
+    }
   }
   return t;
+}
+
+template <int VEC>
+__device__ __forceinline__ void vec_fma(Vec<VEC>& a, float w, const Vec<VEC>& t) {
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    a.v[e].x = fmaf(w, t.v[e].x, a.v[e].x); a.v[e].y = fmaf(w, t.v[e].y, a.v[e].y);
+    a.v[e].z = fmaf(w, t.v[e].z, a.v[e].z); a.v[e].w = fmaf(w, t.v[e].w, a.v[e].w);
+  }
+}
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> vec_zero() {
+  Vec<VEC> z;
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) z.v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  return z;
 }
 
 // split + store of one output vector: packed conversions (the same round-to-nearest-even as split2)
@@ -242,43 +268,42 @@ __device__ __forceinline__ void store_bin_packed(const float4& a, float* __restr
   }
 }
 
-template <int NC>
+template <int NC, int VEC>
 __device__ __forceinline__ void roi_column_walk(const RowTap* __restrict__ rows, int ph, const char* const (&pc)[4],
                                                 const float (&w)[4], float* o_f32, __nv_bfloat16* o_hi,
                                                 __nv_bfloat16* o_lo, size_t step) {
   uint32_t ca = kRowInvalid, cb = kRowInvalid;
-  float4 ta = make_float4(0.f, 0.f, 0.f, 0.f), tb = ta;
-  float4 acc = ta;
-  // NOT unrolled: four NC variants of a fully unrolled 14-sample walk are ~100 KB of code, and the warps of a CTA run
-  // different variants - the instruction cache (32 KB) thrashed (measured: -33 % instructions gave only -11 % time)
+  Vec<VEC> ta = vec_zero<VEC>(), tb = ta, acc = ta;
+  // NOT unrolled: four NC variants of a fully unrolled 14-sample walk are ~100 KB of code
 #pragma unroll 1
   for (int s = 0; s < 2 * ph; ++s) {
     const RowTap r = rows[s];
     if (r.o0 != kRowInvalid) {
       if (r.o0 == cb) { ta = tb; ca = cb; }
-      else if (r.o0 != ca) { ta = row_interp_nc<NC>(pc, w, r.o0); ca = r.o0; }
-      acc.x = fmaf(r.w0, ta.x, acc.x); acc.y = fmaf(r.w0, ta.y, acc.y);
-      acc.z = fmaf(r.w0, ta.z, acc.z); acc.w = fmaf(r.w0, ta.w, acc.w);
+      else if (r.o0 != ca) { ta = row_interp_nc<NC, VEC>(pc, w, r.o0); ca = r.o0; }
+      vec_fma<VEC>(acc, r.w0, ta);
       if (r.w1 != 0.f) {
         if (r.o1 != ca) {
-          if (r.o1 != cb) { tb = row_interp_nc<NC>(pc, w, r.o1); cb = r.o1; }
-          acc.x = fmaf(r.w1, tb.x, acc.x); acc.y = fmaf(r.w1, tb.y, acc.y);
-          acc.z = fmaf(r.w1, tb.z, acc.z); acc.w = fmaf(r.w1, tb.w, acc.w);
+          if (r.o1 != cb) { tb = row_interp_nc<NC, VEC>(pc, w, r.o1); cb = r.o1; }
+          vec_fma<VEC>(acc, r.w1, tb);
         } else {
-          acc.x = fmaf(r.w1, ta.x, acc.x); acc.y = fmaf(r.w1, ta.y, acc.y);
-          acc.z = fmaf(r.w1, ta.z, acc.z); acc.w = fmaf(r.w1, ta.w, acc.w);
+          vec_fma<VEC>(acc, r.w1, ta);
         }
       }
     }
     if (s & 1) {                                     // second sample of the bin: emit, next bin
-      store_bin_packed(acc, o_f32, o_hi, o_lo);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e)
+        store_bin_packed(acc.v[e], o_f32 ? o_f32 + 4 * e : nullptr, o_hi ? o_hi + 4 * e : nullptr,
+                         o_hi ? o_lo + 4 * e : nullptr);
       if (o_f32) o_f32 += step;
       if (o_hi) { o_hi += step; o_lo += step; }
-      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      acc = vec_zero<VEC>();
     }
   }
 }
 
+template <int VEC>
 __device__ __forceinline__ void roi_align_sep_body(
     const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
     float scale, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
@@ -287,8 +312,8 @@ __device__ __forceinline__ void roi_align_sep_body(
   const int roi = blockIdx.x;
   const RoiGeom g = roi_geom(rois + (size_t)roi * 5, scale, ph, pw, n_imgs);
   if ((int)threadIdx.x < 2 * ph) rows[threadIdx.x] = row_tap_sn2(g.sh, g.bh, threadIdx.x, H, (uint32_t)(W * C) * 4u);
-  const int cg = C >> 2;
-  const int q = threadIdx.x / cg, c4 = threadIdx.x - q * cg;
+  const int cg = C / (4 * VEC);                       // channel groups of 4 * VEC channels
+  const int q = threadIdx.x / cg, c4 = (threadIdx.x - q * cg) * VEC;
   const ColTaps ct = col_taps_sn2(g.sw, g.bw, q, W, (uint32_t)C * 4u);
   __syncthreads();
   const char* base = reinterpret_cast<const char*>(feat + (size_t)g.b * H * W * C + c4 * 4);
@@ -302,17 +327,23 @@ __device__ __forceinline__ void roi_align_sep_body(
     __nv_bfloat16* oh = out_hi ? out_hi + o_split : nullptr;
     __nv_bfloat16* ol = out_hi ? out_lo + o_split : nullptr;
     switch (ct.n) {
-      case 1: roi_column_walk<1>(rows, ph, pc, w, of, oh, ol, step); break;
-      case 2: roi_column_walk<2>(rows, ph, pc, w, of, oh, ol, step); break;
-      case 3: roi_column_walk<3>(rows, ph, pc, w, of, oh, ol, step); break;
-      default: roi_column_walk<4>(rows, ph, pc, w, of, oh, ol, step); break;
+      case 1: roi_column_walk<1, VEC>(rows, ph, pc, w, of, oh, ol, step); break;
+      case 2: roi_column_walk<2, VEC>(rows, ph, pc, w, of, oh, ol, step); break;
+      case 3: roi_column_walk<3, VEC>(rows, ph, pc, w, of, oh, ol, step); break;
+      default: roi_column_walk<4, VEC>(rows, ph, pc, w, of, oh, ol, step); break;
     }
     return;
   }
-  const TapLoad ld{base};
-  roi_column_sep_sn2(rows, ph, ct, ld,
-                     [&](int p, const float4& v) { store_bin(v, out, out_hi, out_lo, o_f32 + p * step, o_split + p * step); },
-                     nullptr);
+  // no column tap at all (every x sample outside the map): zeros, through the generic core
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    const TapLoad ld{base + 16 * e};
+    roi_column_sep_sn2(rows, ph, ct, ld,
+                       [&](int p, const float4& v) {
+                         store_bin(v, out, out_hi, out_lo, o_f32 + 4 * e + p * step, o_split + 4 * e + p * step);
+                       },
+                       nullptr);
+  }
 }
 
 // MINB = 2: 63 registers, two CTAs (28 warps) per SM.  MINB = 3: capped at 48 registers for three CTAs (42 warps) per SM
@@ -321,13 +352,20 @@ __global__ void __launch_bounds__(448, 2) roi_align_sep_kernel(
     const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
     float scale, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
     long long ld_split) {
-  roi_align_sep_body(feat, rois, n_imgs, C, H, W, ph, pw, scale, out, out_hi, out_lo, ld_split);
+  roi_align_sep_body<1>(feat, rois, n_imgs, C, H, W, ph, pw, scale, out, out_hi, out_lo, ld_split);
+}
+// thread = (output column, 8 channels): pw * C/8 <= 224 threads per RoI
+__global__ void __launch_bounds__(224, 3) roi_align_sep8_kernel(
+    const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
+    float scale, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+    long long ld_split) {
+  roi_align_sep_body<2>(feat, rois, n_imgs, C, H, W, ph, pw, scale, out, out_hi, out_lo, ld_split);
 }
 __global__ void __maxnreg__(48) roi_align_sep48_kernel(
     const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
     float scale, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
     long long ld_split) {
-  roi_align_sep_body(feat, rois, n_imgs, C, H, W, ph, pw, scale, out, out_hi, out_lo, ld_split);
+  roi_align_sep_body<1>(feat, rois, n_imgs, C, H, W, ph, pw, scale, out, out_hi, out_lo, ld_split);
 }
 
 // Slab variant of the fast path.  ncu of the RoI-per-CTA kernels above (profiles/r01q_*, r02a_*): every variant
@@ -465,6 +503,7 @@ __global__ void roi_align_generic_kernel(const float* __restrict__ feat, const f
 
 int g_roi_variant = 0;   // test hook (hvr_debug_roi_variant): 0 = heuristic, 1 = always the per-bin kernel
 int g_sep_minb = 2;      // test hook (hvr_debug_roi_variant 2 / 3): resident CTAs per SM the fast kernel is built for
+bool g_sep_vec8 = true;  // test hook (hvr_debug_roi_variant 7 / 8): 8 channels per thread on (default: 835 vs 915 us on the bench launch) / off
 int g_slab = 0;          // test hook (hvr_debug_roi_variant 4 / 5 / 6): 0 = heuristic (= never), 1 = slab kernel whenever it applies, 2 = never
 
 }  // namespace
@@ -472,6 +511,10 @@ int g_slab = 0;          // test hook (hvr_debug_roi_variant 4 / 5 / 6): 0 = heu
 extern "C" int hvr_debug_roi_variant(int v) {
   if (v == 2 || v == 3) {          // occupancy variant of the fast kernel (experiments)
     g_sep_minb = v;
+    return HVR_OK;
+  }
+  if (v == 7 || v == 8) {
+    g_sep_vec8 = v == 7;
     return HVR_OK;
   }
   if (v >= 4 && v <= 6) {          // 4 = heuristic, 5 = slab kernel whenever it applies, 6 = never the slab kernel
@@ -538,6 +581,12 @@ extern "C" int hvr_roi_align_fwd_fast(const float* feat, int feat_nhwc, const fl
     return HVR_OK;
   }
   const int threads = pw * (C >> 2);
+  if (g_sep_vec8 && C % 8 == 0 && pw * (C >> 3) <= 224) {
+    roi_align_sep8_kernel<<<n_rois, pw * (C >> 3), 0, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out,
+                                                           (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_split);
+    HVR_LAUNCHED();
+    return HVR_OK;
+  }
   if (g_sep_minb == 3)
     roi_align_sep48_kernel<<<n_rois, threads, 0, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out,
                                                        (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_split);

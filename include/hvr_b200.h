@@ -169,7 +169,8 @@ int hvr_roi_align_fwd(const float* feat, int feat_nhwc, const float* rois, int n
 /* Test hook: 1 = always the generic per-bin kernel (16 loads per output vector, as the reference),
  * 0 = heuristic (sample_num 2 + out_layout 1 run roi_align_sn2_kernel, which reuses taps held in registers);
  * 2 / 3 = resident CTAs per SM the fast RoI-per-CTA kernel below is compiled for (experiments);
- * 4 / 5 / 6 = fast path launch shape: heuristic / slab kernel whenever it applies / never the slab kernel. */
+ * 4 / 5 / 6 = fast path launch shape: heuristic / slab kernel whenever it applies / never the slab kernel;
+ * 7 / 8 = fast RoI-per-CTA kernel with 8 / 4 channels per thread. */
 int hvr_debug_roi_variant(int v);
 /* Fast arithmetic for the pipeline (feat_nhwc = 1, out_layout = 1, sample_num = 2): the same average of
  * bilinear samples evaluated separably - every map row of the RoI is interpolated once along x with the

@@ -547,14 +547,21 @@ def test_roi_align_fast_variant_vs_strict(cuda, C, out_size):
     ref = cref.roi_align(feat, rois, out_size=out_size, feat_nhwc=True, out_nhwc=True)
     f, r = feat.to(cuda), rois.to(cuda)
     from hvrnet_b200 import _lib
-    assert _lib.lib().hvr_debug_roi_variant(6) == 0                               # the RoI-per-CTA launch shape
+    assert _lib.lib().hvr_debug_roi_variant(6) == 0                               # the RoI-per-CTA launch shape,
+    _lib.lib().hvr_debug_roi_variant(8)                                           # 4 channels per thread
     try:
         o, sp = ops.roi_align(f, r, out_size=out_size, feat_nhwc=True, out_nhwc=True, want_split=True, arithmetic='fast')
+        # 8 channels per thread: the same operations per element -> the same bits
+        _lib.lib().hvr_debug_roi_variant(7)
+        o_8, sp_8 = ops.roi_align(f, r, out_size=out_size, feat_nhwc=True, out_nhwc=True, want_split=True, arithmetic='fast')
+        _lib.lib().hvr_debug_roi_variant(8)
+        assert torch.equal(o_8.view(torch.int32), o.view(torch.int32)) and torch.equal(sp_8.lo.view(torch.int16), sp.lo.view(torch.int16))
         # the slab launch shape (CTA = frame x 16-channel slab, map slab in shared memory): the same separable core,
         # so identical bits wherever it applies (C % 16 == 0, out_size <= 8)
         _lib.lib().hvr_debug_roi_variant(5)
         o_s, sp_s = ops.roi_align(f, r, out_size=out_size, feat_nhwc=True, out_nhwc=True, want_split=True, arithmetic='fast')
     finally:
+        _lib.lib().hvr_debug_roi_variant(7)
         _lib.lib().hvr_debug_roi_variant(4)
     if C == 512:
         # no RoI-per-CTA launch shape (7 * 128 threads > 448): with the slab shape disabled this is the strict kernel;
@@ -573,7 +580,7 @@ def test_roi_align_fast_variant_vs_strict(cuda, C, out_size):
     assert torch.equal(sp.hi.view(torch.int16), sp2.hi.view(torch.int16))
     assert torch.equal(sp.lo.view(torch.int16), sp2.lo.view(torch.int16))
     # split rows only (the pipeline's call) give the same bits
-    _lib.lib().hvr_debug_roi_variant(5 if C == 512 else 6)
+    _lib.lib().hvr_debug_roi_variant(5 if C == 512 else 6)               # (default channel grouping: 8 per thread)
     try:
         _, sp3 = ops.roi_align(f, r, out_size=out_size, feat_nhwc=True, out_nhwc=True, want_split=True, want_f32=False,
                                arithmetic='fast')

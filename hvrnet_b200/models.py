@@ -540,7 +540,11 @@ class TwoStageDetector(nn.Module):
 
     def weights_version(self):
         """Changes whenever a load_state_dict / .to() / _apply touched any packed module."""
-        return tuple(m._hvr_version for m in self.modules() if isinstance(m, _Packed))
+        packed = self.__dict__.get('_hvr_packed_modules')
+        if packed is None:
+            packed = [m for m in self.modules() if isinstance(m, _Packed)]
+            self.__dict__['_hvr_packed_modules'] = packed       # the module tree of a built detector is fixed
+        return tuple(m._hvr_version for m in packed)
 
     def enable_cuda_graphs(self, flag=True, capture=True):
         """Run the trunk and the window stage through captured CUDA graphs (runtime.GraphRunner):

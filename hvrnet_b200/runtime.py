@@ -301,7 +301,9 @@ class GraphRunner:
                 return window.inter_stage_b(m, box['st'], img_meta, rescale, side=c.side)
 
             def fn_c():
-                return window.inter_stage_c(m, box['st'], box['recv'], img_meta, rescale, world, rank, sel=c.sel)
+                # world 1: the "receive buffer" is the send buffer of the state this pass produced (eager re-issue makes a new one)
+                recv = box['recv'] if world > 1 else box['st'].send.unsqueeze(0)
+                return window.inter_stage_c(m, box['st'], recv, img_meta, rescale, world, rank, sel=c.sel)
 
             self._fill(c, windows)
             # warm-up pass of the whole chain (lazy packing, kernel attributes, NCCL communicator), then the captures

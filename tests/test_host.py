@@ -536,3 +536,34 @@ def test_c_host_compiles_against_the_header(tmp_path):
     tests/test_gpu_kernels.py::test_c_host_relation_block.)"""
     exe = _build_c_host(tmp_path)
     assert os.path.exists(exe)
+
+
+def test_result_buffer_layout_and_fixed_blocks():
+    """Host logic of window.py without a GPU: the packed result buffer (one D2H copy per step) round-trips counts, n_dets,
+    dets and labels of every video / head output through typed views of one byte buffer; caller-provided proposal lists
+    become fixed zero-padded blocks with their counts."""
+    from hvrnet_b200 import window
+    V, F, M, n_out = 3, 6, 5, 2
+    rb = window.ResultBuffer(F, V, n_out, M, 'cpu')
+    assert rb.buf.dtype == torch.uint8 and rb.nbytes == rb.buf.numel() and rb.nbytes % 16 == 0
+    rb.counts.copy_(torch.arange(F, dtype=torch.int32) + 7)
+    g = torch.Generator().manual_seed(1)
+    want = []
+    for o, (d, l, k) in enumerate(rb.outs):
+        assert d.shape == (V, M, 5) and l.shape == (V, M) and l.dtype == torch.int64 and k.dtype == torch.int32
+        d.copy_(torch.rand(V, M, 5, generator=g))
+        l.copy_(torch.randint(0, 30, (V, M), generator=g))
+        k.copy_(torch.tensor([M, 0, 2], dtype=torch.int32))
+        want.append((d.clone(), l.clone()))
+    counts, per_video = rb.parse(rb.buf.clone())
+    assert counts == list(range(7, 7 + F))
+    for v, kk in enumerate([M, 0, 2]):
+        assert len(per_video[v]) == n_out
+        for o in range(n_out):
+            d, l = per_video[v][o]
+            assert d.shape == (kk, 5) and torch.equal(d, want[o][0][v, :kk]) and torch.equal(l, want[o][1][v, :kk])
+    props, cnt = window.props_from_lists([torch.ones(3, 5), torch.zeros(0, 5), torch.full((6, 4), 2.0)], 'cpu')
+    assert props.shape == (3, 8, 5) and cnt.tolist() == [3, 0, 6] and cnt.dtype == torch.int32
+    assert bool((props[0, :3] == 1).all()) and not bool(props[0, 3:].any()) and not bool(props[1].any())
+    assert bool((props[2, :6, :4] == 2).all()) and not bool(props[2, :, 4].any())
+    assert window.ring_selection(1, 2, 2, 3, 'cpu').tolist() == [[3, 0, 1], [0, 1, 2]]

@@ -132,7 +132,7 @@ def test_forward_feat_end_to_end(world):
         ref, raux = R.hnmb_forward_feat(sd, [c for c in world['c4_ref'].split(1)], world['metas'], 1,
                                         roi_align_fn=cref.roi_align, return_aux=True)
     # proposals: same per-frame counts; the index lists are compared exactly in test_index_parity (replay) - here the
-    # free-running sets must overlap at the measured rate (profiles/r02a_parity_report.txt: >= 0.98 per frame)
+    # free-running sets must overlap at the measured rate (profiles/r02_parity_report.txt: >= 0.98 per frame)
     for t in range(3):
         a = aux['proposals'][t, :aux['counts'][t]].cpu()
         b = raux['proposals'][t]
@@ -163,7 +163,7 @@ def test_index_parity_full_size(cuda, workload, seed):
           bit for bit, in order, for every frame and every head output: the CUDA index logic is exact;
       (B) FREE-RUNNING - against the oracle on its own tensors, every first divergence is a near-tie: a margin below
           (4x) the measured arithmetic error of the compared quantity, which is itself inside the 1e-3 tolerance;
-          set overlaps at the rates measured in profiles/r02a_parity_report.txt (proposal anchors >= 0.967 per frame,
+          set overlaps at the rates measured in profiles/r02_parity_report.txt (proposal anchors >= 0.967 per frame,
           mean 0.998; detections >= 0.967)."""
     from hvrnet_b200 import configs, synth
     from tests import parity_tools as PT

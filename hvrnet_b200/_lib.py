@@ -94,6 +94,10 @@ SIGNATURES = {
     'hvr_pack_conv_bn': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
                                  c_vp]),
     'hvr_pack_linear': (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'hvr_linear_fwd': (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_i64, c_int, c_f32,
+                               c_vp, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    'hvr_conv_fwd': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp,
+                             c_int, c_vp, c_vp, c_vp, c_vp]),
     'hvr_relation_workspace_bytes': (c_sz, [c_int, c_int, c_int]),
     'hvr_relation_fwd': (c_int, [ctypes.POINTER(HvrRelationWeights), c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_int,
                                  c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),

@@ -102,6 +102,71 @@ extern "C" int hvr_pack_linear(const float* w_host, const float* bias_host, int 
   return upload_split(W, rows_pad, cols_pad, w_hi, w_lo, st);
 }
 
+// ------------------------------------------------------------------------------------------------
+// One nn.Linear / nn.Conv2d (+ folded BN, + residual, + ReLU) on packed weights: the descriptor filling of
+// engine.lin / engine.conv (tile choice, tap offsets, strided views) behind plain arguments.
+// ------------------------------------------------------------------------------------------------
+extern "C" int hvr_linear_fwd(const hvr_bf16* x_hi, const hvr_bf16* x_lo, int rows, int k, int64_t ld_x,
+                              const hvr_bf16* w_hi, const hvr_bf16* w_lo, const float* bias, int n,
+                              const hvr_bf16* res_hi, const hvr_bf16* res_lo, int64_t ld_res, int relu, float alpha,
+                              hvr_bf16* out_hi, hvr_bf16* out_lo, int64_t ld_out, float* out_f32, int64_t ld_f32,
+                              void* stream) {
+  if (!x_hi || !x_lo || !w_hi || !w_lo || rows < 1 || k < 8 || n < 1) return HVR_ERR_ARG;
+  HvrIGemm g;
+  fill_linear(g, x_hi, x_lo, rows, k, ld_x, w_hi, w_lo, n, rup(k, 64));
+  g.alpha = alpha;
+  g.bias = bias;
+  g.res_hi = res_hi; g.res_lo = res_lo; g.ld_res = ld_res;
+  g.relu = relu;
+  g.out_hi = out_hi; g.out_lo = out_lo; g.ld_out = ld_out;
+  g.out_f32 = out_f32; g.ld_f32 = ld_f32;
+  return hvr_igemm(&g, stream);
+}
+
+extern "C" int hvr_conv_fwd(const hvr_bf16* x_hi, const hvr_bf16* x_lo, int batch, int h, int w, int cin,
+                            const hvr_bf16* w_hi, const hvr_bf16* w_lo, const float* bias, int cout, int ksize,
+                            int dilation, int stride, const hvr_bf16* res_hi, const hvr_bf16* res_lo, int relu,
+                            hvr_bf16* out_hi, hvr_bf16* out_lo, float* out_f32, void* stream) {
+  if (!x_hi || !x_lo || !w_hi || !w_lo || batch < 1 || h < 1 || w < 1 || cin < 8 || cout < 1) return HVR_ERR_ARG;
+  if ((ksize != 1 && ksize != 3) || dilation < 1 || stride < 1) return HVR_ERR_ARG;
+  if (stride != 1 && ksize != 1) return HVR_ERR_UNSUPPORTED;   // strided convs on the path are 1x1 (caffe-style bottleneck)
+  if (!out_hi && !out_f32) return HVR_ERR_ARG;
+  const int ho = (h - 1) / stride + 1, wo = (w - 1) / stride + 1;
+  const int64_t npad = rup(cout, 64);                           // physical rows of the packed weights = output row pitch
+  HvrIGemm g;
+  memset(&g, 0, sizeof(g));
+  g.a_hi = x_hi; g.a_lo = x_lo;
+  g.a_c = cin; g.a_w = wo; g.a_h = ho; g.a_b = batch;          // strided view of the NHWC input: every stride-th pixel
+  g.a_stride_w = (int64_t)cin * stride;
+  g.a_stride_h = (int64_t)w * cin * stride;
+  g.a_stride_b = (int64_t)h * w * cin;
+  if (stride == 1) { g.a_w = w; g.a_h = h; }
+  const int r = ksize / 2;
+  g.ntaps = ksize * ksize;
+  for (int t = 0; t < ksize; ++t)
+    for (int s2 = 0; s2 < ksize; ++s2) {                        // (dx, dy), row-major over the filter (engine._taps)
+      g.tap_dx[t * ksize + s2] = (s2 - r) * dilation;
+      g.tap_dy[t * ksize + s2] = (t - r) * dilation;
+    }
+  g.out_w = wo; g.out_h = ho; g.batch = batch;
+  // ops.pick_tile: the 128-pixel tile shape that wastes the fewest rows
+  long long best = -1;
+  for (int tw = 128; tw >= 8; tw >>= 1) {
+    const int th = 128 / tw;
+    const long long waste = (long long)((wo + tw - 1) / tw * tw) * ((ho + th - 1) / th * th);
+    if (best < 0 || waste < best) { best = waste; g.tile_w = tw; g.tile_h = th; }
+  }
+  g.b_hi = w_hi; g.b_lo = w_lo; g.n = (int)npad; g.ldb = rup((int64_t)ksize * ksize * cin, 64);
+  g.alpha = 1.0f;
+  g.bias = bias;
+  g.res_hi = res_hi; g.res_lo = res_lo; g.ld_res = npad;
+  g.relu = relu;
+  g.out_hi = out_hi; g.out_lo = out_lo; g.ld_out = npad;
+  g.out_f32 = out_f32; g.ld_f32 = rup(npad, 4);
+  g.passes = 3;
+  return hvr_igemm(&g, stream);
+}
+
 namespace {
 struct RelWs {
   hvr_bf16 *q_hi, *q_lo, *k_hi, *k_lo, *p_hi, *p_lo, *xt_hi, *xt_lo, *o_hi, *o_lo;

@@ -303,6 +303,25 @@ int hvr_pack_conv_bn(const float* w_host, const float* bn_weight_host, const flo
 int hvr_pack_linear(const float* w_host, const float* bias_host, int n, int k, const int* col_perm_host,
                     hvr_bf16* w_hi, hvr_bf16* w_lo, float* bias, void* stream);
 
+/* One layer behind one call (the descriptor filling of hvrnet_b200/engine.py in C++; same launches, same bits):
+ *   hvr_linear_fwd : y = alpha * x W^T + bias (+ res) (ReLU); x [rows, k] split (pitch ld_x), W as packed by
+ *       hvr_pack_linear (n valid rows); out split (pitch ld_out) and / or fp32 (pitch ld_f32); res optional.
+ *       Replaces nn.Linear (hrnmp_bbox_head.py:827-906 fc_new_k / fc_cls / fc_reg, convfc_bbox_head.py:126-167).
+ *   hvr_conv_fwd   : NHWC split input [batch, h, w, cin] -> NHWC output [batch, ho, wo, hvr_packed_rows(cout)] for a
+ *       ksize x ksize (1 or 3) convolution with `dilation`, padding = dilation * (ksize / 2) and `stride` (1x1 only when
+ *       > 1: the caffe-style bottleneck puts the stride on conv1 / downsample), weights + bias as packed by
+ *       hvr_pack_conv_bn; optional residual (same shape as the output) and ReLU.  Replaces conv + norm + activation of
+ *       resnet.py:222-257 / res_layer.py:67-74 / rpn_head.py:30-35 (ConvModule). */
+int hvr_linear_fwd(const hvr_bf16* x_hi, const hvr_bf16* x_lo, int rows, int k, int64_t ld_x,
+                   const hvr_bf16* w_hi, const hvr_bf16* w_lo, const float* bias, int n,
+                   const hvr_bf16* res_hi, const hvr_bf16* res_lo, int64_t ld_res, int relu, float alpha,
+                   hvr_bf16* out_hi, hvr_bf16* out_lo, int64_t ld_out, float* out_f32, int64_t ld_f32,
+                   void* stream);
+int hvr_conv_fwd(const hvr_bf16* x_hi, const hvr_bf16* x_lo, int batch, int h, int w, int cin,
+                 const hvr_bf16* w_hi, const hvr_bf16* w_lo, const float* bias, int cout, int ksize,
+                 int dilation, int stride, const hvr_bf16* res_hi, const hvr_bf16* res_lo, int relu,
+                 hvr_bf16* out_hi, hvr_bf16* out_lo, float* out_f32, void* stream);
+
 /* One relation block behind one call.  Replaces forward_single_selsa (hrnmp_bbox_head.py:216-355; SelsaBBoxHead:
  * selsa_bbox_head.py:108-201) with conv_g False / conv_z True (the configs' setting):
  *     Q = xq Wq^T + bq;  K = x Wk^T + bk;  P = softmax_keys(Q K^T / sqrt(D));  O = P x;

@@ -1056,3 +1056,50 @@ def test_abi_packing_and_relation_equal_the_python_engine(cuda):
         assert rc == 0
         assert torch.equal(out.hi.view(torch.int16), want.hi.view(torch.int16))
         assert torch.equal(out.lo.view(torch.int16), want.lo.view(torch.int16))
+
+
+def test_abi_layer_composites_equal_the_python_engine(cuda):
+    """hvr_conv_fwd / hvr_linear_fwd (descriptor filling in C++) return the bits of engine.conv / engine.lin: dilated 3x3,
+    strided 1x1 with residual, plain 1x1 with fp32 output, and a linear layer with residual + ReLU."""
+    import ctypes
+    from hvrnet_b200 import _lib, engine, ops
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(12)
+    fp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for (B, H, W, ci, co, k, dil, stride, use_res, f32) in ((2, 38, 63, 128, 96, 3, 2, 1, False, False),
+                                                             (2, 38, 63, 256, 128, 1, 1, 2, True, False),
+                                                             (1, 20, 24, 64, 60, 1, 1, 1, False, True)):
+        x = ops.nchw_to_nhwc_split(torch.randn(B, ci, H, W, generator=g).to(cuda))
+        w = torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5
+        cp = engine.ConvP(engine.pack_conv(w, None, cuda), torch.randn(engine.round_up(co, 64), generator=g).to(cuda), co, k, ci, dil)
+        Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+        npad = cp.w.shape[0]
+        res = ops.Split((torch.randn(B, Ho, Wo, npad, generator=g)).to(cuda).bfloat16(),
+                        (torch.randn(B, Ho, Wo, npad, generator=g) * 0.01).to(cuda).bfloat16()) if use_res else None
+        want, want_f = engine.conv(x, cp, stride=stride, relu=True, res=res, want_split=not f32, want_f32=f32)
+        out = ops.Split.empty((B, Ho, Wo, npad), cuda) if not f32 else None
+        of = torch.empty((B, Ho, Wo, engine.round_up(npad, 4)), dtype=torch.float32, device=cuda) if f32 else None
+        rc = L.hvr_conv_fwd(fp(x.hi), fp(x.lo), B, H, W, ci, fp(cp.w.hi), fp(cp.w.lo), fp(cp.bias), co, k, dil, stride,
+                            fp(res.hi) if res else None, fp(res.lo) if res else None, 1,
+                            fp(out.hi) if out else None, fp(out.lo) if out else None, fp(of), st())
+        assert rc == 0
+        if f32:
+            assert torch.equal(of, want_f)
+        else:
+            assert torch.equal(out.hi.view(torch.int16), want.hi.view(torch.int16))
+            assert torch.equal(out.lo.view(torch.int16), want.lo.view(torch.int16))
+    M, K, N = 700, 200, 130
+    xs = ops.split(torch.randn(M, K, generator=g).to(cuda))
+    lp = engine.pack_linear(torch.randn(N, K, generator=g) * 0.1, torch.randn(N, generator=g), cuda)
+    npad = lp.w.shape[0]                                   # engine.lin computes the 64-padded rows (exact zeros)
+    res = ops.split(torch.randn(M, npad, generator=g).to(cuda))
+    want, want_f, _ = engine.lin(xs, lp, relu=True, res=res, want_f32=True)
+    out = ops.Split.empty(tuple(want.shape), cuda)
+    of = torch.empty(tuple(want_f.shape), dtype=torch.float32, device=cuda)
+    rc = L.hvr_linear_fwd(fp(xs.hi), fp(xs.lo), M, K, xs.hi.stride(0), fp(lp.w.hi), fp(lp.w.lo), fp(lp.bias), npad,
+                          fp(res.hi), fp(res.lo), res.hi.stride(0), 1, 1.0, fp(out.hi), fp(out.lo), out.hi.stride(0), fp(of),
+                          of.stride(0), st())
+    assert rc == 0
+    assert torch.equal(out.hi.view(torch.int16), want.hi.view(torch.int16))
+    assert torch.equal(out.lo.view(torch.int16), want.lo.view(torch.int16)) and torch.equal(of, want_f)

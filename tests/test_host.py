@@ -514,6 +514,12 @@ def test_abi_argument_checks_without_a_gpu():
     assert L.hvr_support_select(null, 8, 256, 0, 2, 4, one, null, null) == ARG
     assert L.hvr_support_select(one, 8, 256, 7, 2, 4, one, null, null) == ARG            # g0 + n_local > G
     assert L.hvr_support_select(one, 8, 256, 0, 0, 4, one, null, null) == 0              # nothing to select
+    # layer composites (hvr_conv_fwd / hvr_linear_fwd): nulls, impossible geometry, strided 3x3 (not on the path)
+    assert L.hvr_linear_fwd(null, one, 8, 64, 64, one, one, null, 64, null, null, 0, 0, 1.0, one, one, 64, null, 0, null) == ARG
+    assert L.hvr_linear_fwd(one, one, 0, 64, 64, one, one, null, 64, null, null, 0, 0, 1.0, one, one, 64, null, 0, null) == ARG
+    assert L.hvr_conv_fwd(one, one, 1, 38, 63, 64, one, one, null, 64, 5, 1, 1, null, null, 0, one, one, null, null) == ARG
+    assert L.hvr_conv_fwd(one, one, 1, 38, 63, 64, one, one, null, 64, 1, 1, 1, null, null, 0, null, null, null, null) == ARG
+    assert L.hvr_conv_fwd(one, one, 1, 38, 63, 64, one, one, null, 64, 3, 1, 2, null, null, 0, one, one, null, null) == -4
     assert L.hvr_strerror(ARG) not in (b'', b'ok')
 
 

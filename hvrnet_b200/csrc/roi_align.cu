@@ -211,13 +211,16 @@ __global__ void __launch_bounds__(256, SN2_MIN_CTAS) roi_align_sn2_kernel(
 template <int VEC>
 struct Vec { float4 v[VEC]; };
 
-template <int NC, int VEC>
+// ES = bytes between the VEC vectors of a thread: 16 (adjacent channels) or C/VEC*4 (lane-interleaved: vector e of lane j
+// covers channels [(e*C/(4 VEC) + j) * 4, +4), so that every LDG.128 / STG.64 of a warp touches one contiguous run - with
+// adjacent channels each of the two loads of a tap uses half of every 32-byte sector it requests).
+template <int NC, int VEC, int ES>
 __device__ __forceinline__ Vec<VEC> row_interp_nc(const char* const (&pc)[4], const float (&w)[4], uint32_t row_off) {
   float4 v[NC][VEC];
 #pragma unroll
   for (int k = 0; k < NC; ++k)
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) v[k][e] = __ldg(reinterpret_cast<const float4*>(pc[k] + row_off) + e);
+    for (int e = 0; e < VEC; ++e) v[k][e] = __ldg(reinterpret_cast<const float4*>(pc[k] + row_off + e * ES));
   Vec<VEC> t;
 #pragma unroll
   for (int e = 0; e < VEC; ++e) {
@@ -268,7 +271,7 @@ __device__ __forceinline__ void store_bin_packed(const float4& a, float* __restr
   }
 }
 
-template <int NC, int VEC>
+template <int NC, int VEC, int ES>
 __device__ __forceinline__ void roi_column_walk(const RowTap* __restrict__ rows, int ph, const char* const (&pc)[4],
                                                 const float (&w)[4], float* o_f32, __nv_bfloat16* o_hi,
                                                 __nv_bfloat16* o_lo, size_t step) {
@@ -280,11 +283,11 @@ __device__ __forceinline__ void roi_column_walk(const RowTap* __restrict__ rows,
     const RowTap r = rows[s];
     if (r.o0 != kRowInvalid) {
       if (r.o0 == cb) { ta = tb; ca = cb; }
-      else if (r.o0 != ca) { ta = row_interp_nc<NC, VEC>(pc, w, r.o0); ca = r.o0; }
+      else if (r.o0 != ca) { ta = row_interp_nc<NC, VEC, ES>(pc, w, r.o0); ca = r.o0; }
       vec_fma<VEC>(acc, r.w0, ta);
       if (r.w1 != 0.f) {
         if (r.o1 != ca) {
-          if (r.o1 != cb) { tb = row_interp_nc<NC, VEC>(pc, w, r.o1); cb = r.o1; }
+          if (r.o1 != cb) { tb = row_interp_nc<NC, VEC, ES>(pc, w, r.o1); cb = r.o1; }
           vec_fma<VEC>(acc, r.w1, tb);
         } else {
           vec_fma<VEC>(acc, r.w1, ta);
@@ -294,8 +297,8 @@ __device__ __forceinline__ void roi_column_walk(const RowTap* __restrict__ rows,
     if (s & 1) {                                     // second sample of the bin: emit, next bin
 #pragma unroll
       for (int e = 0; e < VEC; ++e)
-        store_bin_packed(acc.v[e], o_f32 ? o_f32 + 4 * e : nullptr, o_hi ? o_hi + 4 * e : nullptr,
-                         o_hi ? o_lo + 4 * e : nullptr);
+        store_bin_packed(acc.v[e], o_f32 ? o_f32 + (ES / 4) * e : nullptr, o_hi ? o_hi + (ES / 4) * e : nullptr,
+                         o_hi ? o_lo + (ES / 4) * e : nullptr);
       if (o_f32) o_f32 += step;
       if (o_hi) { o_hi += step; o_lo += step; }
       acc = vec_zero<VEC>();
@@ -303,7 +306,172 @@ __device__ __forceinline__ void roi_column_walk(const RowTap* __restrict__ rows,
   }
 }
 
-template <int VEC>
+// ---- the walk as a per-RoI row program (roi_align_sepp_kernel) ----------------------------------------------------
+// ncu of the walk above (profiles/r02q_*): 2245 warp instructions per warp and RoI of which 516 are multiply-adds; a
+// quarter are register moves (the ta = tb hand-over of the two-row cache and its compares, kept on the local stack).
+// Here the two cached rows live in fixed registers by ROW PARITY (a sample's two rows y, y + 1 always have different
+// parity, and the rows a column walk needs never decrease, so a slot is never reloaded with an older row), and which
+// sample loads which slot is decided ONCE per RoI by warp 0 (__match_any_sync over the samples' row indices: the first
+// sample that uses a row loads it) into a 16-byte step per sample.  The same operations on the same operands in the same
+// order as roi_column_walk / roi_align_sep.cuh::roi_column_sep_sn2, hence the same bits.
+struct RowStep {
+  uint32_t oe, oo;   // byte offsets of the even / odd map row of this sample; low bits of oe: 1 load even, 2 load odd,
+  float we, wo;      //   4 the sample's upper row is the odd one, 8 sample inside the map.  we / wo: their weights
+};
+
+__device__ __forceinline__ void build_row_program(RowStep* __restrict__ prog, float start, float bin, int ph, int H,
+                                                  uint32_t row_pitch) {
+  const int s = threadIdx.x;                       // warp 0, all 32 lanes (2 * ph <= 32)
+  RowStep st{0u, 0u, 0.f, 0.f};
+  uint32_t key_e = 0x80000000u | (uint32_t)s, key_o = key_e, flags = 0;
+  bool use_e = false, use_o = false;
+  if (s < 2 * ph) {
+    const RowTap r = row_tap_sn2(start, bin, s, H, 1u);          // o0 / o1 = row indices
+    if (r.o0 != kRowInvalid) {
+      const bool odd = r.o0 & 1u, second = r.w1 != 0.f;          // second => o1 == o0 + 1 (axis_tap)
+      flags = 8u | (odd ? 4u : 0u);
+      if (!odd) { st.oe = r.o0; st.we = r.w0; use_e = true; if (second) { st.oo = r.o1; st.wo = r.w1; use_o = true; } }
+      else      { st.oo = r.o0; st.wo = r.w0; use_o = true; if (second) { st.oe = r.o1; st.we = r.w1; use_e = true; } }
+      if (use_e) key_e = st.oe;
+      if (use_o) key_o = st.oo;
+    }
+  }
+  const uint32_t me = __match_any_sync(0xffffffffu, key_e), mo = __match_any_sync(0xffffffffu, key_o);
+  if (use_e && __ffs(me) - 1 == s) flags |= 1u;
+  if (use_o && __ffs(mo) - 1 == s) flags |= 2u;
+  if (s < 2 * ph) {
+    st.oe = st.oe * row_pitch | flags;                           // row_pitch is a multiple of 16 (C % 4 == 0)
+    st.oo = st.oo * row_pitch;
+    prog[s] = st;
+  }
+}
+
+// Row interpolation with the column taps addressed from ONE pointer (PAIR = false: the NC merged taps are consecutive map
+// columns - always the case for RoIs up to 4 columns per bin) or TWO (PAIR = true, NC = 4: columns a, a+1, b, b+1): the
+// column pitch CP = C * 4 bytes is compile-time, so the other taps are immediate offsets of the load (2 or 4 address
+// instructions per row instead of 8, and 2 or 4 pointer registers instead of 8).  Same arithmetic as row_interp_nc.
+template <int NC, int VEC, int ES, int CP, bool PAIR>
+__device__ __forceinline__ Vec<VEC> row_interp_cp(const char* pa, const char* pb, const float (&w)[4], uint32_t row_off) {
+  float4 v[NC][VEC];
+  const char* ra = pa + row_off;
+  const char* rb = PAIR ? pb + row_off : nullptr;
+#pragma unroll
+  for (int k = 0; k < NC; ++k)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e)
+      v[k][e] = __ldg(reinterpret_cast<const float4*>((PAIR && k >= 2 ? rb + (k - 2) * CP : ra + k * CP) + e * ES));
+  Vec<VEC> t;
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    if (NC == 4) {
+      t.v[e].x = w[3] * v[3][e].x; t.v[e].y = w[3] * v[3][e].y; t.v[e].z = w[3] * v[3][e].z; t.v[e].w = w[3] * v[3][e].w;
+    } else {
+      t.v[e] = make_float4(fmaf(w[NC - 1], v[NC - 1][e].x, 0.f), fmaf(w[NC - 1], v[NC - 1][e].y, 0.f),
+                           fmaf(w[NC - 1], v[NC - 1][e].z, 0.f), fmaf(w[NC - 1], v[NC - 1][e].w, 0.f));
+    }
+#pragma unroll
+    for (int k = NC - 2; k >= 0; --k) {
+      t.v[e].x = fmaf(w[k], v[k][e].x, t.v[e].x); t.v[e].y = fmaf(w[k], v[k][e].y, t.v[e].y);
+      t.v[e].z = fmaf(w[k], v[k][e].z, t.v[e].z); t.v[e].w = fmaf(w[k], v[k][e].w, t.v[e].w);
+    }
+  }
+  return t;
+}
+
+template <int NC, int VEC, int ES, int CP, bool PAIR>
+__device__ __forceinline__ void roi_column_walk_prog(const RowStep* __restrict__ prog, int ph, const char* pa, const char* pb,
+                                                     const float (&w)[4], float* o_f32, __nv_bfloat16* o_hi,
+                                                     __nv_bfloat16* o_lo, size_t step) {
+  Vec<VEC> te = vec_zero<VEC>(), to = te, acc = te;
+#pragma unroll 1
+  for (int p = 0; p < ph; ++p) {
+#pragma unroll
+    for (int iy = 0; iy < 2; ++iy) {
+      const uint4 st = *reinterpret_cast<const uint4*>(prog + 2 * p + iy);
+      if (st.x & 1u) te = row_interp_cp<NC, VEC, ES, CP, PAIR>(pa, pb, w, st.x & ~15u);
+      if (st.x & 2u) to = row_interp_cp<NC, VEC, ES, CP, PAIR>(pa, pb, w, st.y);
+      const float we = __uint_as_float(st.z), wo = __uint_as_float(st.w);
+      if (st.x & 8u) {
+        if (st.x & 4u) {
+          vec_fma<VEC>(acc, wo, to);
+          if (we != 0.f) vec_fma<VEC>(acc, we, te);
+        } else {
+          vec_fma<VEC>(acc, we, te);
+          if (wo != 0.f) vec_fma<VEC>(acc, wo, to);
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e)
+      store_bin_packed(acc.v[e], o_f32 ? o_f32 + (ES / 4) * e : nullptr, o_hi ? o_hi + (ES / 4) * e : nullptr,
+                       o_hi ? o_lo + (ES / 4) * e : nullptr);
+    if (o_f32) o_f32 += step;
+    if (o_hi) { o_hi += step; o_lo += step; }
+    acc = vec_zero<VEC>();
+  }
+}
+
+template <int VEC, int ES>
+__device__ __forceinline__ void roi_align_sepp_body(
+    const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
+    float scale, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+    long long ld_split) {
+  __shared__ __align__(16) RowStep prog[32];
+  const int roi = blockIdx.x;
+  const RoiGeom g = roi_geom(rois + (size_t)roi * 5, scale, ph, pw, n_imgs);
+  if (threadIdx.x < 32) build_row_program(prog, g.sh, g.bh, ph, H, (uint32_t)(W * C) * 4u);
+  const int cg = C / (4 * VEC);
+  const int q = threadIdx.x / cg, c4 = (threadIdx.x - q * cg) * (ES == 16 ? VEC : 1);
+  const ColTaps ct = col_taps_sn2(g.sw, g.bw, q, W, (uint32_t)C * 4u);
+  __syncthreads();
+  const char* base = reinterpret_cast<const char*>(feat + (size_t)g.b * H * W * C + c4 * 4);
+  const size_t o_f32 = ((size_t)roi * ph * pw + q) * C + c4 * 4;
+  const size_t o_split = (size_t)roi * ld_split + (size_t)q * C + c4 * 4;
+  const size_t step = (size_t)pw * C;
+  float* of = out ? out + o_f32 : nullptr;
+  __nv_bfloat16* oh = out_hi ? out_hi + o_split : nullptr;
+  __nv_bfloat16* ol = out_hi ? out_lo + o_split : nullptr;
+  if (ct.n >= 1) {
+    constexpr int CP = ES * VEC * 4 / 4;              // column pitch in bytes = C * 4 (lane-interleaved: C = ES * VEC / 4)
+    const float w[4] = {ct.w[0], ct.w[1], ct.w[2], ct.w[3]};
+    bool consec = true;
+    for (int k = 1; k < ct.n; ++k) consec = consec && ct.off[k] == ct.off[0] + (uint32_t)k * CP;
+    const char* pa = base + ct.off[0];
+    if (consec) {
+      switch (ct.n) {
+        case 1: roi_column_walk_prog<1, VEC, ES, CP, false>(prog, ph, pa, nullptr, w, of, oh, ol, step); break;
+        case 2: roi_column_walk_prog<2, VEC, ES, CP, false>(prog, ph, pa, nullptr, w, of, oh, ol, step); break;
+        case 3: roi_column_walk_prog<3, VEC, ES, CP, false>(prog, ph, pa, nullptr, w, of, oh, ol, step); break;
+        default: roi_column_walk_prog<4, VEC, ES, CP, false>(prog, ph, pa, nullptr, w, of, oh, ol, step); break;
+      }
+    } else if (ct.n == 4) {                           // columns a, a+1, b, b+1 (bins wider than 4 columns)
+      roi_column_walk_prog<4, VEC, ES, CP, true>(prog, ph, pa, base + ct.off[2], w, of, oh, ol, step);
+    } else {                                          // 2 or 3 taps with a hole (a sample exactly on a column): the generic walk
+      __shared__ RowTap rows[32];
+      // (every thread of a warp takes the same branch - q is warp-uniform - but not every warp of the CTA: no barrier here)
+      for (int s2 = 0; s2 < 2 * ph; ++s2) {
+        const RowTap r = row_tap_sn2(g.sh, g.bh, s2, H, (uint32_t)(W * C) * 4u);
+        rows[s2] = r;                                 // identical values from every writer
+      }
+      __syncwarp();
+      const char* const pc[4] = {base + ct.off[0], base + ct.off[1], base + ct.off[2], base + ct.off[3]};
+      if (ct.n == 2) roi_column_walk<2, VEC, ES>(rows, ph, pc, w, of, oh, ol, step);
+      else roi_column_walk<3, VEC, ES>(rows, ph, pc, w, of, oh, ol, step);
+    }
+    return;
+  }
+  // no column tap at all (every x sample outside the map): the column is zero
+  const Vec<VEC> z = vec_zero<VEC>();
+  for (int p = 0; p < ph; ++p) {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e)
+      store_bin_packed(z.v[e], of ? of + (ES / 4) * e : nullptr, oh ? oh + (ES / 4) * e : nullptr, oh ? ol + (ES / 4) * e : nullptr);
+    if (of) of += step;
+    if (oh) { oh += step; ol += step; }
+  }
+}
+
+template <int VEC, int ES = 16>
 __device__ __forceinline__ void roi_align_sep_body(
     const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
     float scale, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
@@ -313,7 +481,7 @@ __device__ __forceinline__ void roi_align_sep_body(
   const RoiGeom g = roi_geom(rois + (size_t)roi * 5, scale, ph, pw, n_imgs);
   if ((int)threadIdx.x < 2 * ph) rows[threadIdx.x] = row_tap_sn2(g.sh, g.bh, threadIdx.x, H, (uint32_t)(W * C) * 4u);
   const int cg = C / (4 * VEC);                       // channel groups of 4 * VEC channels
-  const int q = threadIdx.x / cg, c4 = (threadIdx.x - q * cg) * VEC;
+  const int q = threadIdx.x / cg, c4 = (threadIdx.x - q * cg) * (ES == 16 ? VEC : 1);   // first float4 of the thread
   const ColTaps ct = col_taps_sn2(g.sw, g.bw, q, W, (uint32_t)C * 4u);
   __syncthreads();
   const char* base = reinterpret_cast<const char*>(feat + (size_t)g.b * H * W * C + c4 * 4);
@@ -327,20 +495,20 @@ __device__ __forceinline__ void roi_align_sep_body(
     __nv_bfloat16* oh = out_hi ? out_hi + o_split : nullptr;
     __nv_bfloat16* ol = out_hi ? out_lo + o_split : nullptr;
     switch (ct.n) {
-      case 1: roi_column_walk<1, VEC>(rows, ph, pc, w, of, oh, ol, step); break;
-      case 2: roi_column_walk<2, VEC>(rows, ph, pc, w, of, oh, ol, step); break;
-      case 3: roi_column_walk<3, VEC>(rows, ph, pc, w, of, oh, ol, step); break;
-      default: roi_column_walk<4, VEC>(rows, ph, pc, w, of, oh, ol, step); break;
+      case 1: roi_column_walk<1, VEC, ES>(rows, ph, pc, w, of, oh, ol, step); break;
+      case 2: roi_column_walk<2, VEC, ES>(rows, ph, pc, w, of, oh, ol, step); break;
+      case 3: roi_column_walk<3, VEC, ES>(rows, ph, pc, w, of, oh, ol, step); break;
+      default: roi_column_walk<4, VEC, ES>(rows, ph, pc, w, of, oh, ol, step); break;
     }
     return;
   }
   // no column tap at all (every x sample outside the map): zeros, through the generic core
 #pragma unroll
   for (int e = 0; e < VEC; ++e) {
-    const TapLoad ld{base + 16 * e};
+    const TapLoad ld{base + ES * e};
     roi_column_sep_sn2(rows, ph, ct, ld,
                        [&](int p, const float4& v) {
-                         store_bin(v, out, out_hi, out_lo, o_f32 + 4 * e + p * step, o_split + 4 * e + p * step);
+                         store_bin(v, out, out_hi, out_lo, o_f32 + (ES / 4) * e + p * step, o_split + (ES / 4) * e + p * step);
                        },
                        nullptr);
   }
@@ -360,6 +528,28 @@ __global__ void __launch_bounds__(224, 3) roi_align_sep8_kernel(
     float scale, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
     long long ld_split) {
   roi_align_sep_body<2>(feat, rois, n_imgs, C, H, W, ph, pw, scale, out, out_hi, out_lo, ld_split);
+}
+// the same with the thread's vectors lane-interleaved (C == 256): vector e = channels [128 e + 4 lane, +4) - every warp-wide
+// LDG.128 reads 512 contiguous bytes, every STG.64 writes 256
+__global__ void __launch_bounds__(224, 3) roi_align_sep8i_kernel(
+    const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
+    float scale, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+    long long ld_split) {
+  roi_align_sep_body<2, 512>(feat, rois, n_imgs, C, H, W, ph, pw, scale, out, out_hi, out_lo, ld_split);
+}
+// the row-program walk, 8 lane-interleaved channels per thread (C == 256, 2 * ph <= 32)  [shipped]
+__global__ void __launch_bounds__(224, 3) roi_align_sepp_kernel(
+    const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
+    float scale, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+    long long ld_split) {
+  roi_align_sepp_body<2, 512>(feat, rois, n_imgs, C, H, W, ph, pw, scale, out, out_hi, out_lo, ld_split);
+}
+// 16 channels per thread, interleaved (vector e = channels [64 e + 4 lane, +4)): experiments (hvr_debug_roi_variant(12))
+__global__ void __launch_bounds__(112, 4) roi_align_sep16i_kernel(
+    const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
+    float scale, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+    long long ld_split) {
+  roi_align_sep_body<4, 256>(feat, rois, n_imgs, C, H, W, ph, pw, scale, out, out_hi, out_lo, ld_split);
 }
 __global__ void __maxnreg__(48) roi_align_sep48_kernel(
     const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
@@ -504,6 +694,8 @@ __global__ void roi_align_generic_kernel(const float* __restrict__ feat, const f
 int g_roi_variant = 0;   // test hook (hvr_debug_roi_variant): 0 = heuristic, 1 = always the per-bin kernel
 int g_sep_minb = 2;      // test hook (hvr_debug_roi_variant 2 / 3): resident CTAs per SM the fast kernel is built for
 bool g_sep_vec8 = true;  // test hook (hvr_debug_roi_variant 7 / 8): 8 channels per thread on (default: 835 vs 915 us on the bench launch) / off
+int g_sep_layout = 3;    // test hook (hvr_debug_roi_variant 10 .. 13): channels of a thread adjacent / lane-interleaved / 16 interleaved /
+                         // lane-interleaved with the row-program walk (default)
 int g_slab = 0;          // test hook (hvr_debug_roi_variant 4 / 5 / 6): 0 = heuristic (= never), 1 = slab kernel whenever it applies, 2 = never
 
 }  // namespace
@@ -515,6 +707,10 @@ extern "C" int hvr_debug_roi_variant(int v) {
   }
   if (v == 7 || v == 8) {
     g_sep_vec8 = v == 7;
+    return HVR_OK;
+  }
+  if (v >= 10 && v <= 13) {
+    g_sep_layout = v - 10;
     return HVR_OK;
   }
   if (v >= 4 && v <= 6) {          // 4 = heuristic, 5 = slab kernel whenever it applies, 6 = never the slab kernel
@@ -581,6 +777,19 @@ extern "C" int hvr_roi_align_fwd_fast(const float* feat, int feat_nhwc, const fl
     return HVR_OK;
   }
   const int threads = pw * (C >> 2);
+  if (g_sep_vec8 && g_sep_layout != 0 && C == 256 && pw <= 7) {
+    if (g_sep_layout == 3 && 2 * ph <= 32 && pw * 32 >= 32)
+      roi_align_sepp_kernel<<<n_rois, pw * 32, 0, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out,
+                                                        (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_split);
+    else if (g_sep_layout == 2)
+      roi_align_sep16i_kernel<<<n_rois, pw * 16, 0, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out,
+                                                          (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_split);
+    else
+      roi_align_sep8i_kernel<<<n_rois, pw * 32, 0, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out,
+                                                         (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_split);
+    HVR_LAUNCHED();
+    return HVR_OK;
+  }
   if (g_sep_vec8 && C % 8 == 0 && pw * (C >> 3) <= 224) {
     roi_align_sep8_kernel<<<n_rois, pw * (C >> 3), 0, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out,
                                                            (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_split);

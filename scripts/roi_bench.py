@@ -21,10 +21,15 @@ for T, lo, hi in ((1, 16, 396), (15, 16, 396), (105, 16, 396), (105, 16, 112), (
     # generic = per-bin kernel (16 loads per output vector), sn2 = strict tap-reuse kernel, fast_roi_cta / fast_slab = the
     # separable FMA evaluation with one CTA per RoI / with CTA = (frame, 16-channel slab of the map in shared memory)
     for name, variant, arith in (("generic", 1, "strict"), ("sn2", 0, "strict"), ("fast_roi_cta_4ch", 6, "fast"),
-                                 ("fast_roi_cta_8ch [shipped]", 7, "fast"), ("fast_roi_cta_3ctas", 3, "fast"), ("fast_slab", 5, "fast")):
+                                 ("fast_roi_cta_8ch_adjacent", 107, "fast"), ("fast_roi_cta_8ch_interleaved", 117, "fast"),
+                                 ("fast_roi_cta_16ch_interleaved", 127, "fast"), ("fast_roi_cta_8ch_interleaved_row_program [shipped]", 137, "fast"), ("fast_roi_cta_3ctas", 3, "fast"), ("fast_slab", 5, "fast")):
         _lib.lib().hvr_debug_roi_variant(0)
         _lib.lib().hvr_debug_roi_variant(2)
         _lib.lib().hvr_debug_roi_variant(8)
+        _lib.lib().hvr_debug_roi_variant(13)
+        if variant > 100:                                     # 1xy: channel layout 1x of the 8-channel kernel
+            _lib.lib().hvr_debug_roi_variant(variant // 10)
+            variant = 7
         _lib.lib().hvr_debug_roi_variant(6 if variant in (3, 7) else 4)
         _lib.lib().hvr_debug_roi_variant(variant)
         fn = lambda: ops.roi_align(feat, rois, feat_nhwc=True, out_nhwc=True, want_split=True, want_f32=False,
@@ -40,7 +45,7 @@ for T, lo, hi in ((1, 16, 396), (15, 16, 396), (105, 16, 396), (105, 16, 112), (
         torch.cuda.synchronize()
         us = a.elapsed_time(b) / 10 * 1e3
         print('T=%d side %d-%d px variant=%s %.1f us  %.0f GB/s (algorithmic 17.51 MB/frame)' % (T, lo, hi, name, us, 17510256.0 * T / us / 1e3))
-    for v_ in (0, 2, 7, 4):
+    for v_ in (0, 2, 7, 4, 13):
         _lib.lib().hvr_debug_roi_variant(v_)
     # the reference's own CUDA op (oracle/_ref, compiled unmodified for sm_100a): NCHW map in, NCHW fp32 out
     try:

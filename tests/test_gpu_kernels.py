@@ -544,6 +544,8 @@ def test_roi_align_fast_variant_vs_strict(cuda, C, out_size):
     rois[42, 1:] = 0.                                                            # the pad RoI of a batched window
     rois[43, 1:] = torch.tensor([1500., 100., 1600., 200.])                      # entirely outside the map: all zero
     rois[44, 1:] = torch.tensor([100., -500., 200., -100.])
+    rois[45, 1:] = torch.tensor([48., 100., 495., 300.])        # x samples exactly on columns 4, 6, 8 ...: 2 taps with a hole
+    rois[46, 1:] = torch.tensor([44., 50., 603., 400.])         # x samples at 4.0 and 6.5: 3 taps with a hole
     ref = cref.roi_align(feat, rois, out_size=out_size, feat_nhwc=True, out_nhwc=True)
     f, r = feat.to(cuda), rois.to(cuda)
     from hvrnet_b200 import _lib
@@ -554,14 +556,22 @@ def test_roi_align_fast_variant_vs_strict(cuda, C, out_size):
         # 8 channels per thread: the same operations per element -> the same bits
         _lib.lib().hvr_debug_roi_variant(7)
         o_8, sp_8 = ops.roi_align(f, r, out_size=out_size, feat_nhwc=True, out_nhwc=True, want_split=True, arithmetic='fast')
-        _lib.lib().hvr_debug_roi_variant(8)
         assert torch.equal(o_8.view(torch.int32), o.view(torch.int32)) and torch.equal(sp_8.lo.view(torch.int16), sp.lo.view(torch.int16))
+        # the 8-channel kernel's variants at C = 256: 10 adjacent channels, 11 lane-interleaved, 12 = 16 per thread (all with the
+        # two-row-cache walk); 13 = lane-interleaved with the per-RoI row program (default, = o_8 above)
+        for layout in (10, 11, 12):
+            _lib.lib().hvr_debug_roi_variant(layout)
+            o_l, sp_l = ops.roi_align(f, r, out_size=out_size, feat_nhwc=True, out_nhwc=True, want_split=True, arithmetic='fast')
+            assert torch.equal(o_l.view(torch.int32), o.view(torch.int32)) and torch.equal(sp_l.hi.view(torch.int16), sp.hi.view(torch.int16))
+        _lib.lib().hvr_debug_roi_variant(13)
+        _lib.lib().hvr_debug_roi_variant(8)
         # the slab launch shape (CTA = frame x 16-channel slab, map slab in shared memory): the same separable core,
         # so identical bits wherever it applies (C % 16 == 0, out_size <= 8)
         _lib.lib().hvr_debug_roi_variant(5)
         o_s, sp_s = ops.roi_align(f, r, out_size=out_size, feat_nhwc=True, out_nhwc=True, want_split=True, arithmetic='fast')
     finally:
         _lib.lib().hvr_debug_roi_variant(7)
+        _lib.lib().hvr_debug_roi_variant(13)
         _lib.lib().hvr_debug_roi_variant(4)
     if C == 512:
         # no RoI-per-CTA launch shape (7 * 128 threads > 448): with the slab shape disabled this is the strict kernel;

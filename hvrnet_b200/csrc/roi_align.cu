@@ -339,11 +339,10 @@ __device__ __forceinline__ void build_row_program(RowStep* __restrict__ prog, fl
   const uint32_t me = __match_any_sync(0xffffffffu, key_e), mo = __match_any_sync(0xffffffffu, key_o);
   if (use_e && __ffs(me) - 1 == s) flags |= 1u;
   if (use_o && __ffs(mo) - 1 == s) flags |= 2u;
-  if (s < 2 * ph) {
-    st.oe = st.oe * row_pitch | flags;                           // row_pitch is a multiple of 16 (C % 4 == 0)
-    st.oo = st.oo * row_pitch;
-    prog[s] = st;
-  }
+  st.oe = st.oe * row_pitch | flags;                             // row_pitch is a multiple of 16 (C % 4 == 0)
+  st.oo = st.oo * row_pitch;
+  prog[s] = st;                                                  // s >= 2 * ph: empty steps (the walk reads one step ahead)
+  if (s == 0) prog[32] = RowStep{0u, 0u, 0.f, 0.f};
 }
 
 // Row interpolation with the column taps addressed from ONE pointer (PAIR = false: the NC merged taps are consecutive map
@@ -378,10 +377,28 @@ __device__ __forceinline__ Vec<VEC> row_interp_cp(const char* pa, const char* pb
   return t;
 }
 
-template <int NC, int VEC, int ES, int CP, bool PAIR>
+// OUT: 1 = fp32 rows, 2 = split rows, 3 = both (compile-time: no pointer tests in the per-bin epilogue).
+// PF: while a step's rows are in flight, the rows the NEXT step will load are prefetched into L1 - one prefetch per
+// column tap and row, lane j touching 32-byte sector j of the column's 1 KB (CP == 1024): the walk is bound by exposed
+// L2 latency (ncu: 47 % of the cycles without an eligible warp, 46 % of the stall cycles on the loads' scoreboard).
+template <int NC, int VEC, int ES, int CP, bool PAIR, bool PF>
+__device__ __forceinline__ void prefetch_row(const char* pa, const char* pb, uint32_t row_off) {
+  if (!PF) return;
+  const uint32_t lane32 = (threadIdx.x & 31u) * 16u;              // pa already carries lane * 16
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const char* ptr = (PAIR && k >= 2 ? pb + (k - 2) * CP : pa + k * CP) + row_off + lane32;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+  }
+}
+
+// Outputs are addressed as kernel-uniform base + ONE 32-bit element offset shared by the fp32 / hi / lo rows (the launcher
+// checks that the outputs are below 4 GB), which keeps the walk's live registers under the 80 that three CTAs per SM allow.
+template <int NC, int VEC, int ES, int CP, bool PAIR, int OUT, bool PF>
 __device__ __forceinline__ void roi_column_walk_prog(const RowStep* __restrict__ prog, int ph, const char* pa, const char* pb,
-                                                     const float (&w)[4], float* o_f32, __nv_bfloat16* o_hi,
-                                                     __nv_bfloat16* o_lo, size_t step) {
+                                                     const float (&w)[4], float* __restrict__ out,
+                                                     __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                                                     uint32_t o_f32, uint32_t o_split, uint32_t step) {
   Vec<VEC> te = vec_zero<VEC>(), to = te, acc = te;
 #pragma unroll 1
   for (int p = 0; p < ph; ++p) {
@@ -390,6 +407,11 @@ __device__ __forceinline__ void roi_column_walk_prog(const RowStep* __restrict__
       const uint4 st = *reinterpret_cast<const uint4*>(prog + 2 * p + iy);
       if (st.x & 1u) te = row_interp_cp<NC, VEC, ES, CP, PAIR>(pa, pb, w, st.x & ~15u);
       if (st.x & 2u) to = row_interp_cp<NC, VEC, ES, CP, PAIR>(pa, pb, w, st.y);
+      if (PF) {                                                                     // prog has 2 * ph + 1 entries
+        const uint2 nx = *reinterpret_cast<const uint2*>(prog + 2 * p + iy + 1);
+        if (nx.x & 1u) prefetch_row<NC, VEC, ES, CP, PAIR, PF>(pa, pb, nx.x & ~15u);
+        if (nx.x & 2u) prefetch_row<NC, VEC, ES, CP, PAIR, PF>(pa, pb, nx.y);
+      }
       const float we = __uint_as_float(st.z), wo = __uint_as_float(st.w);
       if (st.x & 8u) {
         if (st.x & 4u) {
@@ -403,20 +425,35 @@ __device__ __forceinline__ void roi_column_walk_prog(const RowStep* __restrict__
     }
 #pragma unroll
     for (int e = 0; e < VEC; ++e)
-      store_bin_packed(acc.v[e], o_f32 ? o_f32 + (ES / 4) * e : nullptr, o_hi ? o_hi + (ES / 4) * e : nullptr,
-                       o_hi ? o_lo + (ES / 4) * e : nullptr);
-    if (o_f32) o_f32 += step;
-    if (o_hi) { o_hi += step; o_lo += step; }
+      store_bin_packed(acc.v[e], (OUT & 1) ? out + o_f32 + (ES / 4) * e : nullptr, (OUT & 2) ? out_hi + o_split + (ES / 4) * e : nullptr,
+                       (OUT & 2) ? out_lo + o_split + (ES / 4) * e : nullptr);
+    o_f32 += step;
+    o_split += step;
     acc = vec_zero<VEC>();
   }
 }
 
+// rare column-tap sets (a hole between 2 or 3 taps): the two-row-cache walk, out of line
 template <int VEC, int ES>
+__device__ __noinline__ void sepp_hole_walk(float sh, float bh, int ph, int H, uint32_t row_pitch, const char* base, const ColTaps& ct,
+                                            float* of, __nv_bfloat16* oh, __nv_bfloat16* ol, uint32_t step) {
+  __shared__ RowTap rows[32];
+  // every thread of a warp is here together (q is warp-uniform) but not every warp of the CTA: no CTA barrier; the
+  // writers store identical values
+  for (int s2 = 0; s2 < 2 * ph; ++s2) rows[s2] = row_tap_sn2(sh, bh, s2, H, row_pitch);
+  __syncwarp();
+  const char* const pc[4] = {base + ct.off[0], base + ct.off[1], base + ct.off[2], base + ct.off[3]};
+  const float w[4] = {ct.w[0], ct.w[1], ct.w[2], ct.w[3]};
+  if (ct.n == 2) roi_column_walk<2, VEC, ES>(rows, ph, pc, w, of, oh, ol, step);
+  else roi_column_walk<3, VEC, ES>(rows, ph, pc, w, of, oh, ol, step);
+}
+
+template <int VEC, int ES, int OUT, bool PF>
 __device__ __forceinline__ void roi_align_sepp_body(
     const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
     float scale, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
     long long ld_split) {
-  __shared__ __align__(16) RowStep prog[32];
+  __shared__ __align__(16) RowStep prog[33];
   const int roi = blockIdx.x;
   const RoiGeom g = roi_geom(rois + (size_t)roi * 5, scale, ph, pw, n_imgs);
   if (threadIdx.x < 32) build_row_program(prog, g.sh, g.bh, ph, H, (uint32_t)(W * C) * 4u);
@@ -425,12 +462,9 @@ __device__ __forceinline__ void roi_align_sepp_body(
   const ColTaps ct = col_taps_sn2(g.sw, g.bw, q, W, (uint32_t)C * 4u);
   __syncthreads();
   const char* base = reinterpret_cast<const char*>(feat + (size_t)g.b * H * W * C + c4 * 4);
-  const size_t o_f32 = ((size_t)roi * ph * pw + q) * C + c4 * 4;
-  const size_t o_split = (size_t)roi * ld_split + (size_t)q * C + c4 * 4;
-  const size_t step = (size_t)pw * C;
-  float* of = out ? out + o_f32 : nullptr;
-  __nv_bfloat16* oh = out_hi ? out_hi + o_split : nullptr;
-  __nv_bfloat16* ol = out_hi ? out_lo + o_split : nullptr;
+  const uint32_t step = (uint32_t)(pw * C);
+  const uint32_t o_f32 = (uint32_t)((roi * ph * pw + q) * C + c4 * 4);            // < 2^32 bytes: checked by the launcher
+  const uint32_t o_split = (uint32_t)(roi * (int)ld_split + q * C + c4 * 4);
   if (ct.n >= 1) {
     constexpr int CP = ES * VEC * 4 / 4;              // column pitch in bytes = C * 4 (lane-interleaved: C = ES * VEC / 4)
     const float w[4] = {ct.w[0], ct.w[1], ct.w[2], ct.w[3]};
@@ -439,24 +473,16 @@ __device__ __forceinline__ void roi_align_sepp_body(
     const char* pa = base + ct.off[0];
     if (consec) {
       switch (ct.n) {
-        case 1: roi_column_walk_prog<1, VEC, ES, CP, false>(prog, ph, pa, nullptr, w, of, oh, ol, step); break;
-        case 2: roi_column_walk_prog<2, VEC, ES, CP, false>(prog, ph, pa, nullptr, w, of, oh, ol, step); break;
-        case 3: roi_column_walk_prog<3, VEC, ES, CP, false>(prog, ph, pa, nullptr, w, of, oh, ol, step); break;
-        default: roi_column_walk_prog<4, VEC, ES, CP, false>(prog, ph, pa, nullptr, w, of, oh, ol, step); break;
+        case 1: roi_column_walk_prog<1, VEC, ES, CP, false, OUT, PF>(prog, ph, pa, nullptr, w, out, out_hi, out_lo, o_f32, o_split, step); break;
+        case 2: roi_column_walk_prog<2, VEC, ES, CP, false, OUT, PF>(prog, ph, pa, nullptr, w, out, out_hi, out_lo, o_f32, o_split, step); break;
+        case 3: roi_column_walk_prog<3, VEC, ES, CP, false, OUT, PF>(prog, ph, pa, nullptr, w, out, out_hi, out_lo, o_f32, o_split, step); break;
+        default: roi_column_walk_prog<4, VEC, ES, CP, false, OUT, PF>(prog, ph, pa, nullptr, w, out, out_hi, out_lo, o_f32, o_split, step); break;
       }
     } else if (ct.n == 4) {                           // columns a, a+1, b, b+1 (bins wider than 4 columns)
-      roi_column_walk_prog<4, VEC, ES, CP, true>(prog, ph, pa, base + ct.off[2], w, of, oh, ol, step);
+      roi_column_walk_prog<4, VEC, ES, CP, true, OUT, PF>(prog, ph, pa, base + ct.off[2], w, out, out_hi, out_lo, o_f32, o_split, step);
     } else {                                          // 2 or 3 taps with a hole (a sample exactly on a column): the generic walk
-      __shared__ RowTap rows[32];
-      // (every thread of a warp takes the same branch - q is warp-uniform - but not every warp of the CTA: no barrier here)
-      for (int s2 = 0; s2 < 2 * ph; ++s2) {
-        const RowTap r = row_tap_sn2(g.sh, g.bh, s2, H, (uint32_t)(W * C) * 4u);
-        rows[s2] = r;                                 // identical values from every writer
-      }
-      __syncwarp();
-      const char* const pc[4] = {base + ct.off[0], base + ct.off[1], base + ct.off[2], base + ct.off[3]};
-      if (ct.n == 2) roi_column_walk<2, VEC, ES>(rows, ph, pc, w, of, oh, ol, step);
-      else roi_column_walk<3, VEC, ES>(rows, ph, pc, w, of, oh, ol, step);
+      sepp_hole_walk<VEC, ES>(g.sh, g.bh, ph, H, (uint32_t)(W * C) * 4u, base, ct, (OUT & 1) ? out + o_f32 : nullptr,
+                              (OUT & 2) ? out_hi + o_split : nullptr, (OUT & 2) ? out_lo + o_split : nullptr, step);
     }
     return;
   }
@@ -465,9 +491,9 @@ __device__ __forceinline__ void roi_align_sepp_body(
   for (int p = 0; p < ph; ++p) {
 #pragma unroll
     for (int e = 0; e < VEC; ++e)
-      store_bin_packed(z.v[e], of ? of + (ES / 4) * e : nullptr, oh ? oh + (ES / 4) * e : nullptr, oh ? ol + (ES / 4) * e : nullptr);
-    if (of) of += step;
-    if (oh) { oh += step; ol += step; }
+      store_bin_packed(z.v[e], (OUT & 1) ? out + o_f32 + p * step + (ES / 4) * e : nullptr,
+                       (OUT & 2) ? out_hi + o_split + p * step + (ES / 4) * e : nullptr,
+                       (OUT & 2) ? out_lo + o_split + p * step + (ES / 4) * e : nullptr);
   }
 }
 
@@ -537,12 +563,13 @@ __global__ void __launch_bounds__(224, 3) roi_align_sep8i_kernel(
     long long ld_split) {
   roi_align_sep_body<2, 512>(feat, rois, n_imgs, C, H, W, ph, pw, scale, out, out_hi, out_lo, ld_split);
 }
-// the row-program walk, 8 lane-interleaved channels per thread (C == 256, 2 * ph <= 32)  [shipped]
+// the row-program walk, 8 lane-interleaved channels per thread (C == 256, 2 * ph <= 32)  [shipped: split rows only, PF]
+template <int OUT, bool PF>
 __global__ void __launch_bounds__(224, 3) roi_align_sepp_kernel(
     const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
     float scale, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
     long long ld_split) {
-  roi_align_sepp_body<2, 512>(feat, rois, n_imgs, C, H, W, ph, pw, scale, out, out_hi, out_lo, ld_split);
+  roi_align_sepp_body<2, 512, OUT, PF>(feat, rois, n_imgs, C, H, W, ph, pw, scale, out, out_hi, out_lo, ld_split);
 }
 // 16 channels per thread, interleaved (vector e = channels [64 e + 4 lane, +4)): experiments (hvr_debug_roi_variant(12))
 __global__ void __launch_bounds__(112, 4) roi_align_sep16i_kernel(
@@ -694,8 +721,8 @@ __global__ void roi_align_generic_kernel(const float* __restrict__ feat, const f
 int g_roi_variant = 0;   // test hook (hvr_debug_roi_variant): 0 = heuristic, 1 = always the per-bin kernel
 int g_sep_minb = 2;      // test hook (hvr_debug_roi_variant 2 / 3): resident CTAs per SM the fast kernel is built for
 bool g_sep_vec8 = true;  // test hook (hvr_debug_roi_variant 7 / 8): 8 channels per thread on (default: 835 vs 915 us on the bench launch) / off
-int g_sep_layout = 3;    // test hook (hvr_debug_roi_variant 10 .. 13): channels of a thread adjacent / lane-interleaved / 16 interleaved /
-                         // lane-interleaved with the row-program walk (default)
+int g_sep_layout = 3;    // test hook (hvr_debug_roi_variant 10 .. 14): channels of a thread adjacent / lane-interleaved / 16 interleaved /
+                         // lane-interleaved with the row-program walk (default) / the same + L1 prefetch of the next step's rows
 int g_slab = 0;          // test hook (hvr_debug_roi_variant 4 / 5 / 6): 0 = heuristic (= never), 1 = slab kernel whenever it applies, 2 = never
 
 }  // namespace
@@ -709,7 +736,7 @@ extern "C" int hvr_debug_roi_variant(int v) {
     g_sep_vec8 = v == 7;
     return HVR_OK;
   }
-  if (v >= 10 && v <= 13) {
+  if (v >= 10 && v <= 14) {
     g_sep_layout = v - 10;
     return HVR_OK;
   }
@@ -778,9 +805,15 @@ extern "C" int hvr_roi_align_fwd_fast(const float* feat, int feat_nhwc, const fl
   }
   const int threads = pw * (C >> 2);
   if (g_sep_vec8 && g_sep_layout != 0 && C == 256 && pw <= 7) {
-    if (g_sep_layout == 3 && 2 * ph <= 32 && pw * 32 >= 32)
-      roi_align_sepp_kernel<<<n_rois, pw * 32, 0, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out,
-                                                        (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_split);
+    const size_t out_bytes = (size_t)n_rois * (out_hi ? (size_t)ld_split * 2 : 0) > (size_t)n_rois * ph * pw * C * (out ? 4 : 0)
+                                 ? (size_t)n_rois * ld_split * 2 : (size_t)n_rois * ph * pw * C * 4;
+    if (g_sep_layout >= 3 && 2 * ph <= 32 && out_bytes < ((size_t)1 << 31)) {
+      const int o = (out ? 1 : 0) | (out_hi ? 2 : 0);
+      auto kern = g_sep_layout == 4 ? (o == 1 ? roi_align_sepp_kernel<1, true> : o == 2 ? roi_align_sepp_kernel<2, true> : roi_align_sepp_kernel<3, true>)
+                                    : (o == 1 ? roi_align_sepp_kernel<1, false> : o == 2 ? roi_align_sepp_kernel<2, false> : roi_align_sepp_kernel<3, false>);
+      kern<<<n_rois, pw * 32, 0, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out, (__nv_bfloat16*)out_hi,
+                                       (__nv_bfloat16*)out_lo, ld_split);
+    }
     else if (g_sep_layout == 2)
       roi_align_sep16i_kernel<<<n_rois, pw * 16, 0, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out,
                                                           (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_split);

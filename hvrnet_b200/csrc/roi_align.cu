@@ -564,8 +564,8 @@ __global__ void __launch_bounds__(224, 3) roi_align_sep8i_kernel(
   roi_align_sep_body<2, 512>(feat, rois, n_imgs, C, H, W, ph, pw, scale, out, out_hi, out_lo, ld_split);
 }
 // the row-program walk, 8 lane-interleaved channels per thread (C == 256, 2 * ph <= 32)  [shipped: split rows only, PF]
-template <int OUT, bool PF>
-__global__ void __launch_bounds__(224, 3) roi_align_sepp_kernel(
+template <int OUT, bool PF, int MINB>
+__global__ void __launch_bounds__(224, MINB) roi_align_sepp_kernel(
     const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,
     float scale, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
     long long ld_split) {
@@ -722,7 +722,8 @@ int g_roi_variant = 0;   // test hook (hvr_debug_roi_variant): 0 = heuristic, 1 
 int g_sep_minb = 2;      // test hook (hvr_debug_roi_variant 2 / 3): resident CTAs per SM the fast kernel is built for
 bool g_sep_vec8 = true;  // test hook (hvr_debug_roi_variant 7 / 8): 8 channels per thread on (default: 835 vs 915 us on the bench launch) / off
 int g_sep_layout = 3;    // test hook (hvr_debug_roi_variant 10 .. 14): channels of a thread adjacent / lane-interleaved / 16 interleaved /
-                         // lane-interleaved with the row-program walk (default) / the same + L1 prefetch of the next step's rows
+                         // lane-interleaved with the row-program walk (default) / the same + L1 prefetch of the next step's rows /
+                         // the same built for 3 instead of 4 resident CTAs per SM
 int g_slab = 0;          // test hook (hvr_debug_roi_variant 4 / 5 / 6): 0 = heuristic (= never), 1 = slab kernel whenever it applies, 2 = never
 
 }  // namespace
@@ -736,7 +737,7 @@ extern "C" int hvr_debug_roi_variant(int v) {
     g_sep_vec8 = v == 7;
     return HVR_OK;
   }
-  if (v >= 10 && v <= 14) {
+  if (v >= 10 && v <= 15) {
     g_sep_layout = v - 10;
     return HVR_OK;
   }
@@ -809,8 +810,11 @@ extern "C" int hvr_roi_align_fwd_fast(const float* feat, int feat_nhwc, const fl
                                  ? (size_t)n_rois * ld_split * 2 : (size_t)n_rois * ph * pw * C * 4;
     if (g_sep_layout >= 3 && 2 * ph <= 32 && out_bytes < ((size_t)1 << 31)) {
       const int o = (out ? 1 : 0) | (out_hi ? 2 : 0);
-      auto kern = g_sep_layout == 4 ? (o == 1 ? roi_align_sepp_kernel<1, true> : o == 2 ? roi_align_sepp_kernel<2, true> : roi_align_sepp_kernel<3, true>)
-                                    : (o == 1 ? roi_align_sepp_kernel<1, false> : o == 2 ? roi_align_sepp_kernel<2, false> : roi_align_sepp_kernel<3, false>);
+      // 4 resident CTAs per SM (72 registers) is the default: 551 us on the bench launch against 609 us with 3 (80 registers)
+      // and 630 us with 5 (56 registers, spills)
+      auto kern = g_sep_layout == 5 ? (o == 1 ? roi_align_sepp_kernel<1, false, 3> : o == 2 ? roi_align_sepp_kernel<2, false, 3> : roi_align_sepp_kernel<3, false, 3>) :
+                  g_sep_layout == 4 ? (o == 1 ? roi_align_sepp_kernel<1, true, 4> : o == 2 ? roi_align_sepp_kernel<2, true, 4> : roi_align_sepp_kernel<3, true, 4>)
+                                    : (o == 1 ? roi_align_sepp_kernel<1, false, 4> : o == 2 ? roi_align_sepp_kernel<2, false, 4> : roi_align_sepp_kernel<3, false, 4>);
       kern<<<n_rois, pw * 32, 0, st>>>(feat, rois, n_imgs, C, H, W, ph, pw, spatial_scale, out, (__nv_bfloat16*)out_hi,
                                        (__nv_bfloat16*)out_lo, ld_split);
     }

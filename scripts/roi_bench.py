@@ -22,8 +22,9 @@ for T, lo, hi in ((1, 16, 396), (15, 16, 396), (105, 16, 396), (105, 16, 112), (
     # separable FMA evaluation with one CTA per RoI / with CTA = (frame, 16-channel slab of the map in shared memory)
     for name, variant, arith in (("generic", 1, "strict"), ("sn2", 0, "strict"), ("fast_roi_cta_4ch", 6, "fast"),
                                  ("fast_roi_cta_8ch_adjacent", 107, "fast"), ("fast_roi_cta_8ch_interleaved", 117, "fast"),
-                                 ("fast_roi_cta_16ch_interleaved", 127, "fast"), ("fast_roi_cta_8ch_interleaved_row_program", 137, "fast"),
-                                 ("fast_roi_cta_8ch_interleaved_row_program_prefetch", 147, "fast"), ("fast_roi_cta_3ctas", 3, "fast"), ("fast_slab", 5, "fast")):
+                                 ("fast_roi_cta_16ch_interleaved", 127, "fast"), ("fast_roi_cta_8ch_interleaved_row_program [shipped]", 137, "fast"),
+                                 ("fast_roi_cta_8ch_interleaved_row_program_prefetch", 147, "fast"),
+                                 ("fast_roi_cta_8ch_interleaved_row_program_3ctas_80regs", 157, "fast"), ("fast_roi_cta_3ctas", 3, "fast"), ("fast_slab", 5, "fast")):
         _lib.lib().hvr_debug_roi_variant(0)
         _lib.lib().hvr_debug_roi_variant(2)
         _lib.lib().hvr_debug_roi_variant(8)

@@ -558,8 +558,8 @@ def test_roi_align_fast_variant_vs_strict(cuda, C, out_size):
         o_8, sp_8 = ops.roi_align(f, r, out_size=out_size, feat_nhwc=True, out_nhwc=True, want_split=True, arithmetic='fast')
         assert torch.equal(o_8.view(torch.int32), o.view(torch.int32)) and torch.equal(sp_8.lo.view(torch.int16), sp.lo.view(torch.int16))
         # the 8-channel kernel's variants at C = 256: 10 adjacent channels, 11 lane-interleaved, 12 = 16 per thread (all with the
-        # two-row-cache walk); 13 = lane-interleaved with the per-RoI row program (default, = o_8 above), 14 = 13 + L1 prefetch
-        for layout in (10, 11, 12, 14):
+        # two-row-cache walk); 13 = lane-interleaved with the per-RoI row program (default, = o_8 above), 14 = 13 + L1 prefetch, 15 = 13 built for 3 CTAs per SM
+        for layout in (10, 11, 12, 14, 15):
             _lib.lib().hvr_debug_roi_variant(layout)
             o_l, sp_l = ops.roi_align(f, r, out_size=out_size, feat_nhwc=True, out_nhwc=True, want_split=True, arithmetic='fast')
             assert torch.equal(o_l.view(torch.int32), o.view(torch.int32)) and torch.equal(sp_l.hi.view(torch.int16), sp.hi.view(torch.int16))

@@ -580,8 +580,9 @@ def main():
         if k_:
             hbm_peak, src = v_, 'MEASURED_PEAKS.json ' + k_
         gbs = nbytes / us / 1e3
-        out = {'bound': 'hbm', 'kernel': 'roi_align_sep8_kernel (one CTA per RoI, thread = output column x 8 channels, rows of the RoI '
-                                         'interpolated once along x with merged column taps, LDG.128 along C, FMA)', 'frames': Tn,
+        out = {'bound': 'hbm', 'kernel': 'roi_align_sepp_kernel (one CTA per RoI, thread = output column x 8 lane-interleaved channels, '
+                                         'per-RoI row program in shared memory, rows interpolated once along x with merged column taps, '
+                                         'coalesced LDG.128, FMA)', 'frames': Tn,
                'rois': Tn * 300, 'us_per_launch': us, 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                'frac': gbs / hbm_peak, 'peak_source': src, 'algorithmic_bytes': nbytes,
                'strict_twin': {'kernel': 'roi_align_sn2_kernel (bit-exact with the reference built -fmad=false)',

@@ -107,7 +107,13 @@ constexpr int IM_PH = 2 * IM_TH + 5, IM_PW = 2 * IM_TW + 5, IM_PS = IM_PW + 3;  
 __global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restrict__ img, int B, int H, int W, int OH,
                                                           int OW, __nv_bfloat16* __restrict__ hi,
                                                           __nv_bfloat16* __restrict__ lo) {
-  __shared__ float patch[3 * IM_PH * IM_PS];
+  __shared__ float patch[3 * IM_PH * IM_PS + 1];
+  __shared__ __align__(16) unsigned short ktab[192];     // column k = (r*7 + s)*3 + c -> offset of (c, r, s) inside the patch; padding -> the zero word
+  if (threadIdx.x < 192) {
+    const int k = threadIdx.x, c = k % 3, rs = k / 3;
+    ktab[k] = k < 147 ? (unsigned short)((c * IM_PH + rs / 7) * IM_PS + rs % 7) : (unsigned short)0xffff;
+  }
+  if (threadIdx.x == 255) patch[3 * IM_PH * IM_PS] = 0.f;
   const int ox0 = blockIdx.x * IM_TW, oy0 = blockIdx.y * IM_TH, b = blockIdx.z;
   const int ix0 = ox0 * 2 - 3, iy0 = oy0 * 2 - 3;
   for (int i = threadIdx.x; i < 3 * IM_PH * IM_PW; i += blockDim.x) {
@@ -125,18 +131,15 @@ __global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restric
     if (ox >= OW || oy >= OH) continue;
     const int base = (2 * py) * IM_PS + 2 * px;
     uint32_t hp[4], lp[4];
+    const uint4 tv = *reinterpret_cast<const uint4*>(ktab + g * 8);
+    const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
       unsigned short hs[2], ls[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int k = g * 8 + j + e;
-        float v = 0.f;
-        if (k < 147) {
-          const int c = k % 3, rs = k / 3;
-          const int sx = rs % 7, r = rs / 7;
-          v = patch[(c * IM_PH + r) * IM_PS + sx + base];
-        }
+        const int t = (int)((tw[j / 2] >> (16 * e)) & 0xffffu);
+        const float v = patch[t == 0xffff ? 3 * IM_PH * IM_PS : t + base];
         __nv_bfloat16 h, l;
         split2(v, h, l);
         hs[e] = __bfloat16_as_ushort(h);

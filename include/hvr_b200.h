@@ -170,7 +170,10 @@ int hvr_roi_align_fwd(const float* feat, int feat_nhwc, const float* rois, int n
  * 0 = heuristic (sample_num 2 + out_layout 1 run roi_align_sn2_kernel, which reuses taps held in registers);
  * 2 / 3 = resident CTAs per SM the fast RoI-per-CTA kernel below is compiled for (experiments);
  * 4 / 5 / 6 = fast path launch shape: heuristic / slab kernel whenever it applies / never the slab kernel;
- * 7 / 8 = fast RoI-per-CTA kernel with 8 / 4 channels per thread. */
+ * 7 / 8 = fast RoI-per-CTA kernel with 8 / 4 channels per thread;
+ * 10 .. 15 = the 8-channel kernel at C == 256: channels of a thread adjacent / lane-interleaved / 16 per thread (all with
+ * the two-row-cache walk) / lane-interleaved with the per-RoI row program (13, the default) / 13 + L1 prefetch /
+ * 13 built for 3 instead of 4 CTAs per SM.  Every variant of the fast path returns the same bits. */
 int hvr_debug_roi_variant(int v);
 /* Fast arithmetic for the pipeline (feat_nhwc = 1, out_layout = 1, sample_num = 2): the same average of
  * bilinear samples evaluated separably - every map row of the RoI is interpolated once along x with the
@@ -179,11 +182,11 @@ int hvr_debug_roi_variant(int v);
  * summation order differs, so values agree with hvr_roi_align_fwd to a few ulp of the largest term (1e-5
  * relative, the agreement between the reference's own default build, which nvcc contracts into FMAs, and its
  * -fmad=false build), not bit for bit.  Other argument combinations run the strict kernels.
- * Launch shapes: when a 16-channel slab of the whole map fits in shared memory (H*W*64 B <= 220 KB) and the launch
- * has at least one (frame, slab) pair per SM, CTA = (frame, slab): the slab is staged in shared memory once and all
- * RoIs of the frame are pooled from it (the L2 -> SM traffic falls from one patch per RoI to one pass over the
- * maps); otherwise one CTA per RoI.  ws: hvr_roi_align_fast_workspace_bytes(n_rois, n_imgs) bytes (the RoIs
- * bucketed by frame); with ws == NULL only the CTA-per-RoI shape is used. */
+ * Launch shape: one CTA per RoI (C == 256, ph <= 16, pw <= 7: roi_align_sepp_kernel - thread = output column x 8
+ * lane-interleaved channels walking a per-RoI row program; other C: roi_align_sep8_kernel / roi_align_sep_kernel).
+ * A second shape, CTA = (frame, 16-channel slab of the whole map staged in shared memory, H*W*64 B <= 220 KB), cuts the
+ * L2 -> SM traffic 9-fold but measured slower (instruction bound); it runs only under hvr_debug_roi_variant(5) and is the
+ * only user of ws: hvr_roi_align_fast_workspace_bytes(n_rois, n_imgs) bytes (the RoIs bucketed by frame); ws may be NULL. */
 size_t hvr_roi_align_fast_workspace_bytes(int n_rois, int n_imgs);
 int hvr_roi_align_fwd_fast(const float* feat, int feat_nhwc, const float* rois, int n_rois, int n_imgs,
                            int C, int H, int W, int ph, int pw, float spatial_scale, int sample_num,

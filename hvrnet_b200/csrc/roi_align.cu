@@ -437,10 +437,12 @@ __device__ __forceinline__ void roi_column_walk_prog(const RowStep* __restrict__
 template <int VEC, int ES>
 __device__ __noinline__ void sepp_hole_walk(float sh, float bh, int ph, int H, uint32_t row_pitch, const char* base, const ColTaps& ct,
                                             float* of, __nv_bfloat16* oh, __nv_bfloat16* ol, uint32_t step) {
-  __shared__ RowTap rows[32];
-  // every thread of a warp is here together (q is warp-uniform) but not every warp of the CTA: no CTA barrier; the
-  // writers store identical values
-  for (int s2 = 0; s2 < 2 * ph; ++s2) rows[s2] = row_tap_sn2(sh, bh, s2, H, row_pitch);
+  __shared__ RowTap rows_w[8][32];
+  // every thread of a warp is here together (q is warp-uniform) but not every warp of the CTA: no CTA barrier, a private
+  // table per warp (<= 7 warps: 224 threads), lane s computes sample s
+  RowTap* rows = rows_w[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  if (lane < 2 * ph) rows[lane] = row_tap_sn2(sh, bh, lane, H, row_pitch);
   __syncwarp();
   const char* const pc[4] = {base + ct.off[0], base + ct.off[1], base + ct.off[2], base + ct.off[3]};
   const float w[4] = {ct.w[0], ct.w[1], ct.w[2], ct.w[3]};

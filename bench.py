@@ -530,6 +530,15 @@ def main():
             fh.write('M,N,K,launches_per_step,ms_per_step,algorithmic_TFLOPs\n')
             for shp, (n_, t_, f_) in agg.items():
                 fh.write('%d,%d,%d,%.1f,%.4f,%.1f\n' % (shp[0], shp[1], shp[2], n_ / K, t_ / K, f_ / t_ / 1e9))
+        # the launches of the LAST profiled step in issue order: start offset from the step's first igemm launch, duration
+        per_step = len(prof) // K
+        last = prof[-per_step:]
+        with open(args.gemm_report.replace('.csv', '') + '_timeline.csv', 'w') as fh:
+            fh.write('launch,M,N,K,start_us,us,algorithmic_TFLOPs\n')
+            for i_, (e0_, e1_, f_, shp) in enumerate(last):
+                t_ = e0_.elapsed_time(e1_)
+                fh.write('%d,%d,%d,%d,%.1f,%.1f,%.1f\n' % (i_, shp[0], shp[1], shp[2], last[0][0].elapsed_time(e0_) * 1e3,
+                                                             t_ * 1e3, f_ / max(t_, 1e-6) / 1e9))
     peaks, peak_src = None, 'fallback (B200_PROFILING.md: 1590 TFLOP/s burst)'
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))

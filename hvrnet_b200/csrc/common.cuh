@@ -187,6 +187,49 @@ __device__ __forceinline__ uint32_t leader_addr(const void* p) { return smem_u32
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(bar)) : "memory");
 }
+// ---- cluster launch control (Blackwell): a running cluster cancels the launch of a not-yet-started cluster of its own
+// grid and processes that cluster's tile itself - a hardware work queue for persistent kernels.
+// arrive + expect_tx on the copy of `bar` in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_expect_tx_cta(uint64_t* bar, uint32_t bytes, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.expect_tx.shared::cluster.b64 _, [ra], %2;\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta), "r"(bytes)
+      : "memory");
+}
+// plain arrive on the copy of `bar` in CTA `cta`
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+// The 16-byte response lands at the same shared-memory offset in EVERY CTA of the cluster, each signalled through its own
+// copy of `bar` (complete_tx of 16 bytes).  One thread of the cluster issues it.
+__device__ __forceinline__ void clc_try_cancel(void* resp, uint64_t* bar) {
+  asm volatile(
+      "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+      ::"r"(smem_u32(resp)), "r"(smem_u32(bar))
+      : "memory");
+}
+// ctaid.x of the first CTA of the cancelled cluster, or -1 when nothing was left to cancel
+__device__ __forceinline__ int clc_query(const void* resp) {
+  uint32_t valid, x;
+  asm volatile(
+      "{\n\t.reg .pred p1;\n\t.reg .b128 r;\n\t.reg .b32 y, z, w;\n\t"
+      "mov.u32 %0, 0;\n\t"
+      "ld.shared.b128 r, [%2];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+      "selp.u32 %1, 1, 0, p1;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, y, z, w}, r;\n\t}"
+      : "=r"(x), "=r"(valid)
+      : "r"(smem_u32(resp))
+      : "memory");
+  return valid ? (int)x : -1;
+}
 __device__ __forceinline__ void tma2_load_2d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

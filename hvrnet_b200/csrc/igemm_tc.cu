@@ -54,6 +54,7 @@ struct alignas(64) KParams {
   int b_batched;                                 // B operand has its own matrix per image (3rd TMA coordinate)
   int passes;
   int pf;                                        // L2 prefetch distance of the A operand in K steps (0 = off)
+  int clc;                                       // pair kernel: tiles handed out by cluster launch control (grid = one cluster per tile)
   int relu;
   float alpha;
   const float* bias;
@@ -542,7 +543,7 @@ struct Cfg2 {
   static constexpr int EPI_WARP = DEEP ? DEEP_NBUF * DEEP_BUF_BYTES
                                        : (LEAN ? 2 * EPI_TILE_BYTES : EPI_WARP_BYTES);   // per lane quarter
   static constexpr int EPI_BYTES = 4 * EPI_WARP;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 512;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int THREADS = DEEP ? 320 : 192;                // 2 + 8 or 2 + 4 warps
 };
@@ -624,6 +625,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 1 ? 320 : 19
   constexpr int NRES = DEEP ? 4 * DEEP_NBUF : 4;     // residual TMA barriers: per lane quarter (x staging buffer)
   uint64_t* res_bar = tmem_empty_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + NRES);
+  // Tile sequence of this cluster.  Static (p.clc == 0): cluster c of G takes tiles c, c + G, ...  Dynamic (p.clc == 1):
+  // the grid has one cluster per tile; a running cluster starts with its own tile and then cancels the launch of
+  // pending clusters, taking their tiles (clusterlaunchcontrol).  Response j (the tile after this cluster's j-th one,
+  // j = 0, 1, ...) is requested by the leader's producer thread when it starts tile j, lands in slot j % CLC_NS of BOTH
+  // CTAs, and is read by every role (producer, MMA, epilogue warps) when it finishes tile j; the slot is reused once
+  // every reader of both CTAs has released it on the leader's clc_empty barrier.  A co-running kernel of another stream
+  // (proposal / detection branches) that holds an SM for a while then costs that SM's share of the tiles, not a stall of
+  // a fixed 1/74 of the tiles.
+  constexpr int CLC_NS = 4;
+  constexpr uint32_t CLC_READERS = 3 + 2 * (DEEP ? 8 : 4);     // leader: producer + MMA + epilogue warps; peer: producer + epilogue warps
+  uint8_t* clc_resp = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_ptr_smem + 1) + 15) & ~(uintptr_t)15);
+  uint64_t* clc_full = reinterpret_cast<uint64_t*>(clc_resp + 16 * CLC_NS);
+  uint64_t* clc_empty = clc_full + CLC_NS;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -636,6 +650,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 1 ? 320 : 19
   const int num_tiles = m_pairs * n_tiles;           // pair tiles
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
+  const bool clc = p.clc != 0;
+  // tile after this cluster's j-th tile `tile` (-1: none).  Idempotent until seq_release(j).
+  auto seq_get = [&](int j, int tile) -> int {
+    if (!clc) return tile + num_clusters < num_tiles ? tile + num_clusters : -1;
+    mbar_wait(&clc_full[j % CLC_NS], (uint32_t)((j / CLC_NS) & 1));
+    const int x = clc_query(clc_resp + 16 * (j % CLC_NS));
+    return x < 0 ? -1 : (x >> 1);
+  };
+  // one thread per reader (after every lane of the warp has read the response)
+  auto seq_release = [&](int j) {
+    if (clc) {
+      fence_proxy_async();                           // this read before the async-proxy write of a later response
+      mbar_arrive_cta(&clc_empty[j % CLC_NS], 0);
+    }
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA_hi);
@@ -651,6 +680,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 1 ? 320 : 19
       mbar_init(&tmem_empty_bar[b], DEEP ? 16 : 8);   // epilogue warps x 2 CTAs (used in the leader only)
     }
     for (int w = 0; w < NRES; ++w) mbar_init(&res_bar[w], 1);
+    for (int s = 0; s < CLC_NS; ++s) {
+      mbar_init(&clc_full[s], 1);
+      mbar_init(&clc_empty[s], CLC_READERS);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -694,8 +727,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 1 ? 320 : 19
         if (q_tile < num_tiles) q_decode();
         for (int i = 0; i < p.pf; ++i) q_step();
       }
-      int it = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int it = 0, tj = 0;
+      for (int tile = cluster_id; tile >= 0; tile = seq_get(tj, tile), seq_release(tj), ++tj) {
+        if (clc && leader) {                                  // ask for the tile after this one
+          const int s = tj % CLC_NS;
+          mbar_wait(&clc_empty[s], (uint32_t)(((tj / CLC_NS) & 1) ^ 1));
+          mbar_expect_tx_cta(&clc_full[s], 16u, 0u);
+          mbar_expect_tx_cta(&clc_full[s], 16u, 1u);
+          clc_try_cancel(clc_resp + 16 * s, &clc_full[s]);
+        }
         const int nt = tile % n_tiles;
         const MTile mt = pair_m_tile(p, tile / n_tiles, (int)rank);
         const int bimg = mt.bimg;                             // idle half of an odd pair: TMA zero-fills
@@ -738,7 +778,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 1 ? 320 : 19
     if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(BN, 256);
       int it = 0, lt = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
+      for (int tile = cluster_id; tile >= 0; ++lt) {
         const int ab = lt & 1;
         const uint32_t aph = (uint32_t)((lt >> 1) & 1);
         mbar_wait(&tmem_empty_bar[ab], aph ^ 1u);
@@ -767,6 +807,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 1 ? 320 : 19
           }
           __syncwarp();
         }
+        tile = seq_get(lt, tile);
+        __syncwarp();
+        if (lane == 0) seq_release(lt);
       }
     }
   } else {
@@ -786,7 +829,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 1 ? 320 : 19
       const int sw = lane & 7;
       const int qx = (q * 32) % p.tile_w, qy = (q * 32) / p.tile_w;
       // load cursor (issuer only): runs two chunks ahead of the consumer, across tile boundaries
-      int l_tile = cluster_id, l_c = 0, l_g = 0, l_n0 = 0, l_x = 0, l_y = 0, l_b = 0;
+      int l_tile = cluster_id, l_j = 0, l_c = 0, l_g = 0, l_n0 = 0, l_x = 0, l_y = 0, l_b = 0;
       auto load_tile = [&]() {
         const int nt = l_tile % n_tiles;
         const MTile mt = pair_m_tile(p, l_tile / n_tiles, (int)rank);
@@ -796,7 +839,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 1 ? 320 : 19
         l_b = mt.bimg;
       };
       auto issue_load = [&]() {
-        if (l_tile < num_tiles) {
+        if (l_tile >= 0) {
           uint8_t* dst = wbuf + (l_g % DEEP_NBUF) * DEEP_BUF_BYTES;
           uint64_t* bar = &rbar[l_g % DEEP_NBUF];
           mbar_expect_tx(bar, DEEP_BUF_BYTES);
@@ -806,18 +849,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 1 ? 320 : 19
           l_c += 64;
           if (l_c >= BN || l_n0 + l_c >= p.n) {
             l_c = 0;
-            l_tile += num_clusters;
-            if (l_tile < num_tiles) load_tile();
+            l_tile = seq_get(l_j, l_tile);             // read ahead of this warp's own release of response l_j
+            ++l_j;
+            if (l_tile >= 0) load_tile();
           }
         }
       };
       if (t_res && issuer) {
-        if (l_tile < num_tiles) load_tile();
+        load_tile();
         issue_load();
         issue_load();
       }
       int g = 0, lt = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
+      for (int tile = cluster_id; tile >= 0; ++lt) {
         const int nt = tile % n_tiles;
         const MTile mt = pair_m_tile(p, tile / n_tiles, (int)rank);
         const int tx = mt.tx, ty = mt.ty, bimg = mt.bimg;
@@ -866,6 +910,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 1 ? 320 : 19
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[ab]);
+        tile = seq_get(lt, tile);
+        __syncwarp();
+        if (lane == 0) seq_release(lt);
       }
       if (issuer) bulk_wait0();
     } else {
@@ -874,7 +921,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 1 ? 320 : 19
       const int m = q * 32 + lane;
       uint32_t res_phase = 0;
       int lt = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
+      for (int tile = cluster_id; tile >= 0; ++lt) {
         const int nt = tile % n_tiles;
         const MTile mt = pair_m_tile(p, tile / n_tiles, (int)rank);
         const int tx = mt.tx, ty = mt.ty, bimg = mt.bimg;
@@ -945,6 +992,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 1 ? 320 : 19
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[ab]);
+        tile = seq_get(lt, tile);
+        __syncwarp();
+        if (lane == 0) seq_release(lt);
       }
       if ((p.tma_epi & 1) && lane == 0) bulk_wait0();
       }
@@ -1107,6 +1157,7 @@ int g_deep_mode = 0;  // test hook: 0 = heuristic, 1 = deep epilogue wherever it
 bool g_lean = true;   // test hook (bit 17 of hvr_debug_force_bn's argument): false = never the lean variant
 int g_pf_mode = 0;    // test hook: 0 = heuristic, 1..14 = L2 prefetch distance in K steps, 15 = off
 bool g_tma_epilogue = true;   // test hook: bit 10 of hvr_debug_force_bn's argument selects the per-row epilogue
+bool g_clc = false;           // test hook: bit 18 of hvr_debug_force_bn's argument: pair kernels take their tiles by cluster launch control
 
 template <int BN>
 int launch(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
@@ -1175,7 +1226,9 @@ int launch2(const HvrIGemm* g, KParams& kp, cudaStream_t st) {
     HVR_CUDA(cudaGetDevice(&dev));
     HVR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const long long clusters = pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2;
+  kp.clc = g_clc && pair_tiles > num_sms / 2 ? 1 : 0;       // (a single wave has nothing to hand out)
+  if (kp.clc) kp.pf = 0;                                    // the L2 prefetch cursor follows the static sequence
+  const long long clusters = kp.clc ? pair_tiles : (pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(2 * clusters));
   cfg.blockDim = dim3(Cfg2<BN, MODE>::THREADS);
@@ -1341,7 +1394,8 @@ extern "C" int hvr_debug_force_bn(int bn) {
   g_deep_mode = (bn & 2048) ? 1 : ((bn & 4096) ? 2 : 0);   // bit 11: deep epilogue wherever it applies, bit 12: never
   g_pf_mode = (bn >> 13) & 15;                             // bits 13-16: L2 prefetch distance (15 = off, 0 = heuristic)
   g_lean = (bn & (1 << 17)) == 0;
-  bn &= ~(1024 | 2048 | 4096 | (15 << 13) | (1 << 17));
+  g_clc = (bn & (1 << 18)) != 0;
+  bn &= ~(1024 | 2048 | 4096 | (15 << 13) | (1 << 17) | (1 << 18));
   // 512 = CTA-pair kernel (256-wide tiles), 640 = CTA-pair kernel with 128-wide tiles
   if (bn != 0 && bn != 64 && bn != 128 && bn != 256 && bn != 512 && bn != 640) return HVR_ERR_ARG;
   g_force_bn = bn;

@@ -207,6 +207,46 @@ def test_igemm_deep_epilogue_bit_identical(cuda, M, K, N, use_res):
     assert _rel(ops.merge(Split(outs[0][0].contiguous(), outs[0][1].contiguous())).double().cpu(), ref) < 3e-5
 
 
+@pytest.mark.parametrize('M,K,N,use_res,f32,flag', [
+    (128 * 400 + 37, 256, 512, False, False, 0),       # lean pair kernel, 402 pair tiles for 74 clusters
+    (128 * 400 + 37, 256, 512, True, False, 0),        # deep epilogue: the residual cursor reads the next tile ahead
+    (128 * 400 + 37, 192, 520, True, True, 0),         # standard pair kernel (fp32 output), clipped N tile
+    (128 * 700 + 5, 64, 128, False, False, 640),       # 256 x 128 pair tiles, one K step per tile (producer far ahead)
+    (128 * 700 + 5, 64, 64, True, False, 512 | 2048),  # deep epilogue, ONE 64-column chunk per tile: cursor two tiles ahead
+    (128 * 150, 128, 256, False, False, 0),            # exactly one wave + 1: 75 pair tiles
+])
+def test_igemm_cluster_launch_control_bit_identical(cuda, M, K, N, use_res, f32, flag):
+    """Dynamic tile hand-out (bit 18 of the debug flags: grid = one cluster per pair tile, a running cluster cancels the
+    launch of pending clusters and takes their tiles) against the static round-robin sequence: the same bits, every
+    tile written exactly once (outputs are pre-filled with NaN)."""
+    from hvrnet_b200 import _lib, ops
+    from hvrnet_b200.ops import Split
+    g = torch.Generator().manual_seed(M + N + K)
+    a = ops.split(torch.randn(M, K, generator=g).to(cuda))
+    w = ops.split((torch.randn(ops.round_up(N, 64), K, generator=g) / math.sqrt(K)).to(cuda))
+    bias = torch.randn(ops.round_up(N, 64), generator=g).to(cuda)
+    res = ops.split(torch.randn(M, ops.round_up(N, 8), generator=g).to(cuda)) if use_res else None
+    outs = []
+    for clc in (0, 1 << 18, 1 << 18):
+        nan = torch.full((M, ops.round_up(N, 8)), float('nan'), device=cuda)
+        out = Split(nan.bfloat16(), nan.bfloat16())
+        _lib.lib().hvr_debug_force_bn(flag | clc)
+        try:
+            o, of, _ = ops.linear(a, w, N, bias=bias, relu=True, res=res, want_split=True, want_f32=f32, out=out)
+            torch.cuda.synchronize()
+        finally:
+            _lib.lib().hvr_debug_force_bn(0)
+        outs.append((o.hi[:, :N].clone(), o.lo[:, :N].clone(), of[:, :N].clone() if f32 else None))
+    assert not bool(torch.isnan(outs[0][0].float()).any())
+    for other in outs[1:]:
+        assert torch.equal(outs[0][0].view(torch.int16), other[0].view(torch.int16))
+        assert torch.equal(outs[0][1].view(torch.int16), other[1].view(torch.int16))
+        if f32:
+            assert torch.equal(outs[0][2], other[2])
+    ref = _ref_linear(a, w, N, bias, res, True, 1.0)
+    assert _rel(ops.merge(Split(outs[0][0].contiguous(), outs[0][1].contiguous())).double().cpu(), ref) < 3e-5
+
+
 @pytest.mark.parametrize('tile', [(16, 8), (8, 16), (32, 4), (64, 2), (128, 1)])
 def test_igemm_deep_epilogue_conv_tile_shapes(cuda, tile):
     """Deep epilogue on every pixel-box shape of the M tile: 1x1 conv + residual + ReLU on a map

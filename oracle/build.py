@@ -74,7 +74,7 @@ def ref_roi_so_path(fma=True):
     return p if os.path.exists(p) else None
 
 
-def build_ref_roi_align(force=False):
+def build_ref_roi_align(force=False, which=(True, False)):
     """Compiles the REFERENCE's own RoIAlign CUDA op (roi_align_cuda.cpp + roi_align_kernel.cu, unmodified,
     where they lie) for sm_100a into oracle/_ref/, twice: with nvcc's default floating-point contraction (what
     the reference's setup.py builds) and with -fmad=false (every product and sum rounded: the arithmetic
@@ -87,7 +87,7 @@ def build_ref_roi_align(force=False):
     os.environ.setdefault('TORCH_CUDA_ARCH_LIST', '10.0a')
     from torch.utils.cpp_extension import load
     shim = os.path.join(HERE, 'shim', 'ref_compat.h')
-    for fma in (True, False):
+    for fma in which:
         if ref_roi_so_path(fma) and not force:
             continue
         bd = os.path.join(REF_DIR, 'build_' + ROI_NAMES[fma])
@@ -161,3 +161,23 @@ if __name__ == '__main__':
     print(build_ref(force='--force' in sys.argv))
     print(build_ref_roi_align(force='--force' in sys.argv))
     print(build_ref_nms_cuda(force='--force' in sys.argv))
+
+
+def build_all_ref():
+    """Every missing oracle/_ref module, each in its own process, side by side: from an empty oracle/_ref the four
+    builds (g++ / nvcc over the torch headers) take about two minutes each.  No-op when they exist or when the
+    reference tree is absent."""
+    import sys
+    todo = []
+    if os.path.exists(REF_SRC) and not ref_so_path():
+        todo.append('build_ref()')
+    if all(os.path.exists(s_) for s_ in ROI_SRCS):
+        todo += ['build_ref_roi_align(which=(%s,))' % fma for fma in (True, False) if not ref_roi_so_path(fma)]
+    if all(os.path.exists(s_) for s_ in NMS_CUDA_SRCS) and not ref_nms_cuda_so_path():
+        todo.append('build_ref_nms_cuda()')
+    root = os.path.dirname(HERE)
+    procs = [subprocess.Popen([sys.executable, '-c', 'from oracle import build as b; b.%s' % call], cwd=root) for call in todo]
+    failed = [call for call, pr in zip(todo, procs) if pr.wait() != 0]
+    if failed:
+        raise RuntimeError('oracle/_ref: %s failed' % ', '.join(failed))
+

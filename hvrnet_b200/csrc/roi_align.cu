@@ -196,13 +196,14 @@ __global__ void __launch_bounds__(256, SN2_MIN_CTAS) roi_align_sn2_kernel(
 }
 
 // Fast variant of the pipeline's path (sample_num == 2, NHWC rows out): the separable evaluation of
-// roi_align_sep.cuh.  One CTA per RoI, thread = (output column q, 4-channel group); the 2*ph y samples of the
+// roi_align_sep.cuh.  (This first walk - two-row cache with tags - serves C != 256 and the bit-identity tests; the
+// pipeline's C == 256 launch runs the row-program walk further down, roi_align_sepp_kernel.)  One CTA per RoI, thread = (output column q, 4-channel group); the 2*ph y samples of the
 // RoI are computed once into shared memory, the <= 4 merged column taps of q live in registers; every thread
 // walks the RoI's rows top to bottom and writes its ph outputs.  All branches depend on the RoI only (rows)
 // or on q only (warp-uniform when C % 128 == 0).  Explicit fmaf: independent of this file's -fmad=false.
 // The walk of roi_align_sep.cuh::roi_column_sep_sn2 specialised for the device: the number of merged column taps NC
 // (1..4, uniform per warp) is compile-time, so a row interpolation is NC loads + 4*NC multiply-adds of straight-line
-// code on pre-added 64-bit column pointers; split stores are packed.  ncu of the first version (profiles/r02e_roi_align_ncu_summary.txt): the
+// code on pre-added 64-bit column pointers; split stores are packed.  ncu of the first version (profiles/r02_roi_align_summary.txt): the
 // kernel is instruction-issue bound - 1867 warp instructions per warp and RoI of which 289 are the multiply-adds -
 // not memory bound, so the instruction count is what this version attacks.  Same operations in the same order as
 // the generic core (the slab kernel, which still runs the core, is its bit-for-bit twin in the tests).
@@ -565,7 +566,8 @@ __global__ void __launch_bounds__(224, 3) roi_align_sep8i_kernel(
     long long ld_split) {
   roi_align_sep_body<2, 512>(feat, rois, n_imgs, C, H, W, ph, pw, scale, out, out_hi, out_lo, ld_split);
 }
-// the row-program walk, 8 lane-interleaved channels per thread (C == 256, 2 * ph <= 32)  [shipped: split rows only, PF]
+// the row-program walk, 8 lane-interleaved channels per thread (C == 256, 2 * ph <= 32).  The pipeline's launch is
+// <OUT = 2 (split rows), PF = false, MINB = 4>: 551 us on the bench launch; PF = true measured 710 us, MINB = 3 610 us.
 template <int OUT, bool PF, int MINB>
 __global__ void __launch_bounds__(224, MINB) roi_align_sepp_kernel(
     const float* __restrict__ feat, const float* __restrict__ rois, int n_imgs, int C, int H, int W, int ph, int pw,

@@ -283,7 +283,7 @@ class ClockSampler:
         return out
 
 
-def inter_video_block(args, dev, world, rank, dist, steps=4, warm=2):
+def inter_video_block(args, dev, world, rank, dist, steps=8, warm=None):
     """BASELINE.json configs[4]: `--inter-keys-per-gpu` key frames per rank, every key frame's stage 4 also attends to
     the key rows of 4 other key frames of the whole job (ring order).  Returns the block added to the JSON line."""
     from collections import deque
@@ -298,6 +298,12 @@ def inter_video_block(args, dev, world, rank, dist, steps=4, warm=2):
     frames = synth.make_frames(T + pool, seed=100 + rank)
     devV = [torch.cat([frames[(i + v) % (T + pool)][None] for v in range(V)]).to(dev) for i in range(T + pool)]
     model.enable_cuda_graphs(True)
+    # Warm-up = one full turn of the window deques after each capture: the per-step C4 copies handed to the caller come from
+    # torch's caching allocator, and the first pass after a capture (which takes its private pools out of the free memory)
+    # showed 50-120 ms host stalls inside those allocations for a few steps around the first turn-over
+    # (scripts/inter_step_times.py); afterwards the per-step times are flat.
+    warm = T + 3 if warm is None else warm
+    prefetch = os.environ.get('HVR_NO_PREFETCH') != '1'      # (experiments: the next step's trunk on the side stream on / off)
     dqs = [deque(maxlen=T) for _ in range(V)]
     for i in range(T):
         c4 = model(img=devV[i], img_meta=[metas[0]] * V, backbone_feat=True)[0]
@@ -308,7 +314,8 @@ def inter_video_block(args, dev, world, rank, dist, steps=4, warm=2):
         c4 = model(img=devV[T + i % pool], img_meta=[metas[0]] * V, backbone_feat=True)[0]
         # the next step's trunk runs on the side stream under this step's window graphs (as in the headline loop): it also
         # keeps the GPU busy while graph C waits for the slowest rank to reach the all-gather
-        model._runner.prefetch(devV[T + (i + 1) % pool])
+        if prefetch:
+            model._runner.prefetch(devV[T + (i + 1) % pool])
         for v, t in enumerate(GraphRunner.per_frame(c4)):
             dqs[v].append(t)
         return model.forward_feat_intervideo([list(d) for d in dqs], metas, n_support=4, rescale=True)
@@ -323,7 +330,7 @@ def inter_video_block(args, dev, world, rank, dist, steps=4, warm=2):
         e0.record()
         for i in range(steps):
             fn(warm + i)
-            extra.append(model._runner.last_all_gather_ms())   # events on the communication stream; the step has ended
+            extra.append(model._runner.last_all_gather_ms() or 0.0)   # events on the communication stream; the step has ended
         e1.record()
         torch.cuda.synchronize()
         dist.barrier()
@@ -333,7 +340,8 @@ def inter_video_block(args, dev, world, rank, dist, steps=4, warm=2):
     # effects between two large captures on one device showed up as +-10 %); the better of the two is reported.
     def step_intra(i):
         c4 = model(img=devV[T + i % pool], img_meta=[metas[0]] * V, backbone_feat=True)[0]
-        model._runner.prefetch(devV[T + (i + 1) % pool])
+        if prefetch:
+            model._runner.prefetch(devV[T + (i + 1) % pool])
         for v, t in enumerate(GraphRunner.per_frame(c4)):
             dqs[v].append(t)
         return model.forward_feat_batch([list(d) for d in dqs], metas, rescale=True)
@@ -347,13 +355,15 @@ def inter_video_block(args, dev, world, rank, dist, steps=4, warm=2):
     torch.cuda.synchronize()
     dist.barrier()
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dist.all_gather_into_tensor(c.recv_flat, c.state['st'].send)
-    a0.record()
-    for _ in range(reps):
+    ag_iso = 0.0
+    if world > 1:                                             # (world 1: scripts/inter_loss_1gpu.py, no collective)
         dist.all_gather_into_tensor(c.recv_flat, c.state['st'].send)
-    a1.record()
-    torch.cuda.synchronize()
-    ag_iso = a0.elapsed_time(a1) / reps
+        a0.record()
+        for _ in range(reps):
+            dist.all_gather_into_tensor(c.recv_flat, c.state['st'].send)
+        a1.record()
+        torch.cuda.synchronize()
+        ag_iso = a0.elapsed_time(a1) / reps
     t = torch.tensor([ms, max(ag), sum(ag) / len(ag), ms_intra, ag_iso], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ag_max, ag_mean, ms_intra, ag_iso = [float(x) for x in t.tolist()]
@@ -371,7 +381,7 @@ def inter_video_block(args, dev, world, rank, dist, steps=4, warm=2):
                                  'ms_per_step_before_and_after': [ms_intra_a / steps, ms_intra_b / steps],
                                  'note': 'forward_feat_batch on the same %d windows per rank (no inter-video stage)' % V},
             'loss_vs_intra_same_batch': 1.0 - fps / fps_intra,
-            'all_gather': {'ms_isolated': ag_iso, 'achieved_GBs_per_rank': recv_bytes / (ag_iso / 1e3) / 1e9,
+            'all_gather': {'ms_isolated': ag_iso, 'achieved_GBs_per_rank': recv_bytes / (ag_iso / 1e3) / 1e9 if ag_iso > 0 else 0.0,
                            'nvlink_reference_GBs': 770.0, 'bytes_sent_per_rank': send_bytes,
                            'bytes_received_per_rank': recv_bytes, 'share_of_step_isolated': ag_iso / (ms / steps),
                            'ms_in_step_mean': ag_mean, 'ms_in_step_max': ag_max,

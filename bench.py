@@ -298,10 +298,8 @@ def inter_video_block(args, dev, world, rank, dist, steps=8, warm=None):
     frames = synth.make_frames(T + pool, seed=100 + rank)
     devV = [torch.cat([frames[(i + v) % (T + pool)][None] for v in range(V)]).to(dev) for i in range(T + pool)]
     model.enable_cuda_graphs(True)
-    # Warm-up = one full turn of the window deques after each capture: the per-step C4 copies handed to the caller come from
-    # torch's caching allocator, and the first pass after a capture (which takes its private pools out of the free memory)
-    # showed 50-120 ms host stalls inside those allocations for a few steps around the first turn-over
-    # (scripts/inter_step_times.py); afterwards the per-step times are flat.
+    # Warm-up = one full turn of the window deques after each switch between the two captured paths (allocator steady
+    # state; DESIGN.md section 6 has the trace of what a shorter warm-up used to measure).
     warm = T + 3 if warm is None else warm
     prefetch = os.environ.get('HVR_NO_PREFETCH') != '1'      # (experiments: the next step's trunk on the side stream on / off)
     dqs = [deque(maxlen=T) for _ in range(V)]

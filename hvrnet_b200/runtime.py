@@ -13,6 +13,8 @@ max_num rows and its proposal count stays on the device as a mask (window.py), s
 whether or not a frame yields fewer proposals than max_num - there is no speculation and no eager failover.
 The inter-video split (configs 4-5) is three graphs around the one all-gather (``detect_inter``).
 """
+import weakref
+
 import torch
 
 from . import _lib, ops
@@ -35,7 +37,10 @@ class WindowRing:
 
     def __init__(self, n_videos, n_frames):
         self.V, self.T = n_videos, n_frames
-        self.slots = [[None] * n_frames for _ in range(n_videos)]   # slot -> (hi tensor, its version, lo's version)
+        # slot -> (weak reference to the frame's hi tensor, its version, lo's version).  Weak: a ring that is not being
+        # used (another window shape / the other execution path took over) must not keep the caller's dropped C4 maps
+        # alive - at 32 key frames per step that pinned 9 GB per idle ring and made the maps' memory pool grow.
+        self.slots = [[None] * n_frames for _ in range(n_videos)]
 
     def place(self, windows):
         """windows: V lists of T per-frame Splits.  Returns (copies, perm): copies = [(slot index into the
@@ -44,7 +49,11 @@ class WindowRing:
         copies, perm = [], []
         for v, w in enumerate(windows):
             sl = self.slots[v]
-            held = {id(q[0]): j for j, q in enumerate(sl) if q is not None}   # ids are unique while the refs are held
+            live = [(j, q[0]()) for j, q in enumerate(sl) if q is not None]
+            for j, obj in live:
+                if obj is None:
+                    sl[j] = None                                # the caller dropped that frame
+            held = {id(obj): j for j, obj in live if obj is not None}         # ids are unique while `live` holds the refs
             where = []
             for p in w:
                 j = held.get(id(p.hi))
@@ -59,7 +68,7 @@ class WindowRing:
                     if j is None:
                         j = next(j for j in range(T) if j not in used)
                         copies.append((v * T + j, p))
-                        sl[j] = (p.hi, p.hi._version, p.lo._version)
+                        sl[j] = (weakref.ref(p.hi), p.hi._version, p.lo._version)
                         used.add(j)
                     where[t] = j
             perm += [v * T + j for j in where]
@@ -78,6 +87,7 @@ class GraphRunner:
         self._window = {}
         self.replayed_launches = 0      # kernels launched through graph replays (bench.py gpu_launches)
         self._copy_stream = None
+        self._out_pool = None           # torch.cuda.MemPool of the C4 copies handed to the caller (extract)
         self._staged = None             # (the prefetched tensor, trunk already run, ready event)
         self._version = model.weights_version()
 
@@ -171,8 +181,26 @@ class GraphRunner:
             self._replay(c)
         self.replayed_launches += c.launches
         s, nchw = c.outputs
-        out = nchw.clone()                              # the caller keeps C4 maps in its window deque
-        out._hvr_split = ops.Split(s.hi.clone(), s.lo.clone())
+        # The caller keeps C4 maps in its window deque, so every step hands out fresh copies.  They come from a memory
+        # pool of their own: in the general pool the blocks a dropped map returns are taken (and split) by other
+        # allocations after a new capture, the copies then fall through to cudaMalloc, and cudaMalloc blocks the host for
+        # 20-180 ms while persistent GEMM kernels own the GPU (scripts/inter_step_times.py).  In a private pool the
+        # T + 1 blocks of a window just rotate - ONE block per step (NCHW fp32 | hi | lo), so that every request is of
+        # the same size and finds the block the dropped map returned (three sizes in one pool split each other's blocks).
+        if self._out_pool is None:
+            self._out_pool = torch.cuda.MemPool()
+        nb_n, nb_s = nchw.numel() * 4, s.hi.numel() * 2
+        o1 = ops.round_up(nb_n, 256)
+        o2 = o1 + ops.round_up(nb_s, 256)
+        with torch.cuda.use_mem_pool(self._out_pool):
+            buf = torch.empty(o2 + nb_s, dtype=torch.uint8, device=nchw.device)
+        out = buf[:nb_n].view(torch.float32).view(nchw.shape)
+        hi = buf[o1:o1 + nb_s].view(torch.bfloat16).view(s.hi.shape)
+        lo = buf[o2:o2 + nb_s].view(torch.bfloat16).view(s.lo.shape)
+        out.copy_(nchw)
+        hi.copy_(s.hi)
+        lo.copy_(s.lo)
+        out._hvr_split = ops.Split(hi, lo)
         return (out,)
 
     @staticmethod

@@ -74,30 +74,38 @@ ext = []
 _r = model._runner
 
 
-def _timed_extract(img):                                      # GraphRunner.extract with host timers (trunk graph exists)
-    from hvrnet_b200 import ops
+_orig_extract = _r.extract
+_orig_empty = torch.empty
+_orig_copy = torch.Tensor.copy_
+fine = {}
+
+
+def _empty(*a, **k):                                          # host time and cudaMalloc count of every torch.empty inside extract
+    n0 = torch.cuda.memory_stats()['segment.all.allocated']
     t0 = time.perf_counter()
-    _r._check_weights()
-    t1 = time.perf_counter()
-    c = _r._trunk[tuple(img.shape)]
-    staged, _r._staged = _r._staged, None
-    if staged is not None:
-        torch.cuda.current_stream().wait_event(staged[2])
-    t2 = time.perf_counter()
-    if staged is not None and staged[0] is img:
-        if not staged[1]:
-            _r._replay(c)
-    else:
-        c.inputs.copy_(img, non_blocking=True)
-        _r._replay(c)
-    t3 = time.perf_counter()
-    s_, nchw = c.outputs
-    out = nchw.clone()
-    t4 = time.perf_counter()
-    out._hvr_split = ops.Split(s_.hi.clone(), s_.lo.clone())
-    t5 = time.perf_counter()
-    ext.append(tuple(round((b - a) * 1e3, 1) for a, b in ((t0, t1), (t1, t2), (t2, t3), (t3, t4), (t4, t5))))
-    return (out,)
+    r = _orig_empty(*a, **k)
+    fine['empty_ms'] = fine.get('empty_ms', 0.0) + (time.perf_counter() - t0) * 1e3
+    fine['cudaMalloc'] = fine.get('cudaMalloc', 0) + torch.cuda.memory_stats()['segment.all.allocated'] - n0
+    return r
+
+
+def _copy(self, *a, **k):
+    t0 = time.perf_counter()
+    r = _orig_copy(self, *a, **k)
+    fine.setdefault('copy_ms', []).append(round((time.perf_counter() - t0) * 1e3, 1))
+    return r
+
+
+def _timed_extract(img):                                      # GraphRunner.extract under host timers
+    fine.clear()
+    torch.empty, torch.Tensor.copy_ = _empty, _copy
+    t0 = time.perf_counter()
+    try:
+        out = _orig_extract(img)
+    finally:
+        torch.empty, torch.Tensor.copy_ = _orig_empty, _orig_copy
+    ext.append((round((time.perf_counter() - t0) * 1e3, 1), dict(fine)))
+    return out
 
 
 _r.extract = _timed_extract
@@ -125,7 +133,7 @@ for inter in (False, True, False, True):
     per = len(trace) // steps
     slow = [i for i, t in enumerate(ts) if t > 1.15 * sorted(ts)[len(ts) // 2]]
     for i in slow[:4] + [steps - 1]:
-        print('   step %d host phases (trunk pick-up, prefetch, lists, window call) ms: %s; inside pick-up (check_weights, wait_event, replay, clone nchw, clone split): %s' % (i, phases[i], ext[i]))
+        print('   step %d host phases (trunk pick-up, prefetch, lists, window call) ms: %s; GraphRunner.extract: %s ms' % (i, phases[i], ext[i]))
         print('   step %d: %.0f ms device, %.0f ms host call; graph replays (launches: ms): %s' % (
             i, ts[i], host[i], ', '.join('%d: %.1f (host %.1f)' % (n, a.elapsed_time(b), h) for a, b, n, h in trace[i * per:(i + 1) * per])))
 

@@ -409,6 +409,17 @@ def test_window_ring_bookkeeping():
     # a caller that rebuilds its tensors every call just gets every frame copied (correct, only slower)
     copies, perm = ring.place([[frame(7) for _ in range(T)] for _ in range(V)])
     assert len(copies) == V * T and sorted(perm) == list(range(V * T))
+    # the ring does not keep dropped frames alive (an idle ring would pin the caller's C4 maps): weak references
+    import gc
+    import weakref
+    f = frame(9)
+    w = weakref.ref(f.hi)
+    ring.place([[f] * T for _ in range(V)])
+    del f
+    gc.collect()
+    assert w() is None
+    copies, perm = ring.place([[frame(9)] * T for _ in range(V)])       # a new tensor (possibly at the same id): copied again
+    assert len(copies) == V
 
 
 def test_bench_keeps_native_prints_off_stdout():

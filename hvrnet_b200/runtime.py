@@ -193,10 +193,10 @@ class GraphRunner:
         o1 = ops.round_up(nb_n, 256)
         o2 = o1 + ops.round_up(nb_s, 256)
         with torch.cuda.use_mem_pool(self._out_pool):
-            buf = torch.empty(o2 + nb_s, dtype=torch.uint8, device=nchw.device)
-        out = buf[:nb_n].view(torch.float32).view(nchw.shape)
-        hi = buf[o1:o1 + nb_s].view(torch.bfloat16).view(s.hi.shape)
-        lo = buf[o2:o2 + nb_s].view(torch.bfloat16).view(s.lo.shape)
+            blk = torch.empty(o2 + nb_s, dtype=torch.uint8, device=nchw.device)   # (not `buf`: fn() above closes over that name)
+        out = blk[:nb_n].view(torch.float32).view(nchw.shape)
+        hi = blk[o1:o1 + nb_s].view(torch.bfloat16).view(s.hi.shape)
+        lo = blk[o2:o2 + nb_s].view(torch.bfloat16).view(s.lo.shape)
         out.copy_(nchw)
         hi.copy_(s.hi)
         lo.copy_(s.lo)

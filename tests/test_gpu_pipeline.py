@@ -554,6 +554,34 @@ def test_full_size_hrnmp_window_T15(cuda):
         assert tot == 0 or hit / tot >= 0.96, (hit, tot)                    # measured: 0.967-1.0 (test_index_parity)
 
 
+def test_runner_eager_reissue_mode_matches_graphs(world):
+    """enable_cuda_graphs(True, capture=False) - the runner's closures re-issued eagerly every call (bench.py's roofline
+    leg brackets the individual launches this way) - over several steps: the same C4 bits and detections as the captured
+    graphs.  (The closures are called again on LATER steps in this mode, so nothing they close over may be rebound.)"""
+    import numpy as np
+    m, dev = world['model'], world['dev']
+    frames = world['frames'].to(dev)
+    outs = {}
+    for capture in (True, False):
+        m.enable_cuda_graphs(True, capture=capture)
+        try:
+            res = []
+            for rep in range(3):
+                c4 = [m(img=frames[(i + rep) % 3:(i + rep) % 3 + 1], img_meta=[world['metas'][i]], backbone_feat=True)[0]
+                      for i in range(3)]
+                det = m(x=c4, img=None, img_meta=world['metas'], forward_feat=True, return_loss=False, rescale=True)
+                res.append(([t.clone() for t in c4], det))
+            outs[capture] = res
+        finally:
+            m.enable_cuda_graphs(False)
+    for (c4g, dg), (c4e, de) in zip(outs[True], outs[False]):
+        for a, b in zip(c4g, c4e):
+            assert torch.equal(a, b)
+        for o in range(2):
+            for c in range(30):
+                assert np.array_equal(dg[o][c], de[o][c])
+
+
 def test_prefetch_pipelining_same_results(world):
     """GraphRunner.prefetch (next step's H2D + trunk on a side stream, overlapping the current window
     graph) hands extract() the same C4 bits as the in-line path, from pinned host or device frames."""

@@ -75,6 +75,35 @@ class WindowRing:
         return copies, perm
 
 
+class _BlockPool:
+    """Recycles the device blocks of the per-step C4 copies `extract` hands to the caller.  Taken from torch's general
+    caching allocator, the blocks a dropped map returns are split by other allocations after a new capture, the next
+    copy then falls through to cudaMalloc, and cudaMalloc blocks the host for 8-180 ms while persistent GEMM kernels
+    own the GPU (scripts/inter_step_times.py).  A block is free again when nothing but the pool
+    references its storage - the caller's per-frame views keep the storage, not the tensor object, alive, hence the
+    storage use count.  (A torch.cuda.MemPool would do the same, but its destructor frees device memory, and the cyclic
+    garbage collector may run it in the middle of a later stream capture, which aborts the process.)"""
+
+    def __init__(self):
+        self.blocks = {}                                  # (bytes, device) -> [uint8 tensors]
+        self._count = getattr(torch._C, '_storage_Use_Count', None)
+        self.idle = self._use(torch.empty(8, dtype=torch.uint8)) if self._count is not None else 0
+
+    def _use(self, t):
+        return self._count(t.untyped_storage()._cdata)
+
+    def get(self, nbytes, device):
+        if self._count is None:                           # no way to tell when a block is free: plain allocation
+            return torch.empty(nbytes, dtype=torch.uint8, device=device)
+        lst = self.blocks.setdefault((nbytes, str(device)), [])
+        for b in lst:
+            if self._use(b) <= self.idle:
+                return b
+        b = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        lst.append(b)
+        return b
+
+
 class GraphRunner:
 
     def __init__(self, model, capture=True):
@@ -87,7 +116,7 @@ class GraphRunner:
         self._window = {}
         self.replayed_launches = 0      # kernels launched through graph replays (bench.py gpu_launches)
         self._copy_stream = None
-        self._out_pool = None           # torch.cuda.MemPool of the C4 copies handed to the caller (extract)
+        self._out_pool = _BlockPool()   # memory of the C4 copies handed to the caller (extract)
         self._staged = None             # (the prefetched tensor, trunk already run, ready event)
         self._version = model.weights_version()
 
@@ -181,19 +210,13 @@ class GraphRunner:
             self._replay(c)
         self.replayed_launches += c.launches
         s, nchw = c.outputs
-        # The caller keeps C4 maps in its window deque, so every step hands out fresh copies.  They come from a memory
-        # pool of their own: in the general pool the blocks a dropped map returns are taken (and split) by other
-        # allocations after a new capture, the copies then fall through to cudaMalloc, and cudaMalloc blocks the host for
-        # 20-180 ms while persistent GEMM kernels own the GPU (scripts/inter_step_times.py).  In a private pool the
-        # T + 1 blocks of a window just rotate - ONE block per step (NCHW fp32 | hi | lo), so that every request is of
-        # the same size and finds the block the dropped map returned (three sizes in one pool split each other's blocks).
-        if self._out_pool is None:
-            self._out_pool = torch.cuda.MemPool()
+        # The caller keeps C4 maps in its window deque, so every step hands out fresh copies: ONE block per step
+        # (NCHW fp32 | hi | lo) out of the runner's own block pool (see _BlockPool), where the T + 1 blocks of a window
+        # just rotate.
         nb_n, nb_s = nchw.numel() * 4, s.hi.numel() * 2
         o1 = ops.round_up(nb_n, 256)
         o2 = o1 + ops.round_up(nb_s, 256)
-        with torch.cuda.use_mem_pool(self._out_pool):
-            blk = torch.empty(o2 + nb_s, dtype=torch.uint8, device=nchw.device)   # (not `buf`: fn() above closes over that name)
+        blk = self._out_pool.get(o2 + nb_s, nchw.device)     # (not `buf`: fn() above closes over that name)
         out = blk[:nb_n].view(torch.float32).view(nchw.shape)
         hi = blk[o1:o1 + nb_s].view(torch.bfloat16).view(s.hi.shape)
         lo = blk[o2:o2 + nb_s].view(torch.bfloat16).view(s.lo.shape)

@@ -422,6 +422,32 @@ def test_window_ring_bookkeeping():
     assert len(copies) == V
 
 
+def test_runner_block_pool_recycles_by_storage_use():
+    """runtime._BlockPool (memory of the C4 copies GraphRunner.extract hands out): a block is lent again only when no
+    view of its storage is alive any more - the caller keeps per-frame VIEWS, not the tensor the views were cut from."""
+    from hvrnet_b200.runtime import _BlockPool
+    pool = _BlockPool()
+
+    def lend():
+        blk = pool.get(4096, 'cpu')
+        out = blk[:1024].view(torch.float32).view(2, 128)
+        return [out[i:i + 1] for i in range(2)], blk.data_ptr()      # what a caller keeps: per-frame views only
+
+    held, ptrs = [], []
+    for _ in range(4):
+        v, p = lend()
+        held.append(v)
+        ptrs.append(p)
+    assert len(set(ptrs)) == 4 and len(pool.blocks[(4096, 'cpu')]) == 4
+    held[1] = None                                                    # the caller drops one map
+    v, p = lend()
+    assert p == ptrs[1] and len(pool.blocks[(4096, 'cpu')]) == 4      # its block comes back, nothing new is allocated
+    held[0][0] = None                                                 # one of two frame views dropped: still in use
+    v2, p2 = lend()
+    assert p2 not in ptrs and len(pool.blocks[(4096, 'cpu')]) == 5
+    assert pool.get(8192, 'cpu').numel() == 8192                      # sizes do not mix
+
+
 def test_bench_keeps_native_prints_off_stdout():
     """Multi-GPU bench: after bench._stdout_to_stderr() anything written to file descriptor 1 by native code
     (NCCL prints its version banner there) or by print() lands on stderr; only bench._emit() reaches the real

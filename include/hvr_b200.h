@@ -135,7 +135,11 @@ typedef struct HvrIGemm {
 
 /* tcgen05 / TMEM / TMA kernel.  rows = batch*out_h*out_w. */
 int hvr_igemm(const HvrIGemm* g, void* stream);
-/* Test hook: force the N tile width of hvr_igemm (64, 128, 256; 0 = heuristic). */
+/* Test hook (process-wide, not for production use): low bits = N tile width of hvr_igemm (64, 128, 256: single-CTA
+ * kernels; 512 / 640: CTA-pair kernel with 256 / 128-wide tiles; 0 = heuristic), OR-ed with: 1024 per-row instead of
+ * TMA epilogue, 2048 / 4096 deep epilogue always / never, bits 13-16 L2 prefetch distance (15 = off), 1 << 17 never
+ * the lean variant, 1 << 18 tiles handed out by cluster launch control instead of the static round-robin.  Every
+ * combination returns the same bits (tests/test_gpu_kernels.py).  HVR_DEBUG_FLAGS=<int> applies a value at first use. */
 int hvr_debug_force_bn(int bn);
 /* fp32 SIMT evaluation of the same descriptor (one thread per output, fmaf in k order):
  * the on-device cross-check used by the tests at sizes the CPU oracle cannot reach. */

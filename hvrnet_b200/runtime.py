@@ -84,8 +84,12 @@ class _BlockPool:
     storage use count.  (A torch.cuda.MemPool would do the same, but its destructor frees device memory, and the cyclic
     garbage collector may run it in the middle of a later stream capture, which aborts the process.)"""
 
+    STALE = 64                                            # requests after which an unused size gives its idle blocks back
+
     def __init__(self):
         self.blocks = {}                                  # (bytes, device) -> [uint8 tensors]
+        self._last = {}                                   # (bytes, device) -> request number of its last use
+        self._n = 0
         self._count = getattr(torch._C, '_storage_Use_Count', None)
         self.idle = self._use(torch.empty(8, dtype=torch.uint8)) if self._count is not None else 0
 
@@ -95,10 +99,18 @@ class _BlockPool:
     def get(self, nbytes, device):
         if self._count is None:                           # no way to tell when a block is free: plain allocation
             return torch.empty(nbytes, dtype=torch.uint8, device=device)
-        lst = self.blocks.setdefault((nbytes, str(device)), [])
+        key = (nbytes, str(device))
+        self._n += 1
+        self._last[key] = self._n
+        lst = self.blocks.setdefault(key, [])
         for b in lst:
             if self._use(b) <= self.idle:
                 return b
+        # growing: first give back what sizes that are no longer requested (another batch size, another input shape) hold
+        for k in [k for k, n in self._last.items() if self._n - n > self.STALE]:
+            self.blocks[k] = [b for b in self.blocks[k] if self._use(b) > self.idle]
+            if not self.blocks[k]:
+                del self.blocks[k], self._last[k]
         b = torch.empty(nbytes, dtype=torch.uint8, device=device)
         lst.append(b)
         return b

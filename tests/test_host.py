@@ -446,6 +446,13 @@ def test_runner_block_pool_recycles_by_storage_use():
     v2, p2 = lend()
     assert p2 not in ptrs and len(pool.blocks[(4096, 'cpu')]) == 5
     assert pool.get(8192, 'cpu').numel() == 8192                      # sizes do not mix
+    # a size that is no longer requested gives its idle blocks back once another size has to grow
+    del held, v, v2
+    keep = []
+    for _ in range(pool.STALE + 2):
+        b = pool.get(8192, 'cpu')
+        keep.append(b[:8])                                            # every block stays in use: the 8192 list grows
+    assert (4096, 'cpu') not in pool.blocks and len(pool.blocks[(8192, 'cpu')]) >= pool.STALE
 
 
 def test_bench_keeps_native_prints_off_stdout():

@@ -448,7 +448,8 @@ __device__ __noinline__ void sepp_hole_walk(float sh, float bh, int ph, int H, u
   const char* const pc[4] = {base + ct.off[0], base + ct.off[1], base + ct.off[2], base + ct.off[3]};
   const float w[4] = {ct.w[0], ct.w[1], ct.w[2], ct.w[3]};
   if (ct.n == 2) roi_column_walk<2, VEC, ES>(rows, ph, pc, w, of, oh, ol, step);
-  else roi_column_walk<3, VEC, ES>(rows, ph, pc, w, of, oh, ol, step);
+  else if (ct.n == 3) roi_column_walk<3, VEC, ES>(rows, ph, pc, w, of, oh, ol, step);
+  else roi_column_walk<4, VEC, ES>(rows, ph, pc, w, of, oh, ol, step);
 }
 
 template <int VEC, int ES, int OUT, bool PF>
@@ -481,9 +482,10 @@ __device__ __forceinline__ void roi_align_sepp_body(
         case 3: roi_column_walk_prog<3, VEC, ES, CP, false, OUT, PF>(prog, ph, pa, nullptr, w, out, out_hi, out_lo, o_f32, o_split, step); break;
         default: roi_column_walk_prog<4, VEC, ES, CP, false, OUT, PF>(prog, ph, pa, nullptr, w, out, out_hi, out_lo, o_f32, o_split, step); break;
       }
-    } else if (ct.n == 4) {                           // columns a, a+1, b, b+1 (bins wider than 4 columns)
+    } else if (ct.n == 4 && ct.off[1] == ct.off[0] + (uint32_t)CP && ct.off[3] == ct.off[2] + (uint32_t)CP) {
+      // columns a, a+1, b, b+1 (bins wider than 4 columns; the only way col_taps_sn2 produces four taps with a hole)
       roi_column_walk_prog<4, VEC, ES, CP, true, OUT, PF>(prog, ph, pa, base + ct.off[2], w, out, out_hi, out_lo, o_f32, o_split, step);
-    } else {                                          // 2 or 3 taps with a hole (a sample exactly on a column): the generic walk
+    } else {                                          // any other tap set with a hole (a sample exactly on a column): the generic walk
       sepp_hole_walk<VEC, ES>(g.sh, g.bh, ph, H, (uint32_t)(W * C) * 4u, base, ct, (OUT & 1) ? out + o_f32 : nullptr,
                               (OUT & 2) ? out_hi + o_split : nullptr, (OUT & 2) ? out_lo + o_split : nullptr, step);
     }
